@@ -1,0 +1,127 @@
+// simlod_b200.h — C ABI of the B200-native SimLOD hot path.
+//
+// The reference has no C library boundary: its host (modules/progressive_octree/
+// main_progressive_octree.cpp) compiles three CUDA programs at run time through
+// CudaModularProgram (include/CudaModularProgram.h:140-264) and launches the kernels they export
+// with cuLaunchCooperativeKernel. This header is that launch surface restated headless (no
+// OpenGL window, no loader threads): each entry point names the reference function it replaces.
+// Plain pointers and sizes only; no C++ or torch types cross the boundary.
+//
+// The kernels themselves (kernel_construct, kernel_render, kernel) keep the reference's names and
+// argument lists, so a cubin built from simlod_b200/csrc can equally be loaded by the reference's
+// own host through its kernels[name] map.
+#pragma once
+#include <stdint.h>
+#include "simlod_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct SimlodContext SimlodContext;
+
+enum {
+    SIMLOD_OK                = 0,
+    SIMLOD_ERR_CUDA          = -1,   // a CUDA driver call failed; see simlod_last_error()
+    SIMLOD_ERR_INVALID       = -2,   // bad argument
+    SIMLOD_ERR_RING_FULL     = -3,   // all 50 ring slots hold unprocessed batches (back-pressure, main.cpp:820,1012)
+    SIMLOD_ERR_MODULE        = -4,   // cubin could not be loaded or lacks the required kernel
+    SIMLOD_ERR_CAPACITY      = -5,   // persistent heap almost full: the device stopped consuming batches (Stats::memCapacityReached)
+};
+
+enum {  // the three CUDA programs of main_progressive_octree.cpp:603-626
+    SIMLOD_PROGRAM_CONSTRUCT = 0,    // exports kernel_construct
+    SIMLOD_PROGRAM_RENDER    = 1,    // exports kernel_render
+    SIMLOD_PROGRAM_RESET     = 2,    // exports kernel
+};
+
+typedef struct SimlodConfig {
+    int32_t  device;                  // CUDA ordinal (reference: always 0, main.cpp:274)
+    uint32_t width, height;           // render target; replaces the GL colour attachment (main.cpp:472-486)
+    uint64_t momentary_bytes;         // 0 -> 300 000 000 (main.cpp:554). The reference kernels need >= 408 800 192.
+    uint64_t nodes_bytes;             // 0 ->  40 000 000 (main.cpp:552-555)
+    uint64_t renderbuffer_bytes;      // 0 -> 200 000 000 (main.cpp:556)
+    uint64_t persistent_bytes;        // 0 -> 80 % of free device memory (main.cpp:584)
+    int32_t  construct_blocks_per_sm; // 0 -> occupancy query; 1 = the reference's launch shape (main.cpp:370-371)
+    int32_t  render_blocks_per_sm;    // 0 -> occupancy query (main.cpp:493-497)
+} SimlodConfig;
+
+// initCuda + initCudaProgram (main.cpp:272-281, 549-642): context, streams, events, all device
+// buffers, the three programs (built-in sm_100a cubins), and a surface-capable RGBA8 array.
+int  simlod_create(const SimlodConfig* config, SimlodContext** out);
+void simlod_destroy(SimlodContext* ctx);
+const char* simlod_last_error(void);
+
+// CudaModularProgram's module map / hot reload (CudaModularProgram.h:166-190,245-252): replace one
+// program by a cubin file that exports the same kernel name; NULL restores the built-in program.
+// This is how the tests run the reference's own kernels on the same buffers.
+int simlod_use_module(SimlodContext* ctx, int program, const char* cubin_path);
+
+// getUniforms (main.cpp:283-331). The caller fills camera matrices, box and settings; the
+// library overwrites width/height and the two buffer capacities with its own values.
+int simlod_set_uniforms(SimlodContext* ctx, const SimlodUniforms* uniforms);
+int simlod_get_uniforms(SimlodContext* ctx, SimlodUniforms* out);
+
+// resetCUDA (main.cpp:333-361). Also clears nodes[] first (the reference relies on a zeroed allocation).
+int simlod_reset(SimlodContext* ctx);
+
+// spawnUploader's inner step (main.cpp:1033-1056): copy one batch (<= 1 000 000 points) into ring
+// slot (uploaded % 50) on the upload stream, then publish batchSizes[slot] and numBatchesUploaded.
+// Asynchronous when `points` is page-locked. SIMLOD_ERR_RING_FULL if 50 batches are pending.
+int simlod_upload_batch(SimlodContext* ctx, const SimlodPoint* host_points, uint32_t count);
+// same, source already in device memory (device-to-device copy)
+int simlod_upload_batch_device(SimlodContext* ctx, uint64_t device_points, uint32_t count);
+
+// updateOctree (main.cpp:364-428): ONE cooperative launch of kernel_construct, timed with an event
+// pair as the reference does (main.cpp:394,408-421). Consumes up to 20 uploaded batches or 10 ms.
+// Blocks until the launch has finished; *kernel_ms (optional) receives the event time.
+int simlod_update_octree(SimlodContext* ctx, float* kernel_ms);
+
+// The main loop's streaming behaviour (main.cpp:1176-1180 + uploader thread) for a point set in
+// host memory: uploads in 1 000 000-point batches overlapped with update launches until every
+// point is inserted. *kernel_ms (optional) = sum of kernel_construct event times.
+int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t count, float* kernel_ms);
+// same with the whole point set resident in device memory (batches are copied device-to-device)
+int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms);
+
+// renderCUDA (main.cpp:465-546): one cooperative launch of kernel_render into the surface.
+int simlod_render(SimlodContext* ctx, float* kernel_ms);
+
+// Stats read-back (main.cpp:1201-1216)
+int simlod_get_stats(SimlodContext* ctx, SimlodStats* out);
+// packed depth|colour framebuffer, width*height u64 (render buffer byte 31 200 144, render.cu:1122-1123)
+int simlod_read_framebuffer(SimlodContext* ctx, uint64_t* out);
+// RGBA8 surface written by kernel_render, width*height u32 (what the reference displays)
+int simlod_read_surface(SimlodContext* ctx, uint32_t* out);
+
+// Raw access for tests and tools: device addresses and sizes of the buffers the kernels share
+// (nodes[], persistent heap, momentary buffer, render buffer, point ring) and a bounded copy.
+typedef struct SimlodBuffers {
+    uint64_t nodes, nodes_bytes;
+    uint64_t persistent, persistent_bytes;
+    uint64_t momentary, momentary_bytes;
+    uint64_t renderbuffer, renderbuffer_bytes;
+    uint64_t ring, ring_bytes;
+    uint64_t stats;
+} SimlodBuffers;
+int simlod_get_buffers(SimlodContext* ctx, SimlodBuffers* out);
+int simlod_memcpy_dtoh(SimlodContext* ctx, void* dst, uint64_t src_device, uint64_t bytes);
+int simlod_memcpy_htod(SimlodContext* ctx, uint64_t dst_device, const void* src, uint64_t bytes);
+
+// pinned host memory (the reference's pinned pool, main.cpp:141-222) and plain device memory
+int simlod_host_alloc(SimlodContext* ctx, uint64_t bytes, void** out);
+int simlod_host_free(SimlodContext* ctx, void* ptr);
+int simlod_device_alloc(SimlodContext* ctx, uint64_t bytes, uint64_t* out);
+int simlod_device_free(SimlodContext* ctx, uint64_t ptr);
+
+// launch bookkeeping: kernels launched by this context so far, and the grid sizes in use
+int simlod_get_launch_info(SimlodContext* ctx, uint64_t* launches, uint32_t* construct_blocks, uint32_t* render_blocks, uint32_t* num_sms);
+// MUFU.RCP(x) as the device computes it (the one float a CPU restatement cannot derive when the
+// octree cube size is not a power of two; see oracle/)
+int simlod_device_rcp(SimlodContext* ctx, float x, float* out);
+// flush the L2 cache by overwriting a scratch buffer larger than it (bench hygiene)
+int simlod_flush_l2(SimlodContext* ctx);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,726 @@
+// construct.cu — incremental octree/LOD builder for sm_100a (B200).
+//
+// Drop-in for the reference's `kernel_construct`
+// (modules/progressive_octree/progressive_octree_voxels.cu:804-1010): same extern "C"
+// name, same argument list, same Node/Chunk/OccupancyGrid/Stats contents afterwards
+// (canonical form: DESIGN.md §3), launched cooperatively with 256-thread blocks by
+// updateOctree() (main_progressive_octree.cpp:364-428). It is NOT a translation of that
+// kernel; what is preserved is the observable state, what is new is how it is computed:
+//
+//   reference                                           here
+//   ------------------------------------------------    ------------------------------------------
+//   3 full passes over the batch (count, voxel-         1 streaming pass (count + voxel-sample fused),
+//   sample, insert), each re-descending the tree        leaf id + slot cached per point (8 B), 1 insert pass
+//   via 64-byte children[] pointer arrays               descent through a 4 B/node first-child table
+//   contiguous-per-thread ranges (uncoalesced)          grid-stride 128-bit coalesced loads
+//   atomicAdd(numPoints) per point at insert            slot = warp-aggregated counter add (no atomics at insert)
+//   chunk lists walked i/1000 hops per point/voxel      per-batch chunk directory: O(1) address per element
+//   one thread walks/extends each node's list           tail pointers kept per node; only dirty nodes visited
+//   1 global atomic per created voxel (backlog)         one atomic per warp per level (ballot-aggregated)
+//   >= 24 grid-wide barriers per batch                  5 (+4 per split round)
+//
+// The scratch ("momentary") buffer is carved with our own layout (Scratch below); it fits in
+// the 300 000 000 bytes the unmodified host allocates (main_progressive_octree.cpp:554),
+// unlike the reference's carve-out which needs 408 800 192 (voxels.cu:834-856).
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include "../../include/simlod_abi.h"
+#include "fpmath.cuh"
+
+namespace cg = cooperative_groups;
+
+typedef SimlodPoint Point;
+typedef SimlodChunk Chunk;
+typedef SimlodNode Node;
+typedef SimlodStats Stats;
+typedef SimlodUniforms Uniforms;
+typedef SimlodHeapHeader Heap;
+struct CudaPrint;   // opaque: the reference's debug channel is a dead parameter (CudaPrint.cuh:51)
+
+// ------------------------------------------------------------------------------------------
+// scratch layout inside the momentary buffer (all offsets 256-byte aligned)
+// ------------------------------------------------------------------------------------------
+namespace scratch {
+constexpr uint64_t NODE_CAP       = 263168;            // >= floor(40 000 000 / 152) nodes the host allocates
+constexpr uint64_t MAX_BATCH      = SIMLOD_MAX_BATCH_SIZE;
+constexpr uint64_t SPILL_CAP      = 3ull << 20;        // spilled points per batch (reference re-inserts <= 3 000 001)
+constexpr uint64_t ITEM_CAP       = MAX_BATCH + SPILL_CAP;
+constexpr uint64_t VOXEL_CAP      = 8ull << 20;        // voxels created per batch (reference backlog: 10 M)
+constexpr uint64_t DIR_CAP        = 1ull << 20;        // chunk directory entries per batch
+constexpr uint64_t QUEUE_CAP      = 4ull << 20;        // free-chunk stack (reference: 1 M)
+constexpr uint64_t SPILLNODE_CAP  = 100000;            // voxels.cu:847
+
+constexpr uint64_t align256(uint64_t x) { return (x + 255) & ~255ull; }
+constexpr uint64_t OFF_CTL        = 0;
+constexpr uint64_t OFF_FIRSTCHILD = 4096;
+constexpr uint64_t OFF_GRIDPTR    = align256(OFF_FIRSTCHILD + NODE_CAP * 4);
+constexpr uint64_t OFF_PTAIL      = align256(OFF_GRIDPTR + NODE_CAP * 8);
+constexpr uint64_t OFF_VTAIL      = align256(OFF_PTAIL + NODE_CAP * 8);
+constexpr uint64_t OFF_PDIR       = align256(OFF_VTAIL + NODE_CAP * 8);
+constexpr uint64_t OFF_VDIR       = align256(OFF_PDIR + NODE_CAP * 8);
+constexpr uint64_t OFF_DIRTYLEAF  = align256(OFF_VDIR + NODE_CAP * 8);
+constexpr uint64_t OFF_DIRTYVOX   = align256(OFF_DIRTYLEAF + NODE_CAP * 4);
+constexpr uint64_t OFF_SPILLNODES = align256(OFF_DIRTYVOX + NODE_CAP * 4);
+constexpr uint64_t OFF_CHUNKDIR   = align256(OFF_SPILLNODES + SPILLNODE_CAP * 4);
+constexpr uint64_t OFF_QUEUE      = align256(OFF_CHUNKDIR + DIR_CAP * 8);
+constexpr uint64_t OFF_LEAFOF     = align256(OFF_QUEUE + QUEUE_CAP * 8);
+constexpr uint64_t OFF_SLOTOF     = align256(OFF_LEAFOF + ITEM_CAP * 4);
+constexpr uint64_t OFF_SPILLED    = align256(OFF_SLOTOF + ITEM_CAP * 4);
+constexpr uint64_t OFF_VKEY       = align256(OFF_SPILLED + SPILL_CAP * 16);
+constexpr uint64_t OFF_VCOLOR     = align256(OFF_VKEY + VOXEL_CAP * 8);
+constexpr uint64_t TOTAL          = align256(OFF_VCOLOR + VOXEL_CAP * 4);
+static_assert(TOTAL <= 300000000ull, "scratch must fit the host's 300 MB momentary buffer (main.cpp:554)");
+}  // namespace scratch
+
+enum : uint32_t {   // Ctl::errorFlags, mirrored into Stats::dbg
+    ERR_SPILL_OVERFLOW  = 1u << 0,   // more than SPILL_CAP spilled points in one batch (reference-undefined regime)
+    ERR_VOXEL_OVERFLOW  = 1u << 1,   // more than VOXEL_CAP voxels created in one batch
+    ERR_DIR_OVERFLOW    = 1u << 2,
+    ERR_NODE_OVERFLOW   = 1u << 3,   // nodes[] capacity exceeded
+    ERR_QUEUE_OVERFLOW  = 1u << 4,
+    ERR_SPILLNODE_OVERFLOW = 1u << 5,
+};
+
+struct Ctl {
+    uint32_t numBatchesUploaded;   // snapshot of the volatile host-updated counter (voxels.cu:872-876)
+    uint32_t errorFlags;
+    uint64_t elapsedNanos;
+    uint32_t numSpillTotal;        // spilling nodes found so far in this batch (monotonic)
+    uint32_t numSpilled;           // spilled points in this batch
+    uint32_t numBacklog;           // voxels created in this batch
+    uint32_t numDirtyLeaves;
+    uint32_t numDirtyVox;
+    uint32_t dirCursor;
+    uint32_t workCounter;
+    uint32_t _pad;
+    uint32_t statCounters[8];
+};
+
+struct DirEntry { uint32_t base; uint32_t k0; };   // chunkDir[base + (slot/1000 - k0)] holds element `slot`
+
+struct Ctx {
+    Node*      nodes;
+    Stats*     stats;
+    Heap*      heap;
+    uint8_t*   heapBytes;
+    Ctl*       ctl;
+    uint32_t*  firstChild;    // node -> index of child 0 (children are 8 consecutive nodes); 0 = leaf
+    uint64_t*  gridPtr;       // node -> OccupancyGrid* (0 = none)
+    uint64_t*  pointTail;     // node -> last Chunk* of points list (valid iff node.points != 0)
+    uint64_t*  voxelTail;     // node -> last Chunk* of voxel list  (valid iff node.voxelChunks != 0)
+    DirEntry*  pointDir;
+    DirEntry*  voxelDir;
+    uint32_t*  dirtyLeaves;
+    uint32_t*  dirtyVox;
+    uint32_t*  spillingNodes;
+    uint64_t*  chunkDir;
+    uint64_t*  chunkQueue;
+    uint32_t*  leafOf;        // item -> leaf node | level << 24
+    uint32_t*  slotOf;        // item -> index inside the leaf
+    Point*     spilled;
+    uint64_t*  vkey;          // cell | node << 21 | slot << 41
+    uint32_t*  vcolor;
+    float minx, miny, minz, size, rcpSize;
+};
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ldv(const uint32_t* p) { return *(volatile const uint32_t*)p; }
+__device__ __forceinline__ uint64_t ldv(const uint64_t* p) { return *(volatile const uint64_t*)p; }
+__device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemaskLt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+__device__ __forceinline__ uint64_t globaltimer() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__device__ __forceinline__ uint4 ldPoint(const Point* p) {     // streaming 128-bit load
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stPoint(Point* p, uint4 v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct Coords { uint32_t X, Y, Z, pX, pY, pZ; };
+
+// voxels.cu:148-155 — X = u32(2^20 * (p - min) / size), pX = u32(2^28 * (p - min) / size)
+__device__ __forceinline__ Coords quantize(const Ctx& c, uint4 pt) {
+    float dx = fpx::add(__uint_as_float(pt.x), -c.minx);
+    float dy = fpx::add(__uint_as_float(pt.y), -c.miny);
+    float dz = fpx::add(__uint_as_float(pt.z), -c.minz);
+    Coords q;
+    q.X  = fpx::f2u(fpx::mul_ftz(fpx::mul(dx, 1048576.0f), c.rcpSize));
+    q.Y  = fpx::f2u(fpx::mul_ftz(fpx::mul(dy, 1048576.0f), c.rcpSize));
+    q.Z  = fpx::f2u(fpx::mul_ftz(fpx::mul(dz, 1048576.0f), c.rcpSize));
+    q.pX = fpx::f2u(fpx::mul_ftz(fpx::mul(dx, 268435456.0f), c.rcpSize));
+    q.pY = fpx::f2u(fpx::mul_ftz(fpx::mul(dy, 268435456.0f), c.rcpSize));
+    q.pZ = fpx::f2u(fpx::mul_ftz(fpx::mul(dz, 268435456.0f), c.rcpSize));
+    return q;
+}
+// voxels.cu:171-179
+__device__ __forceinline__ uint32_t childIndexAt(const Coords& q, uint32_t level) {
+    uint32_t sh = SIMLOD_MAX_DEPTH - 1 - level;
+    return (((q.X >> sh) & 1u) << 2) | (((q.Y >> sh) & 1u) << 1) | ((q.Z >> sh) & 1u);
+}
+// voxels.cu:78-88
+__device__ __forceinline__ uint32_t cellAt(const Coords& q, uint32_t level) {
+    uint32_t sh = SIMLOD_MAX_DEPTH + 1 - level;
+    uint32_t cx = (q.pX >> sh) & 127u, cy = (q.pY >> sh) & 127u, cz = (q.pZ >> sh) & 127u;
+    return cx | (cy << 7) | (cz << 14);
+}
+
+template <typename T>
+__device__ __forceinline__ T* carve(uint32_t* buffer, uint64_t off) { return reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(buffer) + off); }
+
+// ------------------------------------------------------------------------------------------
+// the per-point walk: descend from (node, level) to the leaf; optionally voxel-sample every
+// node on the way that owns an occupancy grid; optionally count the point into the leaf.
+// Warp-synchronous: all 32 lanes call it together, `valid` masks lanes without an item.
+//   count : voxels.cu:145-220 (doCounting::countPoint)     sample: voxels.cu:426-470 + 50-121
+// ------------------------------------------------------------------------------------------
+template <bool SAMPLE, bool COUNT>
+__device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_t node, uint32_t level,
+                                     uint32_t& leafPacked, uint32_t& slot) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = laneId();
+    const uint32_t ltmask = lanemaskLt();
+    Coords q = quantize(c, pt);
+    bool walking = valid;
+
+    while (__any_sync(FULL, walking)) {
+        if (walking && level >= SIMLOD_MAX_DEPTH) walking = false;     // voxels.cu:169 loop bound: level-20 node is the leaf
+        if (SAMPLE) {
+            bool won = false;
+            uint32_t cell = 0;
+            if (walking) {
+                uint64_t g = c.gridPtr[node];
+                if (g != 0) {
+                    cell = cellAt(q, level);
+                    uint32_t* word = reinterpret_cast<uint32_t*>(g) + (cell >> 5);
+                    uint32_t bit = 1u << (cell & 31u);
+                    uint32_t seen = *word;                               // non-atomic pre-test (voxels.cu:93-94)
+                    if ((seen & bit) == 0) {
+                        uint32_t old = atomicOr(word, bit);
+                        won = (old & bit) == 0;
+                    }
+                }
+            }
+            uint32_t winMask = __ballot_sync(FULL, won);
+            if (won) {
+                // numVoxels: one atomic per distinct node in the warp; backlog cursor: one per warp
+                uint32_t peers = __match_any_sync(winMask, node);
+                uint32_t leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (lane == leader) {
+                    base = atomicAdd(&c.nodes[node].numVoxels, (uint32_t)__popc(peers));
+                    if (base == ldv(&c.nodes[node].numVoxelsStored)) {   // first voxel of this node in this batch
+                        uint32_t d = atomicAdd(&c.ctl->numDirtyVox, 1u);
+                        c.dirtyVox[d] = node;
+                    }
+                }
+                base = __shfl_sync(peers, base, leader);
+                uint32_t vslot = base + __popc(peers & ltmask);
+                uint32_t wleader = __ffs(winMask) - 1;
+                uint32_t bbase = 0;
+                if (lane == wleader) bbase = atomicAdd(&c.ctl->numBacklog, (uint32_t)__popc(winMask));
+                bbase = __shfl_sync(winMask, bbase, wleader);
+                uint32_t b = bbase + __popc(winMask & ltmask);
+                if (b < scratch::VOXEL_CAP) {
+                    c.vkey[b] = (uint64_t)cell | ((uint64_t)node << 21) | ((uint64_t)vslot << 41);
+                    c.vcolor[b] = pt.w;
+                } else {
+                    atomicOr(&c.ctl->errorFlags, ERR_VOXEL_OVERFLOW);
+                }
+            }
+        }
+        if (walking) {
+            uint32_t fc = c.firstChild[node];
+            if (fc == 0) {
+                walking = false;
+            } else {
+                node = fc + childIndexAt(q, level);
+                level++;
+            }
+        }
+    }
+
+    leafPacked = node | (level << 24);
+    if (COUNT) {
+        uint32_t vmask = __ballot_sync(FULL, valid);
+        if (valid) {
+            // warp-aggregated leaf counter (voxels.cu:203-218)
+            uint32_t peers = __match_any_sync(vmask, node);
+            uint32_t leader = __ffs(peers) - 1;
+            uint32_t cnt = __popc(peers);
+            uint32_t old = 0;
+            if (lane == leader) {
+                Node* leaf = &c.nodes[node];
+                old = atomicAdd(&leaf->counter, cnt);
+                if (old == ldv(&leaf->numPoints)) {                      // first point of this leaf in this batch
+                    uint32_t d = atomicAdd(&c.ctl->numDirtyLeaves, 1u);
+                    c.dirtyLeaves[d] = node;
+                }
+                if (old <= SIMLOD_MAX_POINTS_PER_NODE && old + cnt > SIMLOD_MAX_POINTS_PER_NODE) {
+                    uint32_t s = atomicAdd(&c.ctl->numSpillTotal, 1u);
+                    if (s < scratch::SPILLNODE_CAP) c.spillingNodes[s] = node;
+                    else atomicOr(&c.ctl->errorFlags, ERR_SPILLNODE_OVERFLOW);
+                }
+            }
+            old = __shfl_sync(peers, old, leader);
+            slot = old + __popc(peers & ltmask);
+        }
+    }
+}
+
+// one pass over batch points (ring slot) followed by the spilled points of this batch
+//   FRESH  : items start at the root (first visit); otherwise only items whose cached leaf has
+//            been split since are walked on, starting at that (now inner) node
+template <bool SAMPLE, bool COUNT, bool FRESH>
+__device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, uint32_t numSpilled) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    // batch points
+    for (uint32_t base = tid - laneId(); base < numBatch; base += stride) {
+        uint32_t i = base + laneId();
+        bool valid = i < numBatch;
+        uint32_t node = 0, level = 0;
+        if (!FRESH && valid) {
+            uint32_t lp = c.leafOf[i];
+            node = lp & 0xffffffu; level = lp >> 24;
+            valid = c.firstChild[node] != 0 && level < SIMLOD_MAX_DEPTH;
+        }
+        uint4 pt = make_uint4(0, 0, 0, 0);
+        if (valid) pt = ldPoint(batch + i);
+        uint32_t lp = 0, slot = 0;
+        walk<SAMPLE, COUNT>(c, valid, pt, node, level, lp, slot);
+        if (valid && COUNT) { c.leafOf[i] = lp; c.slotOf[i] = slot; }
+    }
+    // spilled points (always carry a cached start node: the leaf they were spilled from)
+    for (uint32_t base = tid - laneId(); base < numSpilled; base += stride) {
+        uint32_t j = base + laneId();
+        bool valid = j < numSpilled;
+        uint32_t node = 0, level = 0;
+        if (valid && !(FRESH && !COUNT)) {       // sampling-only fresh pass restarts at the root
+            uint32_t lp = c.leafOf[scratch::MAX_BATCH + j];
+            node = lp & 0xffffffu; level = lp >> 24;
+            valid = c.firstChild[node] != 0 && level < SIMLOD_MAX_DEPTH;
+        }
+        uint4 pt = make_uint4(0, 0, 0, 0);
+        if (valid) pt = *reinterpret_cast<const uint4*>(c.spilled + j);
+        uint32_t lp = 0, slot = 0;
+        walk<SAMPLE, COUNT>(c, valid, pt, node, level, lp, slot);
+        if (valid && COUNT) { c.leafOf[scratch::MAX_BATCH + j] = lp; c.slotOf[scratch::MAX_BATCH + j] = slot; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// split round (voxels.cu:245-289 spill copy, :308-383 doSplitting)
+// ------------------------------------------------------------------------------------------
+__device__ void copySpilledPoints(const Ctx& c, uint32_t begin, uint32_t end) {
+    __shared__ uint32_t sh_item;
+    __shared__ uint32_t sh_base;
+    __shared__ uint64_t sh_chunks[64];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh_item = begin + atomicAdd(&c.ctl->workCounter, 1u);
+        __syncthreads();
+        uint32_t item = sh_item;
+        if (item >= end) break;
+        uint32_t n = c.spillingNodes[item];
+        Node* node = &c.nodes[n];
+        uint32_t numPoints = node->numPoints;
+        if (numPoints == 0) continue;
+        uint32_t level = node->level;
+        if (threadIdx.x == 0) {
+            uint32_t b = atomicAdd(&c.ctl->numSpilled, numPoints);
+            if ((uint64_t)b + numPoints > scratch::SPILL_CAP) { atomicOr(&c.ctl->errorFlags, ERR_SPILL_OVERFLOW); b = 0xffffffffu; }
+            sh_base = b;
+        }
+        uint32_t numChunks = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        Chunk* chunk = node->points;
+        for (uint32_t k0 = 0; k0 < numChunks; k0 += 64) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (uint32_t k = 0; k < 64 && k0 + k < numChunks; k++) { sh_chunks[k] = (uint64_t)chunk; chunk = chunk->next; }
+            }
+            __syncthreads();
+            uint32_t base = sh_base;
+            if (base == 0xffffffffu) break;
+            uint32_t first = k0 * SIMLOD_POINTS_PER_CHUNK;
+            uint32_t last = min(numPoints, (k0 + 64) * SIMLOD_POINTS_PER_CHUNK);
+            for (uint32_t i = first + threadIdx.x; i < last; i += blockDim.x) {
+                const Chunk* ch = reinterpret_cast<const Chunk*>(sh_chunks[(i / SIMLOD_POINTS_PER_CHUNK) - k0]);
+                uint4 v = *reinterpret_cast<const uint4*>(&ch->points[i % SIMLOD_POINTS_PER_CHUNK]);
+                *reinterpret_cast<uint4*>(c.spilled + base + i) = v;
+                c.leafOf[scratch::MAX_BATCH + base + i] = n | (level << 24);
+            }
+        }
+    }
+}
+
+__device__ void splitNodes(const Ctx& c, uint32_t begin, uint32_t end) {
+    const uint32_t warpsTotal = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = laneId();
+    for (uint32_t item = begin + warp; item < end; item += warpsTotal) {
+        uint32_t n = c.spillingNodes[item];
+        Node* parent = &c.nodes[n];
+        uint32_t childBase = 0;
+        if (lane == 0) childBase = atomicAdd(&c.stats->numNodes, 8u);
+        childBase = __shfl_sync(0xffffffffu, childBase, 0);
+        if (childBase + 8 > scratch::NODE_CAP) { if (lane == 0) atomicOr(&c.ctl->errorFlags, ERR_NODE_OVERFLOW); continue; }
+        uint32_t plevel = parent->level, pX = parent->X, pY = parent->Y, pZ = parent->Z;
+        if (lane < 8) {
+            // default-constructed Node + the fields doSplitting sets (voxels.cu:324-342)
+            Node* child = &c.nodes[childBase + lane];
+            uint64_t* raw = reinterpret_cast<uint64_t*>(child);
+#pragma unroll
+            for (int w = 0; w < 19; w++) raw[w] = 0;
+            child->level = plevel + 1;
+            child->X = 2 * pX + ((lane >> 2) & 1);
+            child->Y = 2 * pY + ((lane >> 1) & 1);
+            child->Z = 2 * pZ + (lane & 1);
+            for (int b = 0; b < 20; b++) child->name[b] = parent->name[b];
+            reinterpret_cast<uint8_t*>(child)[offsetof(Node, name) + plevel + 1] = (uint8_t)('0' + lane);   // name[level] (sic: level 20 lands on `visible`)
+            child->isLeaf = 1;
+            parent->children[lane] = child;
+            c.firstChild[childBase + lane] = 0;
+            c.gridPtr[childBase + lane] = 0;
+        }
+        if (lane == 0) {
+            // return the leaf's chunks to the free stack (voxels.cu:345-357)
+            uint32_t numPoints = parent->numPoints;
+            uint32_t f = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+            if (f > 0) {
+                uint64_t a0 = atomicAdd(reinterpret_cast<unsigned long long*>(&c.stats->numAllocatedChunks), (unsigned long long)(0ull - f));
+                Chunk* chunk = parent->points;
+                for (uint32_t t = 0; t < f && chunk != nullptr; t++) {
+                    Chunk* next = chunk->next;
+                    chunk->next = nullptr;
+                    uint64_t qi = a0 - 1 - t;
+                    if (qi < scratch::QUEUE_CAP) c.chunkQueue[qi] = (uint64_t)chunk;
+                    else atomicOr(&c.ctl->errorFlags, ERR_QUEUE_OVERFLOW);
+                    chunk = next;
+                }
+            }
+            parent->numPoints = 0;
+            parent->points = nullptr;
+            if (parent->grid == nullptr) {
+                uint64_t off = atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)SIMLOD_GRID_STRIDE);
+                parent->grid = reinterpret_cast<SimlodOccupancyGrid*>(c.heapBytes + off);
+            }
+            c.gridPtr[n] = (uint64_t)parent->grid;
+            c.firstChild[n] = childBase;
+        }
+        __syncwarp();
+    }
+}
+
+// voxels.cu:370-382 — clears the grid of every node split in this round (sic: including the
+// root's already populated grid; its cells are then re-created by the re-sampled spilled points)
+__device__ void clearGrids(const Ctx& c, uint32_t begin, uint32_t end) {
+    const uint64_t vecPerGrid = SIMLOD_GRID_WORDS / 4;
+    const uint64_t total = (uint64_t)(end - begin) * vecPerGrid;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        uint32_t n = c.spillingNodes[begin + (uint32_t)(i / vecPerGrid)];
+        uint64_t g = c.gridPtr[n];
+        if (g == 0) continue;
+        reinterpret_cast<uint4*>(g)[i % vecPerGrid] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// chunk allocation for the nodes touched by this batch (voxels.cu:485-538, 641-672)
+// ------------------------------------------------------------------------------------------
+__device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t numDirtyLeaves = ldv(&c.ctl->numDirtyLeaves);
+    const uint32_t numDirtyVox = ldv(&c.ctl->numDirtyVox);
+
+    for (uint32_t d = tid; d < numDirtyLeaves; d += stride) {
+        uint32_t n = c.dirtyLeaves[d];
+        if (c.firstChild[n] != 0) continue;                 // became an inner node in this batch
+        Node* node = &c.nodes[n];
+        uint32_t cnt = node->counter, have = node->numPoints;
+        if (cnt <= have) continue;
+        uint32_t k0 = have / SIMLOD_POINTS_PER_CHUNK, k1 = (cnt - 1) / SIMLOD_POINTS_PER_CHUNK;
+        uint32_t nseg = k1 - k0 + 1;
+        uint32_t existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        uint32_t required = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        uint32_t needed = required - existing;
+        uint32_t base = atomicAdd(&c.ctl->dirCursor, nseg);
+        if ((uint64_t)base + nseg > scratch::DIR_CAP) { atomicOr(&c.ctl->errorFlags, ERR_DIR_OVERFLOW); continue; }
+        c.pointDir[n] = DirEntry{base, k0};
+        Chunk* tail = node->points ? reinterpret_cast<Chunk*>(c.pointTail[n]) : nullptr;
+        uint32_t j = 0;
+        if (have % SIMLOD_POINTS_PER_CHUNK != 0) c.chunkDir[base + j++] = (uint64_t)tail;
+        if (needed > 0) {
+            uint64_t a0 = atomicAdd(reinterpret_cast<unsigned long long*>(&c.stats->numAllocatedChunks), (unsigned long long)needed);
+            uint64_t firstFresh = a0 > poolSize ? a0 : poolSize;          // indices >= poolSize are new heap chunks (voxels.cu:509-515)
+            uint64_t numFresh = a0 + needed > firstFresh ? a0 + needed - firstFresh : 0;
+            uint64_t freshOff = 0;
+            if (numFresh) freshOff = atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)(numFresh * SIMLOD_CHUNK_STRIDE));
+            for (uint32_t t = 0; t < needed; t++) {
+                uint64_t idx = a0 + t;
+                Chunk* chunk = idx < poolSize ? reinterpret_cast<Chunk*>(c.chunkQueue[idx])
+                                              : reinterpret_cast<Chunk*>(c.heapBytes + freshOff + (idx - firstFresh) * SIMLOD_CHUNK_STRIDE);
+                chunk->next = nullptr;
+                if (tail) tail->next = chunk; else node->points = chunk;
+                tail = chunk;
+                c.chunkDir[base + j++] = (uint64_t)chunk;
+            }
+            c.pointTail[n] = (uint64_t)tail;
+        }
+        node->numPoints = cnt;      // slots [have, cnt) were handed out by the counting pass; filled by insertAll
+    }
+
+    for (uint32_t d = tid; d < numDirtyVox; d += stride) {
+        uint32_t n = c.dirtyVox[d];
+        Node* node = &c.nodes[n];
+        uint32_t cnt = node->numVoxels, have = node->numVoxelsStored;
+        if (cnt <= have) continue;
+        uint32_t k0 = have / SIMLOD_POINTS_PER_CHUNK, k1 = (cnt - 1) / SIMLOD_POINTS_PER_CHUNK;
+        uint32_t nseg = k1 - k0 + 1;
+        uint32_t existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        uint32_t required = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        uint32_t needed = required - existing;
+        uint32_t base = atomicAdd(&c.ctl->dirCursor, nseg);
+        if ((uint64_t)base + nseg > scratch::DIR_CAP) { atomicOr(&c.ctl->errorFlags, ERR_DIR_OVERFLOW); continue; }
+        c.voxelDir[n] = DirEntry{base, k0};
+        Chunk* tail = node->voxelChunks ? reinterpret_cast<Chunk*>(c.voxelTail[n]) : nullptr;
+        uint32_t j = 0;
+        if (have % SIMLOD_POINTS_PER_CHUNK != 0) c.chunkDir[base + j++] = (uint64_t)tail;
+        if (needed > 0) {
+            // voxel chunks are never recycled: always fresh heap memory (voxels.cu:652-666)
+            uint64_t freshOff = atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)((uint64_t)needed * SIMLOD_CHUNK_STRIDE));
+            for (uint32_t t = 0; t < needed; t++) {
+                Chunk* chunk = reinterpret_cast<Chunk*>(c.heapBytes + freshOff + (uint64_t)t * SIMLOD_CHUNK_STRIDE);
+                chunk->next = nullptr;
+                if (tail) tail->next = chunk; else node->voxelChunks = chunk;
+                tail = chunk;
+                c.chunkDir[base + j++] = (uint64_t)chunk;
+            }
+            c.voxelTail[n] = (uint64_t)tail;
+        }
+        node->numVoxelsStored = cnt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// insertion: every point/voxel already owns (leaf, slot); the chunk directory turns that into
+// an address with two cached lookups (voxels.cu:540-639 insertPoints, 674-698 insertVoxels)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ Point* slotAddress(const Ctx& c, const DirEntry* dir, uint32_t node, uint32_t slot) {
+    DirEntry d = dir[node];
+    Chunk* chunk = reinterpret_cast<Chunk*>(c.chunkDir[d.base + (slot / SIMLOD_POINTS_PER_CHUNK - d.k0)]);
+    return &chunk->points[slot % SIMLOD_POINTS_PER_CHUNK];
+}
+
+__device__ void insertAll(const Ctx& c, const Point* batch, uint32_t numBatch, uint32_t numSpilled, uint32_t numVoxels) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = tid; i < numBatch; i += stride) {
+        uint4 pt = ldPoint(batch + i);
+        uint32_t node = c.leafOf[i] & 0xffffffu;
+        stPoint(slotAddress(c, c.pointDir, node, c.slotOf[i]), pt);
+    }
+    for (uint32_t j = tid; j < numSpilled; j += stride) {
+        uint4 pt = *reinterpret_cast<const uint4*>(c.spilled + j);
+        uint32_t node = c.leafOf[scratch::MAX_BATCH + j] & 0xffffffu;
+        stPoint(slotAddress(c, c.pointDir, node, c.slotOf[scratch::MAX_BATCH + j]), pt);
+    }
+    for (uint32_t b = tid; b < numVoxels; b += stride) {
+        uint64_t key = c.vkey[b];
+        uint32_t cell = (uint32_t)(key & 0x1fffffu);
+        uint32_t node = (uint32_t)((key >> 21) & 0xfffffu);
+        uint32_t vslot = (uint32_t)(key >> 41);
+        const Node* nd = &c.nodes[node];
+        uint32_t level = nd->level, X = nd->X, Y = nd->Y, Z = nd->Z;
+        // cell centre in world space (voxels.cu:103-114; instruction sequence: see fpmath.cuh)
+        float nodeSize = fpx::mul_ftz(fpx::ex2(-fpx::u2f(level)), c.size);
+        float vx = fpx::add(fpx::fma(nodeSize, fpx::u2f(X), c.minx),
+                            fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f(cell & 127u), 0.5f)), 0.0078125f));
+        float vy = fpx::add(fpx::fma(nodeSize, fpx::u2f(Y), c.miny),
+                            fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f((cell >> 7) & 127u), 0.5f)), 0.0078125f));
+        float vz = fpx::add(fpx::fma(nodeSize, fpx::u2f(Z), c.minz),
+                            fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f((cell >> 14) & 127u), 0.5f)), 0.0078125f));
+        uint4 v = make_uint4(__float_as_uint(vx), __float_as_uint(vy), __float_as_uint(vz), c.vcolor[b]);
+        stPoint(slotAddress(c, c.voxelDir, node, vslot), v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel_construct — voxels.cu:804-1010
+// ------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(256, 4)
+kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8_t* buffer_persistent, Node* nodes,
+                 Stats* stats, uint64_t* frameStartTimestamp, CudaPrint* cudaprint,
+                 uint32_t* numBatchesUploaded_volatile, uint32_t* batchSizes) {
+    cg::grid_group grid = cg::this_grid();
+    const bool first = grid.thread_rank() == 0;
+    const uint64_t tStart = globaltimer();
+
+    Ctx c;
+    c.nodes = nodes;
+    c.stats = stats;
+    c.heap = reinterpret_cast<Heap*>(buffer_persistent);
+    c.heapBytes = buffer_persistent;
+    c.ctl = carve<Ctl>(buffer, scratch::OFF_CTL);
+    c.firstChild = carve<uint32_t>(buffer, scratch::OFF_FIRSTCHILD);
+    c.gridPtr = carve<uint64_t>(buffer, scratch::OFF_GRIDPTR);
+    c.pointTail = carve<uint64_t>(buffer, scratch::OFF_PTAIL);
+    c.voxelTail = carve<uint64_t>(buffer, scratch::OFF_VTAIL);
+    c.pointDir = carve<DirEntry>(buffer, scratch::OFF_PDIR);
+    c.voxelDir = carve<DirEntry>(buffer, scratch::OFF_VDIR);
+    c.dirtyLeaves = carve<uint32_t>(buffer, scratch::OFF_DIRTYLEAF);
+    c.dirtyVox = carve<uint32_t>(buffer, scratch::OFF_DIRTYVOX);
+    c.spillingNodes = carve<uint32_t>(buffer, scratch::OFF_SPILLNODES);
+    c.chunkDir = carve<uint64_t>(buffer, scratch::OFF_CHUNKDIR);
+    c.chunkQueue = carve<uint64_t>(buffer, scratch::OFF_QUEUE);
+    c.leafOf = carve<uint32_t>(buffer, scratch::OFF_LEAFOF);
+    c.slotOf = carve<uint32_t>(buffer, scratch::OFF_SLOTOF);
+    c.spilled = carve<Point>(buffer, scratch::OFF_SPILLED);
+    c.vkey = carve<uint64_t>(buffer, scratch::OFF_VKEY);
+    c.vcolor = carve<uint32_t>(buffer, scratch::OFF_VCOLOR);
+
+    // octree cube = boxMin + max extent on every axis (voxels.cu:860-863)
+    float sx = fpx::sub(uniforms.boxMax[0], uniforms.boxMin[0]);
+    float sy = fpx::sub(uniforms.boxMax[1], uniforms.boxMin[1]);
+    float sz = fpx::sub(uniforms.boxMax[2], uniforms.boxMin[2]);
+    c.size = fmaxf(fmaxf(sx, sy), sz);
+    c.rcpSize = fpx::rcp(c.size);
+    c.minx = uniforms.boxMin[0]; c.miny = uniforms.boxMin[1]; c.minz = uniforms.boxMin[2];
+
+    if (first) {
+        *frameStartTimestamp = tStart;
+        c.ctl->numBatchesUploaded = *(volatile uint32_t*)numBatchesUploaded_volatile;   // one snapshot for all threads
+        c.ctl->errorFlags = 0;
+        c.ctl->elapsedNanos = 0;
+        c.ctl->numSpillTotal = 0; c.ctl->numSpilled = 0; c.ctl->numBacklog = 0;
+        c.ctl->numDirtyLeaves = 0; c.ctl->numDirtyVox = 0; c.ctl->dirCursor = 0; c.ctl->workCounter = 0;
+        for (int i = 0; i < 8; i++) c.ctl->statCounters[i] = 0;
+        if (stats->batchletIndex == 0) {       // fresh after the reset kernel: the tree is the root alone
+            c.firstChild[0] = 0;
+            c.gridPtr[0] = (uint64_t)nodes[0].grid;
+        }
+    }
+    grid.sync();
+
+    const uint32_t numBatchesUploaded = ldv(&c.ctl->numBatchesUploaded);
+    const uint32_t firstBatch = ldv(&stats->batchletIndex);
+    const uint32_t numBatches = min(numBatchesUploaded - firstBatch, 20u);     // voxels.cu:883
+    const uint32_t lastBatch = firstBatch + numBatches;
+
+    for (uint32_t batchIndex = firstBatch; batchIndex < lastBatch; batchIndex++) {
+        const uint32_t ringSlot = batchIndex % SIMLOD_BATCH_STREAM_SIZE;
+        const uint32_t batchSize = min(ldv(&batchSizes[ringSlot]), (uint32_t)SIMLOD_MAX_BATCH_SIZE);
+        const Point* batch = points + (uint64_t)ringSlot * SIMLOD_MAX_BATCH_SIZE;
+
+        // capacity guard (voxels.cu:896-912): stop consuming batches 200 MB before the heap is full
+        const uint64_t memUsed = ldv(&c.heap->offset);
+        const bool memCapacityReached = memUsed + 200000000ull >= uniforms.persistentBufferCapacity;
+        if (first) stats->memCapacityReached = memCapacityReached ? 1 : 0;
+        if (memCapacityReached) break;
+
+        const bool deferSampling = ldv(&c.firstChild[0]) == 0;    // root still a leaf: see DESIGN.md §4 (root grid is wiped when it splits)
+        const uint64_t poolSize = ldv(&stats->chunkPoolSize);
+
+        // ---- pass 1: count (+ sample) every batch point ------------------------------------
+        if (deferSampling) itemPass<false, true, true>(c, batch, batchSize, 0);
+        else               itemPass<true, true, true>(c, batch, batchSize, 0);
+        grid.sync();
+
+        // ---- split rounds (voxels.cu:385-415 expand) ---------------------------------------
+        uint32_t spillBegin = 0;
+        for (int round = 0; round < 20; round++) {
+            const uint32_t spillEnd = min(ldv(&c.ctl->numSpillTotal), (uint32_t)scratch::SPILLNODE_CAP);
+            if (spillEnd == spillBegin) break;
+            copySpilledPoints(c, spillBegin, spillEnd);
+            grid.sync();
+            if (first) c.ctl->workCounter = 0;
+            splitNodes(c, spillBegin, spillEnd);
+            grid.sync();
+            clearGrids(c, spillBegin, spillEnd);
+            grid.sync();
+            const uint32_t numSpilled = min(ldv(&c.ctl->numSpilled), (uint32_t)scratch::SPILL_CAP);
+            if (deferSampling) itemPass<false, true, false>(c, batch, batchSize, numSpilled);
+            else               itemPass<true, true, false>(c, batch, batchSize, numSpilled);
+            grid.sync();
+            spillBegin = spillEnd;
+        }
+        const uint32_t numSpilled = min(ldv(&c.ctl->numSpilled), (uint32_t)scratch::SPILL_CAP);
+        if (deferSampling) {
+            // the root was a leaf when the batch started: sample along the final paths, as the
+            // reference does after expand() (voxels.cu:738-742)
+            itemPass<true, false, true>(c, batch, batchSize, numSpilled);
+            grid.sync();
+        }
+
+        // ---- chunk allocation for touched nodes --------------------------------------------
+        allocateChunks(c, poolSize);
+        grid.sync();
+
+        // ---- insertion ---------------------------------------------------------------------
+        const uint32_t numVoxels = min(ldv(&c.ctl->numBacklog), (uint32_t)scratch::VOXEL_CAP);
+        insertAll(c, batch, batchSize, numSpilled, numVoxels);
+        if (first) {
+            uint64_t allocated = ldv(&stats->numAllocatedChunks);
+            if (allocated > poolSize) stats->chunkPoolSize = allocated;        // voxels.cu:535-537
+        }
+        grid.sync();
+
+        // ---- bookkeeping (voxels.cu:925-949) -----------------------------------------------
+        if (first) {
+            stats->batchletIndex = batchIndex + 1;
+            stats->numPointsProcessed += batchSize;
+            c.ctl->elapsedNanos = globaltimer() - tStart;
+            c.ctl->numSpillTotal = 0; c.ctl->numSpilled = 0; c.ctl->numBacklog = 0;
+            c.ctl->numDirtyLeaves = 0; c.ctl->numDirtyVox = 0; c.ctl->dirCursor = 0; c.ctl->workCounter = 0;
+        }
+        grid.sync();
+        const float elapsedMs = float(ldv(&c.ctl->elapsedNanos)) / 1000000.0f;
+        if (elapsedMs > 10.0f) break;          // MAX_PROCESSING_TIME (voxels.cu:22,940)
+    }
+
+    // ---- octree statistics (voxels.cu:958-1009) --------------------------------------------
+    {
+        const uint32_t numNodes = ldv(&stats->numNodes);
+        const uint32_t stride = gridDim.x * blockDim.x;
+        uint32_t inner = 0, leaves = 0, nonempty = 0, pts = 0, vox = 0, chP = 0, chV = 0;
+        for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < numNodes; n += stride) {
+            const Node* node = &nodes[n];
+            if (c.firstChild[n] == 0) {
+                uint32_t np = node->numPoints;
+                leaves++; pts += np; chP += (np + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+                if (np > 0) nonempty++;
+            } else {
+                uint32_t nv = node->numVoxels;
+                inner++; vox += nv; chV += (nv + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+            }
+        }
+        uint32_t vals[7] = {inner, leaves, nonempty, pts, vox, chP, chV};
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            uint32_t v = vals[k];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (laneId() == 0 && v) atomicAdd(&c.ctl->statCounters[k], v);
+        }
+    }
+    grid.sync();
+    if (first) {
+        stats->numInner = ldv(&c.ctl->statCounters[0]);
+        stats->numLeaves = ldv(&c.ctl->statCounters[1]);
+        stats->numNonemptyLeaves = ldv(&c.ctl->statCounters[2]);
+        stats->numPoints = ldv(&c.ctl->statCounters[3]);
+        stats->numVoxels = ldv(&c.ctl->statCounters[4]);
+        stats->numChunksPoints = ldv(&c.ctl->statCounters[5]);
+        stats->numChunksVoxels = ldv(&c.ctl->statCounters[6]);
+        stats->allocatedBytes_momentary = scratch::TOTAL;
+        stats->allocatedBytes_persistent = ldv(&c.heap->offset);
+        stats->frameID = (uint32_t)uniforms.frameCounter;
+        stats->dbg = ldv(&c.ctl->errorFlags);
+    }
+}

@@ -1,0 +1,560 @@
+// host.cpp — the headless launch surface behind include/simlod_b200.h.
+//
+// Restates, on the CUDA driver API like the reference, the host side of the hot path:
+//   initCuda / initCudaProgram   main_progressive_octree.cpp:272-281, 549-642
+//   getUniforms                  :283-331        resetCUDA     :333-361
+//   updateOctree                 :364-428        renderCUDA    :465-546
+//   uploader step                :1033-1056      stats readback :1201-1216
+// The three programs are sm_100a cubins embedded in this library (the reference NVRTC-compiles
+// its sources at start-up, CudaModularProgram.h:62-135); simlod_use_module swaps one of them
+// for an external cubin with the same kernel name (the reference's hot reload, :181-184).
+// There is no CPU fallback: without a device or a loadable cubin every call fails.
+#include "../../include/simlod_b200.h"
+#include <cuda.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+extern "C" {
+extern const unsigned char simlod_cubin_construct[];
+extern const unsigned char simlod_cubin_render[];
+extern const unsigned char simlod_cubin_reset[];
+extern const unsigned char simlod_cubin_util[];
+}
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// The driver API is bound at run time (dlopen libcuda.so.1) so that the library can be loaded
+// and its exports inspected on a machine without a GPU driver; every entry point that touches
+// the device fails with SIMLOD_ERR_CUDA there. There is no other code path.
+// ------------------------------------------------------------------------------------------
+#define DRV_LIST(X) X(cuArray3DCreate) X(cuArrayDestroy) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuDeviceGet) X(cuDeviceGetAttribute) X(cuDevicePrimaryCtxRelease) X(cuDevicePrimaryCtxRetain) X(cuEventCreate) X(cuEventDestroy) X(cuEventElapsedTime) X(cuEventRecord) X(cuEventSynchronize) X(cuGetErrorString) X(cuInit) X(cuLaunchCooperativeKernel) X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree) X(cuMemFreeHost) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemcpy2D) X(cuMemcpyDtoDAsync) X(cuMemcpyDtoH) X(cuMemcpyDtoHAsync) X(cuMemcpyHtoD) X(cuMemcpyHtoDAsync) X(cuMemsetD32Async) X(cuMemsetD8) X(cuMemsetD8Async) X(cuModuleGetFunction) X(cuModuleLoadData) X(cuModuleUnload) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuSurfObjectCreate) X(cuSurfObjectDestroy)
+#define DRV_STR2(x) #x
+#define DRV_STR(x) DRV_STR2(x)
+struct DriverApi {
+#define X(name) decltype(&name) p_##name = nullptr;
+    DRV_LIST(X)
+#undef X
+    void* handle = nullptr;
+    bool loaded = false;
+};
+DriverApi drv;
+#define D(name) drv.p_##name
+
+int loadDriver() {
+    if (drv.loaded) return SIMLOD_OK;
+    drv.handle = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!drv.handle) return fail(SIMLOD_ERR_CUDA, "cannot load libcuda.so.1 (%s): a CUDA driver and a B200 are required, there is no CPU path", dlerror());
+#define X(name) drv.p_##name = reinterpret_cast<decltype(&name)>(dlsym(drv.handle, DRV_STR(name))); \
+    if (!drv.p_##name) return fail(SIMLOD_ERR_CUDA, "libcuda.so.1 lacks %s", DRV_STR(name));
+    DRV_LIST(X)
+#undef X
+    drv.loaded = true;
+    return SIMLOD_OK;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        CUresult _r = (call);                                                                 \
+        if (_r != CUDA_SUCCESS) {                                                             \
+            const char* _s = nullptr; D(cuGetErrorString)(_r, &_s);                              \
+            return fail(SIMLOD_ERR_CUDA, "%s failed: %s (%d) at %s:%d", #call, _s ? _s : "?", (int)_r, __FILE__, __LINE__); \
+        }                                                                                     \
+    } while (0)
+
+constexpr uint64_t RING_SLOTS = SIMLOD_BATCH_STREAM_SIZE;
+constexpr uint64_t SLOT_POINTS = SIMLOD_MAX_BATCH_SIZE;
+constexpr uint64_t FB_OFFSET = 31200144;       // render.cu:1108-1123 carve-out
+constexpr uint64_t L2_FLUSH_BYTES = 512ull << 20;
+
+struct Program {
+    CUmodule module = nullptr;
+    CUfunction fn = nullptr;
+    bool builtin = true;
+};
+
+}  // namespace
+
+struct SimlodContext {
+    CUdevice device = 0;
+    CUcontext primary = nullptr;
+    int numSMs = 0;
+    CUstream streamMain = nullptr, streamUpload = nullptr;
+    CUevent evStart = nullptr, evEnd = nullptr;
+    SimlodConfig cfg{};
+    SimlodUniforms uniforms{};
+    SimlodBuffers buf{};
+    CUdeviceptr numBatchesUploaded = 0, batchSizes = 0, frameStart = 0, cudaprint = 0, scratch4 = 0, flushBuf = 0;
+    CUarray colorArray = nullptr;
+    CUsurfObject surface = 0;
+    SimlodStats* hStats = nullptr;     // pinned
+    Program programs[3];
+    CUmodule utilModule = nullptr;
+    CUfunction fnRcp = nullptr, fnFill = nullptr;
+    uint32_t uploaded = 0;             // batches published to the device
+    uint32_t processed = 0;            // Stats::batchletIndex as last read
+    uint64_t launches = 0;
+    uint32_t constructBlocks = 0, renderBlocks = 0;
+    uint64_t frameCounter = 0;
+};
+
+namespace {
+
+int devAlloc(uint64_t* out, uint64_t bytes) {
+    CUdeviceptr p = 0;
+    CU(D(cuMemAlloc)(&p, (size_t)bytes));
+    *out = (uint64_t)p;
+    return SIMLOD_OK;
+}
+#define ALLOC(field, bytes) do { int _rc = devAlloc(&(field), (bytes)); if (_rc) return _rc; } while (0)
+
+const char* kernelName(int program) {
+    switch (program) {
+        case SIMLOD_PROGRAM_CONSTRUCT: return "kernel_construct";
+        case SIMLOD_PROGRAM_RENDER: return "kernel_render";
+        case SIMLOD_PROGRAM_RESET: return "kernel";
+    }
+    return nullptr;
+}
+const unsigned char* builtinImage(int program) {
+    switch (program) {
+        case SIMLOD_PROGRAM_CONSTRUCT: return simlod_cubin_construct;
+        case SIMLOD_PROGRAM_RENDER: return simlod_cubin_render;
+        case SIMLOD_PROGRAM_RESET: return simlod_cubin_reset;
+    }
+    return nullptr;
+}
+
+int setCurrent(SimlodContext* ctx) {
+    if (!ctx) return fail(SIMLOD_ERR_INVALID, "null context");
+    CU(D(cuCtxSetCurrent)(ctx->primary));
+    return SIMLOD_OK;
+}
+
+int computeGrids(SimlodContext* ctx) {
+    // updateOctree: numGroups = numSMs (main.cpp:370-371); renderCUDA: occupancy * numSMs (main.cpp:493-497).
+    // Our construct kernel is written for any cooperative grid, so by default both use the occupancy query.
+    int occ = 0;
+    CU(D(cuOccupancyMaxActiveBlocksPerMultiprocessor)(&occ, ctx->programs[SIMLOD_PROGRAM_CONSTRUCT].fn, 256, 0));
+    int per = ctx->cfg.construct_blocks_per_sm > 0 ? std::min(ctx->cfg.construct_blocks_per_sm, occ) : occ;
+    if (per < 1) return fail(SIMLOD_ERR_MODULE, "kernel_construct cannot be resident with 256 threads");
+    ctx->constructBlocks = (uint32_t)(per * ctx->numSMs);
+    CU(D(cuOccupancyMaxActiveBlocksPerMultiprocessor)(&occ, ctx->programs[SIMLOD_PROGRAM_RENDER].fn, 256, 0));
+    per = ctx->cfg.render_blocks_per_sm > 0 ? std::min(ctx->cfg.render_blocks_per_sm, occ) : occ;
+    if (per < 1) return fail(SIMLOD_ERR_MODULE, "kernel_render cannot be resident with 256 threads");
+    ctx->renderBlocks = (uint32_t)(per * ctx->numSMs);
+    return SIMLOD_OK;
+}
+
+int loadProgram(SimlodContext* ctx, int program, const void* image, bool builtin) {
+    CUmodule mod = nullptr;
+    CUresult r = D(cuModuleLoadData)(&mod, image);
+    if (r != CUDA_SUCCESS) {
+        const char* s = nullptr; D(cuGetErrorString)(r, &s);
+        return fail(SIMLOD_ERR_MODULE, "D(cuModuleLoadData)(%s) failed: %s", kernelName(program), s ? s : "?");
+    }
+    CUfunction fn = nullptr;
+    r = D(cuModuleGetFunction)(&fn, mod, kernelName(program));
+    if (r != CUDA_SUCCESS) { D(cuModuleUnload)(mod); return fail(SIMLOD_ERR_MODULE, "module does not export %s", kernelName(program)); }
+    Program& p = ctx->programs[program];
+    if (p.module) D(cuModuleUnload)(p.module);
+    p.module = mod; p.fn = fn; p.builtin = builtin;
+    return SIMLOD_OK;
+}
+
+int readStats(SimlodContext* ctx) {
+    CU(D(cuMemcpyDtoHAsync)(ctx->hStats, ctx->buf.stats, sizeof(SimlodStats), ctx->streamMain));
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    ctx->processed = ctx->hStats->batchletIndex;
+    return SIMLOD_OK;
+}
+
+int publishBatch(SimlodContext* ctx, uint32_t slot, uint32_t count) {
+    // main.cpp:1047-1050: the size of the slot first, then the global counter, in stream order after the copy
+    CU(D(cuMemsetD32Async)(ctx->batchSizes + 4ull * slot, count, 1, ctx->streamUpload));
+    ctx->uploaded++;
+    CU(D(cuMemsetD32Async)(ctx->numBatchesUploaded, ctx->uploaded, 1, ctx->streamUpload));
+    return SIMLOD_OK;
+}
+
+int launchConstruct(SimlodContext* ctx, float* ms) {
+    SimlodUniforms u = ctx->uniforms;
+    u.frameCounter = ctx->frameCounter;
+    CUdeviceptr ring = ctx->buf.ring, momentary = ctx->buf.momentary, persistent = ctx->buf.persistent, nodes = ctx->buf.nodes,
+                stats = ctx->buf.stats, frameStart = ctx->frameStart, cudaprint = ctx->cudaprint,
+                nbu = ctx->numBatchesUploaded, bs = ctx->batchSizes;
+    void* args[] = {&u, &ring, &momentary, &persistent, &nodes, &stats, &frameStart, &cudaprint, &nbu, &bs};   // main.cpp:374-382
+    CU(D(cuEventRecord)(ctx->evStart, ctx->streamMain));
+    CU(D(cuLaunchCooperativeKernel)(ctx->programs[SIMLOD_PROGRAM_CONSTRUCT].fn, ctx->constructBlocks, 1, 1, 256, 1, 1, 0, ctx->streamMain, args));
+    CU(D(cuEventRecord)(ctx->evEnd, ctx->streamMain));
+    ctx->launches++;
+    CU(D(cuEventSynchronize)(ctx->evEnd));
+    if (ms) CU(D(cuEventElapsedTime)(ms, ctx->evStart, ctx->evEnd));
+    return SIMLOD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* simlod_last_error(void) { return g_error.c_str(); }
+
+int simlod_create(const SimlodConfig* config, SimlodContext** out) {
+    if (!config || !out) return fail(SIMLOD_ERR_INVALID, "null argument");
+    if (config->width == 0 || config->height == 0) return fail(SIMLOD_ERR_INVALID, "render target must be non-empty");
+    { int rc0 = loadDriver(); if (rc0) return rc0; }
+    CU(D(cuInit)(0));
+    SimlodContext* ctx = new SimlodContext();
+    ctx->cfg = *config;
+    // the primary context, so the library composes with other runtime-API users in the process
+    CUresult r = D(cuDeviceGet)(&ctx->device, config->device);
+    if (r != CUDA_SUCCESS) { delete ctx; return fail(SIMLOD_ERR_CUDA, "D(cuDeviceGet)(%d) failed: no such CUDA device", config->device); }
+    CU(D(cuDevicePrimaryCtxRetain)(&ctx->primary, ctx->device));
+    CU(D(cuCtxSetCurrent)(ctx->primary));
+    CU(D(cuDeviceGetAttribute)(&ctx->numSMs, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, ctx->device));
+    int coop = 0;
+    CU(D(cuDeviceGetAttribute)(&coop, CU_DEVICE_ATTRIBUTE_COOPERATIVE_LAUNCH, ctx->device));
+    if (!coop) return fail(SIMLOD_ERR_CUDA, "device does not support cooperative launches");
+    CU(D(cuStreamCreate)(&ctx->streamMain, CU_STREAM_NON_BLOCKING));
+    CU(D(cuStreamCreate)(&ctx->streamUpload, CU_STREAM_NON_BLOCKING));      // main.cpp:276
+    CU(D(cuEventCreate)(&ctx->evStart, CU_EVENT_DEFAULT));
+    CU(D(cuEventCreate)(&ctx->evEnd, CU_EVENT_DEFAULT));
+
+    // programs (main.cpp:603-626)
+    for (int p = 0; p < 3; p++) {
+        int rc = loadProgram(ctx, p, builtinImage(p), true);
+        if (rc != SIMLOD_OK) return rc;
+    }
+    CU(D(cuModuleLoadData)(&ctx->utilModule, simlod_cubin_util));
+    CU(D(cuModuleGetFunction)(&ctx->fnRcp, ctx->utilModule, "simlod_util_rcp"));
+    CU(D(cuModuleGetFunction)(&ctx->fnFill, ctx->utilModule, "simlod_util_fill"));
+
+    // buffers (main.cpp:552-586)
+    SimlodBuffers& b = ctx->buf;
+    b.momentary_bytes = config->momentary_bytes ? config->momentary_bytes : 300000000ull;
+    b.nodes_bytes = config->nodes_bytes ? config->nodes_bytes : 40000000ull;
+    b.renderbuffer_bytes = config->renderbuffer_bytes ? config->renderbuffer_bytes : 200000000ull;
+    b.ring_bytes = RING_SLOTS * SLOT_POINTS * sizeof(SimlodPoint);
+    uint64_t fbEnd = FB_OFFSET + (uint64_t)config->width * config->height * (8 + 4 + 16) + 64;
+    if (fbEnd > b.renderbuffer_bytes) return fail(SIMLOD_ERR_INVALID, "render buffer too small for %ux%u", config->width, config->height);
+    ALLOC(b.momentary, b.momentary_bytes);
+    ALLOC(b.nodes, b.nodes_bytes);
+    ALLOC(b.renderbuffer, b.renderbuffer_bytes);
+    ALLOC(b.stats, sizeof(SimlodStats));
+    CU(D(cuMemAlloc)(&ctx->numBatchesUploaded, 4));
+    CU(D(cuMemAlloc)(&ctx->batchSizes, 4 * RING_SLOTS));
+    CU(D(cuMemAlloc)(&ctx->frameStart, 8));
+    CU(D(cuMemAlloc)(&ctx->scratch4, 16));
+    CU(D(cuMemAlloc)(&ctx->cudaprint, 1024 * 1000 + 16));                 // CudaPrint ring (CudaPrint.cuh:33-36); never written
+    CU(D(cuMemAlloc)(&ctx->flushBuf, L2_FLUSH_BYTES));
+    CU(D(cuMemHostAlloc)((void**)&ctx->hStats, sizeof(SimlodStats), 0));
+    ALLOC(b.ring, b.ring_bytes);
+    if (config->persistent_bytes) {
+        b.persistent_bytes = config->persistent_bytes;
+    } else {
+        size_t freeMem = 0, totalMem = 0;
+        CU(D(cuMemGetInfo)(&freeMem, &totalMem));
+        b.persistent_bytes = (uint64_t)((double)freeMem * 0.80);
+    }
+    ALLOC(b.persistent, b.persistent_bytes);
+    CU(D(cuMemsetD8)(b.momentary, 0, b.momentary_bytes));
+    CU(D(cuMemsetD8)(b.nodes, 0, b.nodes_bytes));
+    CU(D(cuMemsetD8)(b.stats, 0, sizeof(SimlodStats)));
+    CU(D(cuMemsetD8)(ctx->numBatchesUploaded, 0, 4));
+    CU(D(cuMemsetD8)(ctx->batchSizes, 0, 4 * RING_SLOTS));
+    CU(D(cuMemsetD8)(ctx->cudaprint, 0, 16));
+
+    // RGBA8 surface-capable array in place of the GL colour attachment (main.cpp:472-486)
+    CUDA_ARRAY3D_DESCRIPTOR ad{};
+    ad.Width = config->width; ad.Height = config->height; ad.Depth = 0;
+    ad.Format = CU_AD_FORMAT_UNSIGNED_INT8; ad.NumChannels = 4; ad.Flags = CUDA_ARRAY3D_SURFACE_LDST;
+    CU(D(cuArray3DCreate)(&ctx->colorArray, &ad));
+    CUDA_RESOURCE_DESC rd{};
+    rd.resType = CU_RESOURCE_TYPE_ARRAY; rd.res.array.hArray = ctx->colorArray;
+    CU(D(cuSurfObjectCreate)(&ctx->surface, &rd));
+
+    memset(&ctx->uniforms, 0, sizeof(ctx->uniforms));
+    ctx->uniforms.width = (float)config->width;
+    ctx->uniforms.height = (float)config->height;
+    ctx->uniforms.persistentBufferCapacity = b.persistent_bytes;
+    ctx->uniforms.momentaryBufferCapacity = b.momentary_bytes;
+    int rc = computeGrids(ctx);
+    if (rc != SIMLOD_OK) return rc;
+    CU(D(cuCtxSynchronize)());
+    *out = ctx;
+    return SIMLOD_OK;
+}
+
+void simlod_destroy(SimlodContext* ctx) {
+    if (!ctx) return;
+    if (D(cuCtxSetCurrent)(ctx->primary) == CUDA_SUCCESS) {
+        D(cuCtxSynchronize)();
+        if (ctx->surface) D(cuSurfObjectDestroy)(ctx->surface);
+        if (ctx->colorArray) D(cuArrayDestroy)(ctx->colorArray);
+        CUdeviceptr ptrs[] = {ctx->buf.momentary, ctx->buf.nodes, ctx->buf.renderbuffer, ctx->buf.stats, ctx->buf.ring, ctx->buf.persistent,
+                              ctx->numBatchesUploaded, ctx->batchSizes, ctx->frameStart, ctx->scratch4, ctx->cudaprint, ctx->flushBuf};
+        for (CUdeviceptr p : ptrs) if (p) D(cuMemFree)(p);
+        if (ctx->hStats) D(cuMemFreeHost)(ctx->hStats);
+        for (int p = 0; p < 3; p++) if (ctx->programs[p].module) D(cuModuleUnload)(ctx->programs[p].module);
+        if (ctx->utilModule) D(cuModuleUnload)(ctx->utilModule);
+        if (ctx->evStart) D(cuEventDestroy)(ctx->evStart);
+        if (ctx->evEnd) D(cuEventDestroy)(ctx->evEnd);
+        if (ctx->streamMain) D(cuStreamDestroy)(ctx->streamMain);
+        if (ctx->streamUpload) D(cuStreamDestroy)(ctx->streamUpload);
+        D(cuDevicePrimaryCtxRelease)(ctx->device);
+    }
+    delete ctx;
+}
+
+int simlod_use_module(SimlodContext* ctx, int program, const char* cubin_path) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (program < 0 || program > 2) return fail(SIMLOD_ERR_INVALID, "unknown program %d", program);
+    CU(D(cuCtxSynchronize)());
+    if (!cubin_path) {
+        rc = loadProgram(ctx, program, builtinImage(program), true);
+    } else {
+        std::ifstream f(cubin_path, std::ios::binary);
+        if (!f) return fail(SIMLOD_ERR_MODULE, "cannot open %s", cubin_path);
+        std::vector<char> image((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        image.push_back(0);
+        rc = loadProgram(ctx, program, image.data(), false);
+    }
+    if (rc) return rc;
+    return computeGrids(ctx);
+}
+
+int simlod_set_uniforms(SimlodContext* ctx, const SimlodUniforms* uniforms) {
+    if (!ctx || !uniforms) return fail(SIMLOD_ERR_INVALID, "null argument");
+    ctx->uniforms = *uniforms;
+    ctx->uniforms.width = (float)ctx->cfg.width;                         // main.cpp:308-309
+    ctx->uniforms.height = (float)ctx->cfg.height;
+    ctx->uniforms.persistentBufferCapacity = ctx->buf.persistent_bytes;  // main.cpp:325-326
+    ctx->uniforms.momentaryBufferCapacity = ctx->buf.momentary_bytes;
+    return SIMLOD_OK;
+}
+
+int simlod_get_uniforms(SimlodContext* ctx, SimlodUniforms* out) {
+    if (!ctx || !out) return fail(SIMLOD_ERR_INVALID, "null argument");
+    *out = ctx->uniforms;
+    return SIMLOD_OK;
+}
+
+int simlod_reset(SimlodContext* ctx) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    CU(D(cuStreamSynchronize)(ctx->streamUpload));
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    CU(D(cuMemsetD8Async)(ctx->buf.nodes, 0, ctx->buf.nodes_bytes, ctx->streamMain));
+    SimlodUniforms u = ctx->uniforms;
+    u.frameCounter = ctx->frameCounter;
+    CUdeviceptr persistent = ctx->buf.persistent, nodes = ctx->buf.nodes, stats = ctx->buf.stats, cudaprint = ctx->cudaprint,
+                nbu = ctx->numBatchesUploaded, bs = ctx->batchSizes;
+    void* args[] = {&u, &persistent, &nodes, &stats, &cudaprint, &nbu, &bs};      // main.cpp:337-345
+    CU(D(cuLaunchCooperativeKernel)(ctx->programs[SIMLOD_PROGRAM_RESET].fn, 1, 1, 1, 1, 1, 1, 0, ctx->streamMain, args));   // 1 block x 1 thread (main.cpp:348-354)
+    ctx->launches++;
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    ctx->uploaded = 0;
+    ctx->processed = 0;
+    return SIMLOD_OK;
+}
+
+static int uploadCommon(SimlodContext* ctx, const void* host, CUdeviceptr dev, uint32_t count) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (count > SLOT_POINTS) return fail(SIMLOD_ERR_INVALID, "batch of %u points exceeds the ring slot size of %llu", count, (unsigned long long)SLOT_POINTS);
+    if (ctx->uploaded - ctx->processed >= RING_SLOTS) {
+        rc = readStats(ctx); if (rc) return rc;
+        if (ctx->uploaded - ctx->processed >= RING_SLOTS) return fail(SIMLOD_ERR_RING_FULL, "all %llu ring slots hold unprocessed batches", (unsigned long long)RING_SLOTS);
+    }
+    uint32_t slot = ctx->uploaded % RING_SLOTS;
+    CUdeviceptr dst = ctx->buf.ring + (uint64_t)slot * SLOT_POINTS * sizeof(SimlodPoint);
+    if (count) {
+        if (host) CU(D(cuMemcpyHtoDAsync)(dst, host, (size_t)count * sizeof(SimlodPoint), ctx->streamUpload));   // main.cpp:1040
+        else      CU(D(cuMemcpyDtoDAsync)(dst, dev, (size_t)count * sizeof(SimlodPoint), ctx->streamUpload));
+    }
+    return publishBatch(ctx, slot, count);
+}
+
+int simlod_upload_batch(SimlodContext* ctx, const SimlodPoint* host_points, uint32_t count) {
+    if (!host_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
+    return uploadCommon(ctx, host_points, 0, count);
+}
+int simlod_upload_batch_device(SimlodContext* ctx, uint64_t device_points, uint32_t count) {
+    if (!device_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
+    return uploadCommon(ctx, nullptr, (CUdeviceptr)device_points, count);
+}
+
+int simlod_update_octree(SimlodContext* ctx, float* kernel_ms) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    rc = launchConstruct(ctx, kernel_ms); if (rc) return rc;
+    return readStats(ctx);
+}
+
+static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr dev, uint64_t count, float* kernel_ms) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    const uint64_t numBatches = (count + SLOT_POINTS - 1) / SLOT_POINTS;
+    rc = readStats(ctx); if (rc) return rc;
+    const uint32_t target = ctx->uploaded + (uint32_t)numBatches;
+    uint64_t next = 0;
+    float total = 0.0f;
+    while (ctx->processed < target) {
+        // uploader: keep the ring as full as back-pressure allows (main.cpp:1012,1033-1056)
+        while (next < numBatches && ctx->uploaded - ctx->processed < RING_SLOTS) {
+            uint64_t first = next * SLOT_POINTS;
+            uint32_t n = (uint32_t)std::min<uint64_t>(SLOT_POINTS, count - first);
+            rc = uploadCommon(ctx, host ? host + first : nullptr, dev ? dev + first * sizeof(SimlodPoint) : 0, n);
+            if (rc) return rc;
+            next++;
+        }
+        float ms = 0.0f;
+        rc = launchConstruct(ctx, &ms); if (rc) return rc;
+        total += ms;
+        rc = readStats(ctx); if (rc) return rc;
+        if (ctx->hStats->memCapacityReached) return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed);
+    }
+    if (kernel_ms) *kernel_ms = total;
+    return SIMLOD_OK;
+}
+
+int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t count, float* kernel_ms) {
+    if (!host_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
+    return insertCommon(ctx, host_points, 0, count, kernel_ms);
+}
+int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms) {
+    if (!device_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
+    return insertCommon(ctx, nullptr, (CUdeviceptr)device_points, count, kernel_ms);
+}
+
+int simlod_render(SimlodContext* ctx, float* kernel_ms) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    SimlodUniforms u = ctx->uniforms;
+    u.frameCounter = ctx->frameCounter++;
+    CUdeviceptr rb = ctx->buf.renderbuffer, nodes = ctx->buf.nodes, stats = ctx->buf.stats, frameStart = ctx->frameStart, cudaprint = ctx->cudaprint;
+    CUsurfObject surf = ctx->surface;
+    void* args[] = {&rb, &u, &nodes, &surf, &stats, &frameStart, &cudaprint};     // main.cpp:499-507
+    CU(D(cuEventRecord)(ctx->evStart, ctx->streamMain));
+    CU(D(cuLaunchCooperativeKernel)(ctx->programs[SIMLOD_PROGRAM_RENDER].fn, ctx->renderBlocks, 1, 1, 256, 1, 1, 0, ctx->streamMain, args));
+    CU(D(cuEventRecord)(ctx->evEnd, ctx->streamMain));
+    ctx->launches++;
+    CU(D(cuEventSynchronize)(ctx->evEnd));
+    if (kernel_ms) CU(D(cuEventElapsedTime)(kernel_ms, ctx->evStart, ctx->evEnd));
+    return SIMLOD_OK;
+}
+
+int simlod_get_stats(SimlodContext* ctx, SimlodStats* out) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!out) return fail(SIMLOD_ERR_INVALID, "null argument");
+    rc = readStats(ctx); if (rc) return rc;
+    *out = *ctx->hStats;
+    return SIMLOD_OK;
+}
+
+int simlod_read_framebuffer(SimlodContext* ctx, uint64_t* out) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!out) return fail(SIMLOD_ERR_INVALID, "null argument");
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    CU(D(cuMemcpyDtoH)(out, ctx->buf.renderbuffer + FB_OFFSET, (size_t)ctx->cfg.width * ctx->cfg.height * 8));
+    return SIMLOD_OK;
+}
+
+int simlod_read_surface(SimlodContext* ctx, uint32_t* out) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!out) return fail(SIMLOD_ERR_INVALID, "null argument");
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    CUDA_MEMCPY2D cp{};
+    cp.srcMemoryType = CU_MEMORYTYPE_ARRAY; cp.srcArray = ctx->colorArray;
+    cp.dstMemoryType = CU_MEMORYTYPE_HOST; cp.dstHost = out; cp.dstPitch = (size_t)ctx->cfg.width * 4;
+    cp.WidthInBytes = (size_t)ctx->cfg.width * 4; cp.Height = ctx->cfg.height;
+    CU(D(cuMemcpy2D)(&cp));
+    return SIMLOD_OK;
+}
+
+int simlod_get_buffers(SimlodContext* ctx, SimlodBuffers* out) {
+    if (!ctx || !out) return fail(SIMLOD_ERR_INVALID, "null argument");
+    *out = ctx->buf;
+    return SIMLOD_OK;
+}
+
+int simlod_memcpy_dtoh(SimlodContext* ctx, void* dst, uint64_t src_device, uint64_t bytes) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    CU(D(cuMemcpyDtoH)(dst, (CUdeviceptr)src_device, (size_t)bytes));
+    return SIMLOD_OK;
+}
+int simlod_memcpy_htod(SimlodContext* ctx, uint64_t dst_device, const void* src, uint64_t bytes) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    CU(D(cuMemcpyHtoD)((CUdeviceptr)dst_device, src, (size_t)bytes));
+    return SIMLOD_OK;
+}
+
+int simlod_host_alloc(SimlodContext* ctx, uint64_t bytes, void** out) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    CU(D(cuMemHostAlloc)(out, (size_t)bytes, CU_MEMHOSTALLOC_PORTABLE));
+    return SIMLOD_OK;
+}
+int simlod_host_free(SimlodContext* ctx, void* ptr) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    CU(D(cuMemFreeHost)(ptr));
+    return SIMLOD_OK;
+}
+int simlod_device_alloc(SimlodContext* ctx, uint64_t bytes, uint64_t* out) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    CUdeviceptr p = 0;
+    CU(D(cuMemAlloc)(&p, (size_t)bytes));
+    *out = (uint64_t)p;
+    return SIMLOD_OK;
+}
+int simlod_device_free(SimlodContext* ctx, uint64_t ptr) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    CU(D(cuMemFree)((CUdeviceptr)ptr));
+    return SIMLOD_OK;
+}
+
+int simlod_get_launch_info(SimlodContext* ctx, uint64_t* launches, uint32_t* construct_blocks, uint32_t* render_blocks, uint32_t* num_sms) {
+    if (!ctx) return fail(SIMLOD_ERR_INVALID, "null context");
+    if (launches) *launches = ctx->launches;
+    if (construct_blocks) *construct_blocks = ctx->constructBlocks;
+    if (render_blocks) *render_blocks = ctx->renderBlocks;
+    if (num_sms) *num_sms = (uint32_t)ctx->numSMs;
+    return SIMLOD_OK;
+}
+
+int simlod_device_rcp(SimlodContext* ctx, float x, float* out) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    CUdeviceptr dst = ctx->scratch4;
+    void* args[] = {&x, &dst};
+    CU(D(cuLaunchKernel)(ctx->fnRcp, 1, 1, 1, 1, 1, 1, 0, ctx->streamMain, args, nullptr));
+    ctx->launches++;
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    CU(D(cuMemcpyDtoH)(out, dst, 4));
+    return SIMLOD_OK;
+}
+
+int simlod_flush_l2(SimlodContext* ctx) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    CUdeviceptr dst = ctx->flushBuf;
+    uint64_t count = L2_FLUSH_BYTES / 16;
+    uint32_t value = 0;
+    void* args[] = {&dst, &count, &value};
+    CU(D(cuLaunchKernel)(ctx->fnFill, (unsigned)(ctx->numSMs * 8), 1, 1, 256, 1, 1, 0, ctx->streamMain, args, nullptr));
+    ctx->launches++;
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    return SIMLOD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,403 @@
+// render.cu — software point/voxel rasteriser for sm_100a (B200).
+//
+// Drop-in for the reference's `kernel_render` (modules/progressive_octree/render.cu:1084-1355):
+// same extern "C" name and arguments, same outputs — Node::visible / Node::isLarge flags, the
+// packed depth|colour u64 framebuffer at byte 31 200 144 of the render buffer, the RGBA8 surface,
+// and Stats::numVisible* — bit for bit for the same octree buffers and Uniforms.
+//
+// What is different is the work decomposition. The reference assigns one 256-thread block per
+// visible NODE (render.cu:181-207), so a 50 000-point leaf and a 200-voxel inner node cost one
+// block each, and every thread re-walks the node's chunk list. Here the LOD cut emits
+// CHUNK-granular work items (<= 1000 samples = 16 KB, contiguous), and persistent warps pull items
+// from one queue with a single atomicAdd each, read samples with coalesced 128-bit loads, and
+// splat with an early-out compare + 64-bit atomicMin (the 16.6 MB framebuffer stays L2-resident).
+//
+// Every floating-point value that decides a pixel or a visibility bit is computed with the exact
+// instruction sequence the reference's SASS uses (see fpmath.cuh and DESIGN.md §5).
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include "../../include/simlod_abi.h"
+#include "fpmath.cuh"
+
+namespace cg = cooperative_groups;
+
+typedef SimlodPoint Point;
+typedef SimlodChunk Chunk;
+typedef SimlodNode Node;
+typedef SimlodStats Stats;
+typedef SimlodUniforms Uniforms;
+typedef SimlodFloat4 Row;
+struct CudaPrint;
+
+// render-buffer layout. The framebuffer and the HQS targets sit where the reference's bump
+// allocator puts them (render.cu:1108-1123,172,224-231), so both kernels can be read back with
+// the same offsets; the area the reference uses for 100 000 Node copies holds our queues.
+namespace rbuf {
+constexpr uint64_t OFF_CTL       = 0;
+constexpr uint64_t OFF_ITEMS     = 4096;
+constexpr uint64_t OFF_FB        = 31200144;                       // 15 200 000 + 7*16 + 32 + 16 000 000
+constexpr uint64_t ITEM_CAP      = (OFF_FB - OFF_ITEMS) / 16;      // ~1.95 M chunk items = 1.9 G samples
+}
+
+struct WorkItem { uint64_t chunk; uint32_t count; uint32_t level; };   // 16 B
+
+struct RCtl {
+    uint32_t numItems;
+    uint32_t head[3];            // queue heads: single pass / HQS depth pass / HQS colour pass
+    uint32_t numVisibleNodes, numVisiblePoints, numVisibleVoxels, numVisibleInner, numVisibleLeaves;
+    uint32_t overflow;
+};
+
+__constant__ uint32_t SPECTRAL[8] = {0x4f3ed5, 0x436df4, 0x61aefd, 0x8be0fe, 0x98f5e6, 0xa4ddab, 0xa5c266, 0xbd8832};
+
+__device__ __forceinline__ uint32_t ldv(const uint32_t* p) { return *(volatile const uint32_t*)p; }
+__device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint64_t globaltimer() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+// mat4 row * (x, y, z, 1): y*r.y -> fma(x, r.x) -> fma(z, r.z) -> + r.w   (helper_math.h:1266 as contracted in the reference SASS)
+__device__ __forceinline__ float rowDot(const Row& r, float x, float y, float z) {
+    return fpx::add(r.w, fpx::fma(z, r.z, fpx::fma(x, r.x, fpx::mul(y, r.y))));
+}
+// dot(float3, float3) with the same contraction
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return fpx::fma(az, bz, fpx::fma(ax, bx, fpx::mul(ay, by)));
+}
+
+// ------------------------------------------------------------------------------------------
+// visibility, pass 1 (render.cu:762-901 + math.cuh:55-64,154-201)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool planeRejects(float px, float py, float pz, float pw,
+                                             float minx, float miny, float minz, float maxx, float maxy, float maxz) {
+    float len = fpx::sqrt_approx(dot3(px, py, pz, px, py, pz));        // length(): x*x + y*y + z*z, MUFU.SQRT
+    float inv = fpx::rcp(len);
+    float nx = fpx::mul_ftz(px, inv), ny = fpx::mul_ftz(py, inv), nz = fpx::mul_ftz(pz, inv);
+    float constant = fpx::mul_ftz(pw, inv);
+    float vx = nx > 0.0f ? maxx : minx;
+    float vy = ny > 0.0f ? maxy : miny;
+    float vz = nz > 0.0f ? maxz : minz;
+    float d = fpx::add(dot3(nx, ny, nz, vx, vy, vz), constant);
+    return d < 0.0f;
+}
+
+__device__ void computeVisibilityFlags(const Uniforms& u, Node* nodes, uint32_t numNodes, float cubeSize,
+                                       float cminx, float cminy, float cminz) {
+    const Row* T = u.transform_updateBound.rows;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < numNodes; n += stride) {
+        Node* node = &nodes[n];
+        uint32_t level = node->level;
+        float fx = fpx::u2f(node->X), fy = fpx::u2f(node->Y), fz = fpx::u2f(node->Z);
+        float nodeSize = fpx::mul_ftz(cubeSize, fpx::ex2(-fpx::u2f(level)));      // cubeSize / pow(2, level)
+        float mn[3] = {fpx::fma(nodeSize, fx, cminx), fpx::fma(nodeSize, fy, cminy), fpx::fma(nodeSize, fz, cminz)};
+        float mx[3] = {fpx::fma(nodeSize, fpx::add(fx, 1.0f), cminx), fpx::fma(nodeSize, fpx::add(fy, 1.0f), cminy),
+                       fpx::fma(nodeSize, fpx::add(fz, 1.0f), cminz)};
+
+        // screen-space bounding rectangle of the 8 corners (render.cu:783-818)
+        float sminx = 0, smaxx = 0, sminy = 0, smaxy = 0;
+#pragma unroll
+        for (int corner = 0; corner < 8; corner++) {
+            float x = (corner & 4) ? mx[0] : mn[0];
+            float y = (corner & 2) ? mx[1] : mn[1];
+            float z = (corner & 1) ? mx[2] : mn[2];
+            float w = rowDot(T[3], x, y, z);
+            float rw = fpx::rcp(w);
+            float sx = fpx::mul(u.width, fpx::fma(fpx::mul_ftz(rowDot(T[0], x, y, z), rw), 0.5f, 0.5f));
+            float sy = fpx::mul(u.height, fpx::fma(fpx::mul_ftz(rowDot(T[1], x, y, z), rw), 0.5f, 0.5f));
+            if (corner == 0) { sminx = smaxx = sx; sminy = smaxy = sy; }
+            else { sminx = fminf(sminx, sx); smaxx = fmaxf(smaxx, sx); sminy = fminf(sminy, sy); smaxy = fmaxf(smaxy, sy); }
+        }
+        float dx = fpx::sub(smaxx, sminx), dy = fpx::sub(smaxy, sminy);
+
+        // frustum planes rows[3] -+ rows[0..2] (math.cuh:175-182)
+        bool inFrustum = true;
+#pragma unroll
+        for (int p = 0; p < 6 && inFrustum; p++) {
+            const Row& a = T[3];
+            const Row& b = T[p == 0 || p == 1 ? 0 : (p == 2 || p == 3 ? 1 : 2)];
+            bool minus = (p == 0 || p == 3 || p == 4);
+            float px = minus ? fpx::sub(a.x, b.x) : fpx::add(a.x, b.x);
+            float py = minus ? fpx::sub(a.y, b.y) : fpx::add(a.y, b.y);
+            float pz = minus ? fpx::sub(a.z, b.z) : fpx::add(a.z, b.z);
+            float pw = minus ? fpx::sub(a.w, b.w) : fpx::add(a.w, b.w);
+            if (planeRejects(px, py, pz, pw, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2])) inFrustum = false;
+        }
+        bool hasSamples = node->numPoints > 0 || node->numVoxels > 0;
+        double limit = 2.0 * (double)u.minNodeSize;
+        node->visible = (inFrustum && hasSamples) ? 1 : 0;
+        node->isLarge = ((double)dx > limit || (double)dy > limit) ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// visibility, pass 2: LOD cut (render.cu:906-933) -> chunk-granular work items
+// ------------------------------------------------------------------------------------------
+__device__ void emitNode(RCtl* ctl, WorkItem* items, const Node* node) {
+    uint32_t numPoints = node->numPoints, numVoxels = node->numVoxels;
+    atomicAdd(&ctl->numVisibleNodes, 1u);
+    if (numPoints > 0) { atomicAdd(&ctl->numVisibleLeaves, 1u); atomicAdd(&ctl->numVisiblePoints, numPoints); }
+    else if (numVoxels > 0) { atomicAdd(&ctl->numVisibleInner, 1u); atomicAdd(&ctl->numVisibleVoxels, numVoxels); }
+    uint32_t nP = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+    uint32_t nV = (numVoxels + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+    if (nP + nV == 0) return;
+    uint32_t base = atomicAdd(&ctl->numItems, nP + nV);
+    if ((uint64_t)base + nP + nV > rbuf::ITEM_CAP) { atomicOr(&ctl->overflow, 1u); return; }
+    uint32_t level = node->level;
+    const Chunk* chunk = node->points;
+    for (uint32_t k = 0, left = numPoints; k < nP && chunk; k++, chunk = chunk->next) {
+        uint32_t cnt = left < SIMLOD_POINTS_PER_CHUNK ? left : SIMLOD_POINTS_PER_CHUNK;
+        items[base + k] = WorkItem{(uint64_t)chunk, cnt, level};
+        left -= cnt;
+    }
+    chunk = node->voxelChunks;
+    for (uint32_t k = 0, left = numVoxels; k < nV && chunk; k++, chunk = chunk->next) {
+        uint32_t cnt = left < SIMLOD_POINTS_PER_CHUNK ? left : SIMLOD_POINTS_PER_CHUNK;
+        items[base + nP + k] = WorkItem{(uint64_t)chunk, cnt, level};
+        left -= cnt;
+    }
+}
+
+__device__ __forceinline__ bool isLeaf(const Node* node) {
+    bool leaf = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) leaf = leaf && node->children[i] == nullptr;
+    return leaf;
+}
+
+__device__ void lodCut(RCtl* ctl, WorkItem* items, Node* nodes, uint32_t numNodes) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < numNodes; n += stride) {
+        const Node* node = &nodes[n];
+        if (!node->isLarge) continue;
+        if (!isLeaf(node)) {
+            for (int i = 0; i < 8; i++) {
+                const Node* child = node->children[i];
+                if (child == nullptr || child->isLarge || !child->visible) continue;
+                emitNode(ctl, items, child);
+            }
+        } else if (node->visible) {
+            emitNode(ctl, items, node);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// projection of one sample (render.cu:61-70)
+// ------------------------------------------------------------------------------------------
+struct Projected { int x, y; float depth; bool inside; };
+
+__device__ __forceinline__ Projected project(const Row* T, float width, float height, float px, float py, float pz) {
+    Projected r;
+    float w = rowDot(T[3], px, py, pz);
+    float rw = fpx::rcp(w);
+    float ndcx = fpx::mul_ftz(rowDot(T[0], px, py, pz), rw);
+    float ndcy = fpx::mul_ftz(rowDot(T[1], px, py, pz), rw);
+    double dw = (double)width, dh = (double)height;
+    r.x = fpx::d2i(fpx::dmul(fpx::dfma((double)ndcx, 0.5, 0.5), dw));       // int((ndc.x * 0.5 + 0.5) * width), in double
+    r.y = fpx::d2i(fpx::dmul(fpx::dfma((double)ndcy, 0.5, 0.5), dh));
+    r.depth = w;
+    r.inside = r.x > 1 && (double)r.x < fpx::dadd(dw, -2.0) && r.y > 1 && (double)r.y < fpx::dadd(dh, -2.0);
+    return r;
+}
+
+__device__ __forceinline__ uint32_t sampleColor(const Uniforms& u, uint32_t pointColor, uint32_t level) {
+    if (u.colorByLOD && !u.colorByNode) {                                    // render.cu:49-59,76-78
+        int index = fpx::f2i(fpx::mul((float)(8 - (int)level), 1.8f));
+        index = max(0, min(index, 7));
+        return SPECTRAL[index];
+    }
+    return pointColor;      // colorByNode (debug colouring by node id) is out of scope: see DESIGN.md
+}
+
+template <typename F>
+__device__ __forceinline__ void forEachSample(const WorkItem* items, uint32_t numItems, uint32_t* head, F&& f) {
+    const uint32_t lane = laneId();
+    for (;;) {
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(head, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= numItems) break;
+        WorkItem w = items[it];
+        const uint4* pts = reinterpret_cast<const uint4*>(w.chunk);
+        for (uint32_t i = lane; i < w.count; i += 32) {
+            uint4 p = pts[i];
+            f(p, w.level);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel_render
+// ------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(256, 4)
+kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfaceObject_t gl_colorbuffer,
+              Stats* stats, uint64_t* frameStartTimestamp, CudaPrint* cudaprint) {
+    cg::grid_group grid = cg::this_grid();
+    const bool first = grid.thread_rank() == 0;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gstride = gridDim.x * blockDim.x;
+
+    uint8_t* base = reinterpret_cast<uint8_t*>(buffer);
+    RCtl* ctl = reinterpret_cast<RCtl*>(base + rbuf::OFF_CTL);
+    WorkItem* items = reinterpret_cast<WorkItem*>(base + rbuf::OFF_ITEMS);
+    uint64_t* framebuffer = reinterpret_cast<uint64_t*>(base + rbuf::OFF_FB);
+
+    const int width = fpx::f2i(uniforms.width), height = fpx::f2i(uniforms.height);
+    const uint32_t numPixels = (uint32_t)(width * height);
+    // HQS targets follow the framebuffer (render.cu:172,224-231: 4-byte counter rounded to 16, depth, colour)
+    const uint64_t fbBytes = (uint64_t)numPixels * 8;
+    uint32_t* fb_depth = reinterpret_cast<uint32_t*>(base + rbuf::OFF_FB + ((fbBytes + 15) & ~15ull) + 16);
+    uint32_t* fb_color = fb_depth + (((uint64_t)numPixels * 4 + 15) & ~15ull) / 4;
+    const bool hqs = uniforms.useHighQualityShading != 0;
+
+    if (first) {
+        *frameStartTimestamp = globaltimer();
+        ctl->numItems = 0; ctl->head[0] = 0; ctl->head[1] = 0; ctl->head[2] = 0;
+        ctl->numVisibleNodes = 0; ctl->numVisiblePoints = 0; ctl->numVisibleVoxels = 0;
+        ctl->numVisibleInner = 0; ctl->numVisibleLeaves = 0; ctl->overflow = 0;
+    }
+    // clear: depth = +inf (0x7f800000), colour = 0x00332211 (render.cu:1126-1131)
+    {
+        const uint64_t clearValue = (0x7f800000ull << 32) | 0x00332211ull;
+        ulonglong2* fb2 = reinterpret_cast<ulonglong2*>(framebuffer);
+        for (uint32_t i = gtid; i < numPixels / 2; i += gstride) fb2[i] = make_ulonglong2(clearValue, clearValue);
+        if ((numPixels & 1) && first) framebuffer[numPixels - 1] = clearValue;
+        if (hqs && uniforms.showPoints) {
+            for (uint32_t i = gtid; i < numPixels; i += gstride) fb_depth[i] = 0x7f800000u;
+            uint4* c4 = reinterpret_cast<uint4*>(fb_color);
+            for (uint32_t i = gtid; i < numPixels; i += gstride) c4[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    grid.sync();
+
+    float bsx = fpx::sub(uniforms.boxMax[0], uniforms.boxMin[0]);
+    float bsy = fpx::sub(uniforms.boxMax[1], uniforms.boxMin[1]);
+    float bsz = fpx::sub(uniforms.boxMax[2], uniforms.boxMin[2]);
+    float cubeSize = fmaxf(fmaxf(bsx, bsy), bsz);
+    const uint32_t numNodes = ldv(&stats->numNodes);
+
+    computeVisibilityFlags(uniforms, nodes, numNodes, cubeSize, uniforms.boxMin[0], uniforms.boxMin[1], uniforms.boxMin[2]);
+    grid.sync();
+    lodCut(ctl, items, nodes, numNodes);
+    grid.sync();
+
+    const uint32_t numItems = min(ldv(&ctl->numItems), (uint32_t)rbuf::ITEM_CAP);
+    const Row* T = uniforms.transform.rows;
+    const int pointSize = uniforms.pointSize;
+
+    if (uniforms.showPoints && !hqs) {
+        // single pass: depth|colour packed in 64 bits, atomicMin (render.cu:61-104,161-210)
+        forEachSample(items, numItems, &ctl->head[0], [&](uint4 p, uint32_t level) {
+            Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
+            if (!pr.inside) return;
+            uint64_t encoded = ((uint64_t)__float_as_uint(pr.depth) << 32) | sampleColor(uniforms, p.w, level);
+            for (int ox = 0; ox < pointSize; ox++)
+            for (int oy = 0; oy < pointSize; oy++) {
+                uint32_t qx = (uint32_t)max(0, min(pr.x + ox, width));        // clamp bounds are inclusive (render.cu:91-92)
+                uint32_t qy = (uint32_t)max(0, min(pr.y + oy, height));
+                uint32_t pixelID = qx + (uint32_t)width * qy;
+                if (encoded < framebuffer[pixelID]) atomicMin(reinterpret_cast<unsigned long long*>(&framebuffer[pixelID]), (unsigned long long)encoded);
+            }
+        });
+    } else if (uniforms.showPoints && hqs) {
+        // pass 1: closest depth per pixel (render.cu:247-391)
+        forEachSample(items, numItems, &ctl->head[1], [&](uint4 p, uint32_t level) {
+            Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
+            if (!pr.inside || !(pr.depth > 0.0f)) return;
+            uint32_t udepth = __float_as_uint(pr.depth);
+            for (int ox = 0; ox < pointSize; ox++)
+            for (int oy = 0; oy < pointSize; oy++) {
+                uint32_t qx = (uint32_t)max(0, min(pr.x + ox, width));
+                uint32_t qy = (uint32_t)max(0, min(pr.y + oy, height));
+                uint32_t pixelID = qx + (uint32_t)width * qy;
+                if (udepth < fb_depth[pixelID]) atomicMin(&fb_depth[pixelID], udepth);
+            }
+        });
+        grid.sync();
+        // pass 2: accumulate colours of samples within 1 % of the closest depth (render.cu:406-602)
+        forEachSample(items, numItems, &ctl->head[2], [&](uint4 p, uint32_t level) {
+            Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
+            if (!pr.inside || !(pr.depth > 0.0f)) return;
+            uint32_t color = sampleColor(uniforms, p.w, level);
+            for (int ox = 0; ox < pointSize; ox++)
+            for (int oy = 0; oy < pointSize; oy++) {
+                uint32_t qx = (uint32_t)max(0, min(pr.x + ox, width));
+                uint32_t qy = (uint32_t)max(0, min(pr.y + oy, height));
+                uint32_t pixelID = qx + (uint32_t)width * qy;
+                float fbDepth = __uint_as_float(fb_depth[pixelID]);
+                if (pr.depth < fpx::mul(fbDepth, 1.01f)) {
+                    atomicAdd(&fb_color[4 * pixelID + 0], color & 0xffu);
+                    atomicAdd(&fb_color[4 * pixelID + 1], (color >> 8) & 0xffu);
+                    atomicAdd(&fb_color[4 * pixelID + 2], (color >> 16) & 0xffu);
+                    atomicAdd(&fb_color[4 * pixelID + 3], 1u);
+                }
+            }
+        });
+        grid.sync();
+        // resolve (render.cu:606-632)
+        for (uint32_t i = gtid; i < numPixels; i += gstride) {
+            uint4 acc = reinterpret_cast<const uint4*>(fb_color)[i];
+            if (acc.w == 0) continue;
+            uint32_t color = ((acc.x / acc.w) & 0xffu) | (((acc.y / acc.w) & 0xffu) << 8) | (((acc.z / acc.w) & 0xffu) << 16) | 0xff000000u;
+            framebuffer[i] = ((uint64_t)fb_depth[i] << 32) | color;
+        }
+    }
+    grid.sync();
+
+    // the line/bounding-box overlay of the reference (render.cu:1197-1233) is empty unless
+    // showBoundingBox is set; it is a debug overlay and not part of this path.
+
+    if (first) {      // render.cu:1244-1252
+        stats->numVisibleNodes = ldv(&ctl->numVisibleNodes);
+        stats->numVisibleInner = ldv(&ctl->numVisibleInner);
+        stats->numVisibleLeaves = ldv(&ctl->numVisibleLeaves);
+        stats->numVisiblePoints = ldv(&ctl->numVisiblePoints);
+        stats->numVisibleVoxels = ldv(&ctl->numVisibleVoxels);
+        stats->frameID = (uint32_t)uniforms.frameCounter;
+    }
+
+    // eye-dome lighting over 16x16 tiles (render.cu:1255-1325). Always on; covers
+    // floor(numTiles / gridDim.x) * gridDim.x tiles (sic: the remainder keeps its raw colour).
+    {
+        struct Pixel { uint32_t color; float depth; };
+        Pixel* fbp = reinterpret_cast<Pixel*>(framebuffer);
+        const uint32_t tileSize = 16;
+        const uint32_t numTilesX = (uint32_t)width / tileSize, numTilesY = (uint32_t)height / tileSize;
+        const uint32_t numTiles = numTilesX * numTilesY;
+        const uint32_t tilesPerBlock = numTiles / gridDim.x;
+        for (uint32_t i = 0; i < tilesPerBlock; i++) {
+            __syncthreads();
+            int tileID = (int)(i * gridDim.x + blockIdx.x);
+            int tileX = tileID % (int)numTilesX, tileY = tileID / (int)numTilesX;
+            int tileStart = tileX * (int)tileSize + tileY * width * (int)tileSize;
+            int pixelID = tileStart + (int)(threadIdx.x % tileSize) + (int)(threadIdx.x / tileSize) * width;
+            Pixel pixel = fbp[pixelID];
+            float lp = fpx::lg2(pixel.depth);
+            float sum = 0.0f;
+            const int offs[4] = {width, 1, -width, -1};           // int(1.5*sin(u)) + width*int(1.5*cos(u)), u = 0, PI/2, PI, 3PI/2
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int index = pixelID + offs[k];
+                index = max(index, 0);
+                index = min(index, width * height);
+                float nd = fbp[index].depth;
+                double diff = (double)fpx::add(lp, -fpx::lg2(nd));
+                sum = (float)fpx::dadd((double)sum, fmax(diff, 0.0));
+            }
+            float response = fpx::mul_ftz(sum, 0.02f);                         // sum / numSamples(50)
+            float e = (float)fpx::dmul(fpx::dmul((double)response, 300.0), (double)0.4f);
+            float shade = fpx::ex2(fpx::mul(e, -1.4426950216293334961f));     // __expf(-response * 300.0 * edlStrength)
+            uint32_t R = fpx::f2u(fpx::mul(shade, (float)(pixel.color & 0xffu)));
+            uint32_t G = fpx::f2u(fpx::mul(shade, (float)((pixel.color >> 8) & 0xffu)));
+            uint32_t B = fpx::f2u(fpx::mul(shade, (float)((pixel.color >> 16) & 0xffu)));
+            fbp[pixelID].color = R | (G << 8) | (B << 16) | 0xff000000u;
+            __syncthreads();
+        }
+    }
+    grid.sync();
+
+    // colour -> RGBA8 surface (render.cu:1334-1343)
+    for (uint32_t i = gtid; i < numPixels; i += gstride) {
+        int x = (int)(i % (uint32_t)width), y = (int)(i / (uint32_t)width);
+        surf2Dwrite((uint32_t)(framebuffer[i] & 0xffffffffull), gl_colorbuffer, x * 4, y);
+    }
+}

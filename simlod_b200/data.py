@@ -1,0 +1,149 @@
+"""Synthetic point streams for the benchmark configurations.
+
+There is no network and no Morro Bay file on the box, so every configuration is generated:
+  uniform_cube   config 1: N uniform-random points in a 2^k cube, one batch
+  terrain        configs 2/3/5: fBm height field 4800 x 4300 x 300 m emitted in 50 m flight strips
+                 (spatially coherent 1 M-point batches, as LiDAR is; the reference's spill buffers
+                 rely on that coherence)
+  shell          config 4: sphere shell in a 4096^3 cube, latitude/longitude tile order
+All generators are counter-based (splitmix64 of the point index), so any sub-range can be produced
+independently (per batch, per rank) and a CPU check sees exactly the bytes the GPU saw.
+"""
+import numpy as np
+
+from .api import POINT_DTYPE
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+
+def _uniform24(counter):
+    """24-bit uniform in [0, 1), exactly representable in float32."""
+    return (splitmix64(counter) >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)
+
+
+def _counters(seed, first, count, lanes):
+    with np.errstate(over="ignore"):
+        base = (np.uint64(seed) << np.uint64(32)) + (np.arange(first, first + count, dtype=np.uint64) * np.uint64(lanes))
+    return base
+
+
+def uniform_cube(n, size=1024.0, seed=42, first=0):
+    """Config 1. Cube [0,size)^3 with size a power of two (exact reciprocal on CPU and GPU)."""
+    with np.errstate(over="ignore"):
+        c = _counters(seed, first, n, 4)
+        pts = np.empty(n, dtype=POINT_DTYPE)
+        pts["x"] = _uniform24(c) * np.float32(size)
+        pts["y"] = _uniform24(c + np.uint64(1)) * np.float32(size)
+        pts["z"] = _uniform24(c + np.uint64(2)) * np.float32(size)
+        pts["color"] = (splitmix64(c + np.uint64(3)) & np.uint64(0xFFFFFF)).astype(np.uint32) | np.uint32(0xFF000000)
+    return pts, (0.0, 0.0, 0.0), (float(size), float(size), float(size))
+
+
+# ---- terrain (Morro Bay stand-in) -------------------------------------------------------------
+TERRAIN_EXTENT = (4800.0, 4300.0, 300.0)
+_STRIP_WIDTH = 50.0
+
+
+def _hash2(ix, iy, seed):
+    with np.errstate(over="ignore"):
+        k = (ix.astype(np.uint64) * np.uint64(0x9E3779B1)) ^ (iy.astype(np.uint64) * np.uint64(0x85EBCA77)) ^ np.uint64(seed)
+    return (splitmix64(k) >> np.uint64(40)).astype(np.float64) * (2.0 ** -24)
+
+
+def _value_noise(x, y, seed):
+    ix, iy = np.floor(x), np.floor(y)
+    fx, fy = x - ix, y - iy
+    ix, iy = ix.astype(np.int64), iy.astype(np.int64)
+    sx, sy = fx * fx * (3 - 2 * fx), fy * fy * (3 - 2 * fy)
+    v00, v10 = _hash2(ix, iy, seed), _hash2(ix + 1, iy, seed)
+    v01, v11 = _hash2(ix, iy + 1, seed), _hash2(ix + 1, iy + 1, seed)
+    return (v00 * (1 - sx) + v10 * sx) * (1 - sy) + (v01 * (1 - sx) + v11 * sx) * sy
+
+
+def terrain_height(x, y, seed=7):
+    h = np.zeros_like(x, dtype=np.float64)
+    amp, freq, norm = 1.0, 1.0 / 1600.0, 0.0
+    for octave in range(5):
+        h += amp * _value_noise(x * freq, y * freq, seed + 101 * octave)
+        norm += amp
+        amp *= 0.5
+        freq *= 2.0
+    return (h / norm) * (TERRAIN_EXTENT[2] - 1.0)
+
+
+def terrain(n_total, first=0, count=None, seed=7):
+    """Points first..first+count of an n_total-point scan of the synthetic terrain.
+
+    The scan covers the 4800 x 4300 m area in 96 flight strips of 50 m; within a strip points
+    advance along y and scatter across the strip, so consecutive 1 M-point batches cover compact
+    patches. z = fBm height + 0.2 m scanner noise; colour = height ramp. boxMin = 0 (the loaders
+    translate to the file's min, tools/las2simlod.mjs:130-132)."""
+    count = n_total - first if count is None else count
+    i = np.arange(first, first + count, dtype=np.uint64)
+    num_strips = int(TERRAIN_EXTENT[0] / _STRIP_WIDTH)
+    per_strip = -(-n_total // num_strips)
+    strip = (i // np.uint64(per_strip)).astype(np.float64)
+    t = (i % np.uint64(per_strip)).astype(np.float64) / float(per_strip)
+    with np.errstate(over="ignore"):
+        c = (np.uint64(seed) << np.uint64(40)) + i * np.uint64(4)
+        u0 = _uniform24(c).astype(np.float64)
+        u1 = _uniform24(c + np.uint64(1)).astype(np.float64)
+        u2 = _uniform24(c + np.uint64(2)).astype(np.float64)
+    x = np.minimum((strip + u0) * _STRIP_WIDTH, TERRAIN_EXTENT[0] - 0.01)
+    # serpentine flight lines; a few metres of along-track jitter
+    along = np.where((strip.astype(np.int64) & 1) == 0, t, 1.0 - t)
+    y = np.clip(along * TERRAIN_EXTENT[1] + (u1 - 0.5) * 4.0, 0.0, TERRAIN_EXTENT[1] - 0.01)
+    z = np.clip(terrain_height(x, y, seed) + (u2 - 0.5) * 0.4, 0.0, TERRAIN_EXTENT[2] - 0.01)
+    pts = np.empty(count, dtype=POINT_DTYPE)
+    pts["x"], pts["y"], pts["z"] = x.astype(np.float32), y.astype(np.float32), z.astype(np.float32)
+    hn = np.clip(z / TERRAIN_EXTENT[2], 0.0, 1.0)
+    r = (40 + 200 * hn).astype(np.uint32)
+    g = (90 + 140 * (1.0 - np.abs(hn - 0.5) * 2.0)).astype(np.uint32)
+    b = (60 + 120 * (1.0 - hn)).astype(np.uint32)
+    pts["color"] = r | (g << np.uint32(8)) | (b << np.uint32(16)) | np.uint32(0xFF000000)
+    return pts, (0.0, 0.0, 0.0), TERRAIN_EXTENT
+
+
+# ---- sphere shell (config 4) --------------------------------------------------------------------
+SHELL_CUBE = 4096.0
+
+
+def shell(n_total, first=0, count=None, seed=1234, tiles_lat=64, tiles_lon=128):
+    """Sphere shell R = 1800 +- 0.25 centred in a 4096^3 cube, emitted tile by tile in latitude /
+    longitude order (equal-area tiles), so that 1 M-point batches cover compact patches."""
+    count = n_total - first if count is None else count
+    i = np.arange(first, first + count, dtype=np.uint64)
+    num_tiles = tiles_lat * tiles_lon
+    per_tile = -(-n_total // num_tiles)
+    tile = (i // np.uint64(per_tile)).astype(np.int64)
+    tlat, tlon = tile // tiles_lon, tile % tiles_lon
+    with np.errstate(over="ignore"):
+        c = (np.uint64(seed) << np.uint64(40)) + i * np.uint64(4)
+        u0 = _uniform24(c).astype(np.float64)
+        u1 = _uniform24(c + np.uint64(1)).astype(np.float64)
+        u2 = _uniform24(c + np.uint64(2)).astype(np.float64)
+        col = (splitmix64(c + np.uint64(3)) & np.uint64(0xFFFFFF)).astype(np.uint32)
+    cz = -1.0 + 2.0 * (tlat + u0) / tiles_lat             # equal-area in z
+    phi = 2.0 * np.pi * (tlon + u1) / tiles_lon
+    r = 1800.0 + (u2 - 0.5) * 0.5
+    s = np.sqrt(np.maximum(0.0, 1.0 - cz * cz))
+    ctr = SHELL_CUBE / 2
+    pts = np.empty(count, dtype=POINT_DTYPE)
+    pts["x"] = (ctr + r * s * np.cos(phi)).astype(np.float32)
+    pts["y"] = (ctr + r * s * np.sin(phi)).astype(np.float32)
+    pts["z"] = (ctr + r * cz).astype(np.float32)
+    pts["color"] = col | np.uint32(0xFF000000)
+    return pts, (0.0, 0.0, 0.0), (SHELL_CUBE, SHELL_CUBE, SHELL_CUBE)
+
+
+def batches(points, batch_size=1_000_000):
+    for s in range(0, points.shape[0], batch_size):
+        yield points[s:s + batch_size]
