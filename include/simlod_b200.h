@@ -79,10 +79,12 @@ int simlod_update_octree(SimlodContext* ctx, float* kernel_ms);
 
 // The main loop's streaming behaviour (main.cpp:1176-1180 + uploader thread) for a point set in
 // host memory: uploads in 1 000 000-point batches overlapped with update launches until every
-// point is inserted. *kernel_ms (optional) = sum of kernel_construct event times.
-int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t count, float* kernel_ms);
+// point is inserted. *kernel_ms (optional) = sum of kernel_construct event times (the reference's
+// "points/sec update kernel" denominator, main.cpp:1484); *total_ms (optional) = device time from
+// the first upload to the end of the last launch, measured with an event pair on the launch stream.
+int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t count, float* kernel_ms, float* total_ms);
 // same with the whole point set resident in device memory (batches are copied device-to-device)
-int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms);
+int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms, float* total_ms);
 
 // renderCUDA (main.cpp:465-546): one cooperative launch of kernel_render into the surface.
 int simlod_render(SimlodContext* ctx, float* kernel_ms);

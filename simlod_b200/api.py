@@ -130,8 +130,8 @@ def load_library():
         "simlod_upload_batch": [vp, vp, u32],
         "simlod_upload_batch_device": [vp, u64, u32],
         "simlod_update_octree": [vp, C.POINTER(C.c_float)],
-        "simlod_insert": [vp, vp, u64, C.POINTER(C.c_float)],
-        "simlod_insert_device": [vp, u64, u64, C.POINTER(C.c_float)],
+        "simlod_insert": [vp, vp, u64, C.POINTER(C.c_float), C.POINTER(C.c_float)],
+        "simlod_insert_device": [vp, u64, u64, C.POINTER(C.c_float), C.POINTER(C.c_float)],
         "simlod_render": [vp, C.POINTER(C.c_float)],
         "simlod_get_stats": [vp, C.POINTER(Stats)],
         "simlod_read_framebuffer": [vp, vp],
@@ -283,21 +283,20 @@ class SimLOD:
         return ms.value
 
     def insert(self, points):
-        """Stream a host point set through the ring in 1 M-point batches; returns summed kernel ms."""
+        """Stream a host point set through the ring in 1 M-point batches (uploads overlap the update
+        launches). Returns (summed kernel ms, total device ms)."""
         pts = _as_points(points)
-        ms = C.c_float(0)
-        self._check(self._lib.simlod_insert(self._ctx, pts.ctypes.data, pts.shape[0], C.byref(ms)))
-        return ms.value
+        return self.insert_host_ptr(pts.ctypes.data, pts.shape[0])
 
     def insert_host_ptr(self, host_ptr, count):
-        ms = C.c_float(0)
-        self._check(self._lib.simlod_insert(self._ctx, int(host_ptr), int(count), C.byref(ms)))
-        return ms.value
+        kms, tms = C.c_float(0), C.c_float(0)
+        self._check(self._lib.simlod_insert(self._ctx, int(host_ptr), int(count), C.byref(kms), C.byref(tms)))
+        return kms.value, tms.value
 
     def insert_device(self, device_ptr, count):
-        ms = C.c_float(0)
-        self._check(self._lib.simlod_insert_device(self._ctx, int(device_ptr), int(count), C.byref(ms)))
-        return ms.value
+        kms, tms = C.c_float(0), C.c_float(0)
+        self._check(self._lib.simlod_insert_device(self._ctx, int(device_ptr), int(count), C.byref(kms), C.byref(tms)))
+        return kms.value, tms.value
 
     def insert_batches(self, batches):
         """Insert explicit batches (each <= 1 M points), each followed by update launches until the

@@ -94,6 +94,8 @@ struct Ctl {
     uint32_t workCounter;
     uint32_t _pad;
     uint32_t statCounters[8];
+    uint64_t spilledTotal;         // spilled (re-inserted) points since the last reset: the `s` of the roofline's 32*s bytes
+    uint64_t voxelsTotal;          // voxels created since the last reset (incl. leaf-root voxels)
 };
 
 struct DirEntry { uint32_t base; uint32_t k0; };   // chunkDir[base + (slot/1000 - k0)] holds element `slot`
@@ -603,6 +605,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         c.ctl->numDirtyLeaves = 0; c.ctl->numDirtyVox = 0; c.ctl->dirCursor = 0; c.ctl->workCounter = 0;
         for (int i = 0; i < 8; i++) c.ctl->statCounters[i] = 0;
         if (stats->batchletIndex == 0) {       // fresh after the reset kernel: the tree is the root alone
+            c.ctl->spilledTotal = 0; c.ctl->voxelsTotal = 0;
             c.firstChild[0] = 0;
             c.gridPtr[0] = (uint64_t)nodes[0].grid;
         }
@@ -676,6 +679,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         if (first) {
             stats->batchletIndex = batchIndex + 1;
             stats->numPointsProcessed += batchSize;
+            c.ctl->spilledTotal += numSpilled; c.ctl->voxelsTotal += numVoxels;
             c.ctl->elapsedNanos = globaltimer() - tStart;
             c.ctl->numSpillTotal = 0; c.ctl->numSpilled = 0; c.ctl->numBacklog = 0;
             c.ctl->numDirtyLeaves = 0; c.ctl->numDirtyVox = 0; c.ctl->dirCursor = 0; c.ctl->workCounter = 0;

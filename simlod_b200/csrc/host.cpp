@@ -96,7 +96,7 @@ struct SimlodContext {
     CUcontext primary = nullptr;
     int numSMs = 0;
     CUstream streamMain = nullptr, streamUpload = nullptr;
-    CUevent evStart = nullptr, evEnd = nullptr;
+    CUevent evStart = nullptr, evEnd = nullptr, evTotalStart = nullptr, evTotalEnd = nullptr;
     SimlodConfig cfg{};
     SimlodUniforms uniforms{};
     SimlodBuffers buf{};
@@ -235,6 +235,8 @@ int simlod_create(const SimlodConfig* config, SimlodContext** out) {
     CU(D(cuStreamCreate)(&ctx->streamUpload, CU_STREAM_NON_BLOCKING));      // main.cpp:276
     CU(D(cuEventCreate)(&ctx->evStart, CU_EVENT_DEFAULT));
     CU(D(cuEventCreate)(&ctx->evEnd, CU_EVENT_DEFAULT));
+    CU(D(cuEventCreate)(&ctx->evTotalStart, CU_EVENT_DEFAULT));
+    CU(D(cuEventCreate)(&ctx->evTotalEnd, CU_EVENT_DEFAULT));
 
     // programs (main.cpp:603-626)
     for (int p = 0; p < 3; p++) {
@@ -315,6 +317,8 @@ void simlod_destroy(SimlodContext* ctx) {
         if (ctx->utilModule) D(cuModuleUnload)(ctx->utilModule);
         if (ctx->evStart) D(cuEventDestroy)(ctx->evStart);
         if (ctx->evEnd) D(cuEventDestroy)(ctx->evEnd);
+        if (ctx->evTotalStart) D(cuEventDestroy)(ctx->evTotalStart);
+        if (ctx->evTotalEnd) D(cuEventDestroy)(ctx->evTotalEnd);
         if (ctx->streamMain) D(cuStreamDestroy)(ctx->streamMain);
         if (ctx->streamUpload) D(cuStreamDestroy)(ctx->streamUpload);
         D(cuDevicePrimaryCtxRelease)(ctx->device);
@@ -404,13 +408,14 @@ int simlod_update_octree(SimlodContext* ctx, float* kernel_ms) {
     return readStats(ctx);
 }
 
-static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr dev, uint64_t count, float* kernel_ms) {
+static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr dev, uint64_t count, float* kernel_ms, float* total_ms) {
     int rc = setCurrent(ctx); if (rc) return rc;
     const uint64_t numBatches = (count + SLOT_POINTS - 1) / SLOT_POINTS;
     rc = readStats(ctx); if (rc) return rc;
     const uint32_t target = ctx->uploaded + (uint32_t)numBatches;
     uint64_t next = 0;
     float total = 0.0f;
+    CU(D(cuEventRecord)(ctx->evTotalStart, ctx->streamMain));
     while (ctx->processed < target) {
         // uploader: keep the ring as full as back-pressure allows (main.cpp:1012,1033-1056)
         while (next < numBatches && ctx->uploaded - ctx->processed < RING_SLOTS) {
@@ -426,17 +431,20 @@ static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr
         rc = readStats(ctx); if (rc) return rc;
         if (ctx->hStats->memCapacityReached) return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed);
     }
+    CU(D(cuEventRecord)(ctx->evTotalEnd, ctx->streamMain));
+    CU(D(cuEventSynchronize)(ctx->evTotalEnd));
     if (kernel_ms) *kernel_ms = total;
+    if (total_ms) CU(D(cuEventElapsedTime)(total_ms, ctx->evTotalStart, ctx->evTotalEnd));
     return SIMLOD_OK;
 }
 
-int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t count, float* kernel_ms) {
+int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t count, float* kernel_ms, float* total_ms) {
     if (!host_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
-    return insertCommon(ctx, host_points, 0, count, kernel_ms);
+    return insertCommon(ctx, host_points, 0, count, kernel_ms, total_ms);
 }
-int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms) {
+int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms, float* total_ms) {
     if (!device_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
-    return insertCommon(ctx, nullptr, (CUdeviceptr)device_points, count, kernel_ms);
+    return insertCommon(ctx, nullptr, (CUdeviceptr)device_points, count, kernel_ms, total_ms);
 }
 
 int simlod_render(SimlodContext* ctx, float* kernel_ms) {
