@@ -17,7 +17,7 @@
 //   chunk lists walked i/1000 hops per point/voxel      per-batch chunk directory: O(1) address per element
 //   one thread walks/extends each node's list           tail pointers kept per node; only dirty nodes visited
 //   1 global atomic per created voxel (backlog)         one atomic per warp per level (ballot-aggregated)
-//   >= 24 grid-wide barriers per batch                  5 (+4 per split round)
+//   >= 24 grid-wide barriers per batch                  3 (+2 per split round)
 //
 // The scratch ("momentary") buffer is carved with our own layout (Scratch below); it fits in
 // the 300 000 000 bytes the unmodified host allocates (main_progressive_octree.cpp:554),
@@ -50,18 +50,22 @@ constexpr uint64_t DIR_CAP        = 1ull << 20;        // chunk directory entrie
 constexpr uint64_t QUEUE_CAP      = 4ull << 20;        // free-chunk stack (reference: 1 M)
 constexpr uint64_t SPILLNODE_CAP  = 100000;            // voxels.cu:847
 
+constexpr uint64_t ROW_CAP        = 65536;             // leaves that hold points at the same time (x 64 chunk slots)
+constexpr uint64_t ROW_SLOTS      = 64;                // chunk pointers per leaf row (a leaf holds <= 50 chunks)
+
 constexpr uint64_t align256(uint64_t x) { return (x + 255) & ~255ull; }
 constexpr uint64_t OFF_CTL        = 0;
 constexpr uint64_t OFF_FIRSTCHILD = 4096;
 constexpr uint64_t OFF_GRIDPTR    = align256(OFF_FIRSTCHILD + NODE_CAP * 4);
-constexpr uint64_t OFF_PTAIL      = align256(OFF_GRIDPTR + NODE_CAP * 8);
-constexpr uint64_t OFF_VTAIL      = align256(OFF_PTAIL + NODE_CAP * 8);
-constexpr uint64_t OFF_PDIR       = align256(OFF_VTAIL + NODE_CAP * 8);
-constexpr uint64_t OFF_VDIR       = align256(OFF_PDIR + NODE_CAP * 8);
+constexpr uint64_t OFF_LEAFROW    = align256(OFF_GRIDPTR + NODE_CAP * 8);
+constexpr uint64_t OFF_VTAIL      = align256(OFF_LEAFROW + NODE_CAP * 4);
+constexpr uint64_t OFF_VDIR       = align256(OFF_VTAIL + NODE_CAP * 8);
 constexpr uint64_t OFF_DIRTYLEAF  = align256(OFF_VDIR + NODE_CAP * 8);
 constexpr uint64_t OFF_DIRTYVOX   = align256(OFF_DIRTYLEAF + NODE_CAP * 4);
-constexpr uint64_t OFF_SPILLNODES = align256(OFF_DIRTYVOX + NODE_CAP * 4);
-constexpr uint64_t OFF_CHUNKDIR   = align256(OFF_SPILLNODES + SPILLNODE_CAP * 4);
+constexpr uint64_t OFF_SPILLINFO  = align256(OFF_DIRTYVOX + NODE_CAP * 4);
+constexpr uint64_t OFF_ROWFREE    = align256(OFF_SPILLINFO + SPILLNODE_CAP * 32);
+constexpr uint64_t OFF_ROWS       = align256(OFF_ROWFREE + ROW_CAP * 4);
+constexpr uint64_t OFF_CHUNKDIR   = align256(OFF_ROWS + ROW_CAP * ROW_SLOTS * 8);
 constexpr uint64_t OFF_QUEUE      = align256(OFF_CHUNKDIR + DIR_CAP * 8);
 constexpr uint64_t OFF_LEAFOF     = align256(OFF_QUEUE + QUEUE_CAP * 8);
 constexpr uint64_t OFF_SLOTOF     = align256(OFF_LEAFOF + ITEM_CAP * 4);
@@ -79,24 +83,45 @@ enum : uint32_t {   // Ctl::errorFlags, mirrored into Stats::dbg
     ERR_NODE_OVERFLOW   = 1u << 3,   // nodes[] capacity exceeded
     ERR_QUEUE_OVERFLOW  = 1u << 4,
     ERR_SPILLNODE_OVERFLOW = 1u << 5,
+    ERR_ROW_OVERFLOW    = 1u << 6,   // more than ROW_CAP non-empty leaves, or a leaf with more than 64 chunks
 };
 
-struct Ctl {
-    uint32_t numBatchesUploaded;   // snapshot of the volatile host-updated counter (voxels.cu:872-876)
-    uint32_t errorFlags;
-    uint64_t elapsedNanos;
+struct BatchCounters {              // one set per batch parity: batch b uses set b & 1, the other one is cleared meanwhile
     uint32_t numSpillTotal;        // spilling nodes found so far in this batch (monotonic)
     uint32_t numSpilled;           // spilled points in this batch
     uint32_t numBacklog;           // voxels created in this batch
     uint32_t numDirtyLeaves;
     uint32_t numDirtyVox;
     uint32_t dirCursor;
-    uint32_t workCounter;
-    uint32_t _pad;
-    uint32_t statCounters[8];
-    uint64_t spilledTotal;         // spilled (re-inserted) points since the last reset: the `s` of the roofline's 32*s bytes
-    uint64_t voxelsTotal;          // voxels created since the last reset (incl. leaf-root voxels)
+    uint32_t _pad[2];
 };
+
+struct Ctl {
+    uint32_t numBatchesUploaded;   // snapshot of the volatile host-updated counter (voxels.cu:872-876)
+    uint32_t errorFlags;
+    uint64_t elapsedNanos;
+    uint64_t memUsed;              // heap offset snapshot for the capacity guard
+    uint32_t rowBump;              // leaf rows handed out so far (persistent across launches)
+    uint32_t rowFreeCount;         // entries on the row free stack (persistent)
+    uint32_t statCounters[8];      // @32
+    uint64_t _reserved[2];         // @64
+    uint64_t spilledTotal;         // @80 spilled (re-inserted) points since the last reset: the `s` of the roofline's 32*s bytes
+    uint64_t voxelsTotal;          // @88 voxels created since the last reset (incl. leaf-root voxels)
+    BatchCounters batch[2];        // @96
+};
+static_assert(offsetof(Ctl, spilledTotal) == 80, "bench.py reads Ctl::spilledTotal at byte 80");
+
+// what the lane that sees a leaf cross 50 000 records about it (everything the split round needs)
+struct SpillInfo {
+    uint32_t node;
+    uint32_t stored;       // points the leaf held before this batch
+    uint32_t base;         // where they go in the spill buffer
+    uint32_t row;          // the leaf's chunk row (+1)
+    uint32_t childBase;    // index of child 0
+    uint32_t level;
+    uint64_t grid;         // occupancy grid of the new inner node
+};
+static_assert(sizeof(SpillInfo) == 32, "SpillInfo");
 
 struct DirEntry { uint32_t base; uint32_t k0; };   // chunkDir[base + (slot/1000 - k0)] holds element `slot`
 
@@ -108,13 +133,15 @@ struct Ctx {
     Ctl*       ctl;
     uint32_t*  firstChild;    // node -> index of child 0 (children are 8 consecutive nodes); 0 = leaf
     uint64_t*  gridPtr;       // node -> OccupancyGrid* (0 = none)
-    uint64_t*  pointTail;     // node -> last Chunk* of points list (valid iff node.points != 0)
+    BatchCounters* bc;        // counters of the batch in flight
+    uint32_t*  leafRow;       // leaf -> row of its chunk pointers (+1; 0 = leaf holds no chunk)
+    uint64_t*  rows;          // [ROW_CAP][64] chunk pointers of leaves, in list order
+    uint32_t*  rowFree;       // stack of recycled rows
     uint64_t*  voxelTail;     // node -> last Chunk* of voxel list  (valid iff node.voxelChunks != 0)
-    DirEntry*  pointDir;
     DirEntry*  voxelDir;
     uint32_t*  dirtyLeaves;
     uint32_t*  dirtyVox;
-    uint32_t*  spillingNodes;
+    SpillInfo* spill;
     uint64_t*  chunkDir;
     uint64_t*  chunkQueue;
     uint32_t*  leafOf;        // item -> leaf node | level << 24
@@ -217,7 +244,7 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
                 if (lane == leader) {
                     base = atomicAdd(&c.nodes[node].numVoxels, (uint32_t)__popc(peers));
                     if (base == ldv(&c.nodes[node].numVoxelsStored)) {   // first voxel of this node in this batch
-                        uint32_t d = atomicAdd(&c.ctl->numDirtyVox, 1u);
+                        uint32_t d = atomicAdd(&c.bc->numDirtyVox, 1u);
                         c.dirtyVox[d] = node;
                     }
                 }
@@ -225,7 +252,7 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
                 uint32_t vslot = base + __popc(peers & ltmask);
                 uint32_t wleader = __ffs(winMask) - 1;
                 uint32_t bbase = 0;
-                if (lane == wleader) bbase = atomicAdd(&c.ctl->numBacklog, (uint32_t)__popc(winMask));
+                if (lane == wleader) bbase = atomicAdd(&c.bc->numBacklog, (uint32_t)__popc(winMask));
                 bbase = __shfl_sync(winMask, bbase, wleader);
                 uint32_t b = bbase + __popc(winMask & ltmask);
                 if (b < scratch::VOXEL_CAP) {
@@ -259,14 +286,32 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
             if (lane == leader) {
                 Node* leaf = &c.nodes[node];
                 old = atomicAdd(&leaf->counter, cnt);
-                if (old == ldv(&leaf->numPoints)) {                      // first point of this leaf in this batch
-                    uint32_t d = atomicAdd(&c.ctl->numDirtyLeaves, 1u);
+                uint32_t stored = ldv(&leaf->numPoints);
+                if (old == stored) {                                     // first point of this leaf in this batch
+                    uint32_t d = atomicAdd(&c.bc->numDirtyLeaves, 1u);
                     c.dirtyLeaves[d] = node;
                 }
                 if (old <= SIMLOD_MAX_POINTS_PER_NODE && old + cnt > SIMLOD_MAX_POINTS_PER_NODE) {
-                    uint32_t s = atomicAdd(&c.ctl->numSpillTotal, 1u);
-                    if (s < scratch::SPILLNODE_CAP) c.spillingNodes[s] = node;
-                    else atomicOr(&c.ctl->errorFlags, ERR_SPILLNODE_OVERFLOW);
+                    // this leaf spills (voxels.cu:211-217). Reserve everything its split needs right here, so the
+                    // split round is one phase: room in the spill buffer, 8 node slots, the occupancy grid.
+                    uint32_t s = atomicAdd(&c.bc->numSpillTotal, 1u);
+                    if (s < scratch::SPILLNODE_CAP) {
+                        SpillInfo info;
+                        info.node = node;
+                        info.stored = stored;
+                        info.level = level;
+                        info.row = c.leafRow[node];
+                        info.base = stored ? atomicAdd(&c.bc->numSpilled, stored) : 0u;
+                        if ((uint64_t)info.base + stored > scratch::SPILL_CAP) atomicOr(&c.ctl->errorFlags, ERR_SPILL_OVERFLOW);
+                        info.childBase = atomicAdd(&c.stats->numNodes, 8u);                                // voxels.cu:317
+                        if (info.childBase + 8 > scratch::NODE_CAP) atomicOr(&c.ctl->errorFlags, ERR_NODE_OVERFLOW);
+                        uint64_t g = c.gridPtr[node];
+                        if (g == 0) g = (uint64_t)(c.heapBytes + atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)SIMLOD_GRID_STRIDE));   // voxels.cu:363-365
+                        info.grid = g;
+                        c.spill[s] = info;
+                    } else {
+                        atomicOr(&c.ctl->errorFlags, ERR_SPILLNODE_OVERFLOW);
+                    }
                 }
             }
             old = __shfl_sync(peers, old, leader);
@@ -317,119 +362,87 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
 }
 
 // ------------------------------------------------------------------------------------------
-// split round (voxels.cu:245-289 spill copy, :308-383 doSplitting)
+// split round, ONE phase (voxels.cu:245-289 spill copy, :308-383 doSplitting). Everything a split
+// needs was reserved by the lane that detected it, so for every spilling leaf the three jobs are
+// independent and spread over the whole grid, one warp per item:
+//   parts 0..63  copy chunk k of the leaf's stored points into the spill buffer (16 KB, 128-bit)
+//   parts 64..79 clear 1/16 of the new inner node's occupancy grid (sic: the root's populated grid too)
+//   part  80     create the 8 children, return the chunks to the free stack, publish the node as inner
 // ------------------------------------------------------------------------------------------
-__device__ void copySpilledPoints(const Ctx& c, uint32_t begin, uint32_t end) {
-    __shared__ uint32_t sh_item;
-    __shared__ uint32_t sh_base;
-    __shared__ uint64_t sh_chunks[64];
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) sh_item = begin + atomicAdd(&c.ctl->workCounter, 1u);
-        __syncthreads();
-        uint32_t item = sh_item;
-        if (item >= end) break;
-        uint32_t n = c.spillingNodes[item];
-        Node* node = &c.nodes[n];
-        uint32_t numPoints = node->numPoints;
-        if (numPoints == 0) continue;
-        uint32_t level = node->level;
-        if (threadIdx.x == 0) {
-            uint32_t b = atomicAdd(&c.ctl->numSpilled, numPoints);
-            if ((uint64_t)b + numPoints > scratch::SPILL_CAP) { atomicOr(&c.ctl->errorFlags, ERR_SPILL_OVERFLOW); b = 0xffffffffu; }
-            sh_base = b;
-        }
-        uint32_t numChunks = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-        Chunk* chunk = node->points;
-        for (uint32_t k0 = 0; k0 < numChunks; k0 += 64) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                for (uint32_t k = 0; k < 64 && k0 + k < numChunks; k++) { sh_chunks[k] = (uint64_t)chunk; chunk = chunk->next; }
-            }
-            __syncthreads();
-            uint32_t base = sh_base;
-            if (base == 0xffffffffu) break;
-            uint32_t first = k0 * SIMLOD_POINTS_PER_CHUNK;
-            uint32_t last = min(numPoints, (k0 + 64) * SIMLOD_POINTS_PER_CHUNK);
-            for (uint32_t i = first + threadIdx.x; i < last; i += blockDim.x) {
-                const Chunk* ch = reinterpret_cast<const Chunk*>(sh_chunks[(i / SIMLOD_POINTS_PER_CHUNK) - k0]);
-                uint4 v = *reinterpret_cast<const uint4*>(&ch->points[i % SIMLOD_POINTS_PER_CHUNK]);
-                *reinterpret_cast<uint4*>(c.spilled + base + i) = v;
-                c.leafOf[scratch::MAX_BATCH + base + i] = n | (level << 24);
-            }
-        }
-    }
-}
+constexpr uint32_t SPLIT_PARTS = 81;
 
-__device__ void splitNodes(const Ctx& c, uint32_t begin, uint32_t end) {
-    const uint32_t warpsTotal = (gridDim.x * blockDim.x) >> 5;
+__device__ void splitRound(const Ctx& c, uint32_t begin, uint32_t end) {
+    const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = laneId();
-    for (uint32_t item = begin + warp; item < end; item += warpsTotal) {
-        uint32_t n = c.spillingNodes[item];
-        Node* parent = &c.nodes[n];
-        uint32_t childBase = 0;
-        if (lane == 0) childBase = atomicAdd(&c.stats->numNodes, 8u);
-        childBase = __shfl_sync(0xffffffffu, childBase, 0);
-        if (childBase + 8 > scratch::NODE_CAP) { if (lane == 0) atomicOr(&c.ctl->errorFlags, ERR_NODE_OVERFLOW); continue; }
-        uint32_t plevel = parent->level, pX = parent->X, pY = parent->Y, pZ = parent->Z;
-        if (lane < 8) {
-            // default-constructed Node + the fields doSplitting sets (voxels.cu:324-342)
-            Node* child = &c.nodes[childBase + lane];
-            uint64_t* raw = reinterpret_cast<uint64_t*>(child);
+    const uint32_t numItems = (end - begin) * SPLIT_PARTS;
+    for (uint32_t item = warp; item < numItems; item += numWarps) {
+        const SpillInfo info = c.spill[begin + item / SPLIT_PARTS];
+        const uint32_t part = item % SPLIT_PARTS;
+        const uint32_t numChunks = (info.stored + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        if (info.childBase + 8 > scratch::NODE_CAP) continue;
+        if (part < 64) {
+            if (part >= numChunks || info.row == 0 || (uint64_t)info.base + info.stored > scratch::SPILL_CAP) continue;
+            const Chunk* chunk = reinterpret_cast<const Chunk*>(c.rows[(uint64_t)(info.row - 1) * scratch::ROW_SLOTS + part]);
+            const uint32_t first = part * SIMLOD_POINTS_PER_CHUNK;
+            const uint32_t n = min((uint32_t)SIMLOD_POINTS_PER_CHUNK, info.stored - first);
+            const uint32_t tag = info.node | (info.level << 24);
+            for (uint32_t i = lane; i < n; i += 32) {
+                uint4 v = *reinterpret_cast<const uint4*>(&chunk->points[i]);
+                *reinterpret_cast<uint4*>(c.spilled + info.base + first + i) = v;
+                c.leafOf[scratch::MAX_BATCH + info.base + first + i] = tag;
+            }
+        } else if (part < 80) {
+            uint4* g = reinterpret_cast<uint4*>(info.grid) + (uint64_t)(part - 64) * (SIMLOD_GRID_WORDS / 4 / 16);
+            for (uint32_t i = lane; i < SIMLOD_GRID_WORDS / 4 / 16; i += 32) g[i] = make_uint4(0, 0, 0, 0);
+        } else {
+            Node* parent = &c.nodes[info.node];
+            const uint32_t pX = parent->X, pY = parent->Y, pZ = parent->Z;
+            if (lane < 8) {
+                // default-constructed Node + the fields doSplitting sets (voxels.cu:324-342)
+                Node* child = &c.nodes[info.childBase + lane];
+                uint64_t* raw = reinterpret_cast<uint64_t*>(child);
 #pragma unroll
-            for (int w = 0; w < 19; w++) raw[w] = 0;
-            child->level = plevel + 1;
-            child->X = 2 * pX + ((lane >> 2) & 1);
-            child->Y = 2 * pY + ((lane >> 1) & 1);
-            child->Z = 2 * pZ + (lane & 1);
-            for (int b = 0; b < 20; b++) child->name[b] = parent->name[b];
-            reinterpret_cast<uint8_t*>(child)[offsetof(Node, name) + plevel + 1] = (uint8_t)('0' + lane);   // name[level] (sic: level 20 lands on `visible`)
-            child->isLeaf = 1;
-            parent->children[lane] = child;
-            c.firstChild[childBase + lane] = 0;
-            c.gridPtr[childBase + lane] = 0;
-        }
-        if (lane == 0) {
+                for (int w = 0; w < 19; w++) raw[w] = 0;
+                child->level = info.level + 1;
+                child->X = 2 * pX + ((lane >> 2) & 1);
+                child->Y = 2 * pY + ((lane >> 1) & 1);
+                child->Z = 2 * pZ + (lane & 1);
+                for (int b = 0; b < 20; b++) child->name[b] = parent->name[b];
+                reinterpret_cast<uint8_t*>(child)[offsetof(Node, name) + info.level + 1] = (uint8_t)('0' + lane);   // name[level] (sic: level 20 lands on `visible`)
+                child->isLeaf = 1;
+                parent->children[lane] = child;
+                c.firstChild[info.childBase + lane] = 0;
+                c.gridPtr[info.childBase + lane] = 0;
+                c.leafRow[info.childBase + lane] = 0;
+            }
             // return the leaf's chunks to the free stack (voxels.cu:345-357)
-            uint32_t numPoints = parent->numPoints;
-            uint32_t f = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-            if (f > 0) {
-                uint64_t a0 = atomicAdd(reinterpret_cast<unsigned long long*>(&c.stats->numAllocatedChunks), (unsigned long long)(0ull - f));
-                Chunk* chunk = parent->points;
-                for (uint32_t t = 0; t < f && chunk != nullptr; t++) {
-                    Chunk* next = chunk->next;
+            if (numChunks > 0 && info.row != 0) {
+                uint64_t a0 = 0;
+                if (lane == 0) a0 = atomicAdd(reinterpret_cast<unsigned long long*>(&c.stats->numAllocatedChunks), (unsigned long long)(0ull - numChunks));
+                a0 = __shfl_sync(0xffffffffu, a0, 0);
+                for (uint32_t k = lane; k < numChunks && k < scratch::ROW_SLOTS; k += 32) {
+                    Chunk* chunk = reinterpret_cast<Chunk*>(c.rows[(uint64_t)(info.row - 1) * scratch::ROW_SLOTS + k]);
                     chunk->next = nullptr;
-                    uint64_t qi = a0 - 1 - t;
+                    uint64_t qi = a0 - 1 - k;
                     if (qi < scratch::QUEUE_CAP) c.chunkQueue[qi] = (uint64_t)chunk;
                     else atomicOr(&c.ctl->errorFlags, ERR_QUEUE_OVERFLOW);
-                    chunk = next;
                 }
             }
-            parent->numPoints = 0;
-            parent->points = nullptr;
-            if (parent->grid == nullptr) {
-                uint64_t off = atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)SIMLOD_GRID_STRIDE);
-                parent->grid = reinterpret_cast<SimlodOccupancyGrid*>(c.heapBytes + off);
+            __syncwarp();
+            if (lane == 0) {
+                if (info.row != 0) {                    // the row goes back to the row pool; its contents stay readable for this phase
+                    uint32_t f = atomicAdd(&c.ctl->rowFreeCount, 1u);
+                    c.rowFree[f] = info.row;
+                    c.leafRow[info.node] = 0;
+                }
+                parent->numPoints = 0;
+                parent->points = nullptr;
+                parent->grid = reinterpret_cast<SimlodOccupancyGrid*>(info.grid);
+                c.gridPtr[info.node] = info.grid;
+                c.firstChild[info.node] = info.childBase;
             }
-            c.gridPtr[n] = (uint64_t)parent->grid;
-            c.firstChild[n] = childBase;
         }
-        __syncwarp();
-    }
-}
-
-// voxels.cu:370-382 — clears the grid of every node split in this round (sic: including the
-// root's already populated grid; its cells are then re-created by the re-sampled spilled points)
-__device__ void clearGrids(const Ctx& c, uint32_t begin, uint32_t end) {
-    const uint64_t vecPerGrid = SIMLOD_GRID_WORDS / 4;
-    const uint64_t total = (uint64_t)(end - begin) * vecPerGrid;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        uint32_t n = c.spillingNodes[begin + (uint32_t)(i / vecPerGrid)];
-        uint64_t g = c.gridPtr[n];
-        if (g == 0) continue;
-        reinterpret_cast<uint4*>(g)[i % vecPerGrid] = make_uint4(0, 0, 0, 0);
     }
 }
 
@@ -439,8 +452,8 @@ __device__ void clearGrids(const Ctx& c, uint32_t begin, uint32_t end) {
 __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t numDirtyLeaves = ldv(&c.ctl->numDirtyLeaves);
-    const uint32_t numDirtyVox = ldv(&c.ctl->numDirtyVox);
+    const uint32_t numDirtyLeaves = ldv(&c.bc->numDirtyLeaves);
+    const uint32_t numDirtyVox = ldv(&c.bc->numDirtyVox);
 
     for (uint32_t d = tid; d < numDirtyLeaves; d += stride) {
         uint32_t n = c.dirtyLeaves[d];
@@ -448,18 +461,26 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
         Node* node = &c.nodes[n];
         uint32_t cnt = node->counter, have = node->numPoints;
         if (cnt <= have) continue;
-        uint32_t k0 = have / SIMLOD_POINTS_PER_CHUNK, k1 = (cnt - 1) / SIMLOD_POINTS_PER_CHUNK;
-        uint32_t nseg = k1 - k0 + 1;
         uint32_t existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
         uint32_t required = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
         uint32_t needed = required - existing;
-        uint32_t base = atomicAdd(&c.ctl->dirCursor, nseg);
-        if ((uint64_t)base + nseg > scratch::DIR_CAP) { atomicOr(&c.ctl->errorFlags, ERR_DIR_OVERFLOW); continue; }
-        c.pointDir[n] = DirEntry{base, k0};
-        Chunk* tail = node->points ? reinterpret_cast<Chunk*>(c.pointTail[n]) : nullptr;
-        uint32_t j = 0;
-        if (have % SIMLOD_POINTS_PER_CHUNK != 0) c.chunkDir[base + j++] = (uint64_t)tail;
         if (needed > 0) {
+            if (required > scratch::ROW_SLOTS) { atomicOr(&c.ctl->errorFlags, ERR_ROW_OVERFLOW); continue; }
+            uint32_t row = c.leafRow[n];
+            if (row == 0) {                                 // first chunk of this leaf: take a row (recycled first)
+                uint32_t f = atomicSub(&c.ctl->rowFreeCount, 1u);
+                if (f >= 1 && f <= scratch::ROW_CAP) {
+                    row = c.rowFree[f - 1];
+                } else {
+                    atomicAdd(&c.ctl->rowFreeCount, 1u);
+                    uint32_t r = atomicAdd(&c.ctl->rowBump, 1u);
+                    if (r >= scratch::ROW_CAP) { atomicOr(&c.ctl->errorFlags, ERR_ROW_OVERFLOW); continue; }
+                    row = r + 1;
+                }
+                c.leafRow[n] = row;
+            }
+            uint64_t* slots = c.rows + (uint64_t)(row - 1) * scratch::ROW_SLOTS;
+            Chunk* tail = existing ? reinterpret_cast<Chunk*>(slots[existing - 1]) : nullptr;
             uint64_t a0 = atomicAdd(reinterpret_cast<unsigned long long*>(&c.stats->numAllocatedChunks), (unsigned long long)needed);
             uint64_t firstFresh = a0 > poolSize ? a0 : poolSize;          // indices >= poolSize are new heap chunks (voxels.cu:509-515)
             uint64_t numFresh = a0 + needed > firstFresh ? a0 + needed - firstFresh : 0;
@@ -472,9 +493,8 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
                 chunk->next = nullptr;
                 if (tail) tail->next = chunk; else node->points = chunk;
                 tail = chunk;
-                c.chunkDir[base + j++] = (uint64_t)chunk;
+                slots[existing + t] = (uint64_t)chunk;
             }
-            c.pointTail[n] = (uint64_t)tail;
         }
         node->numPoints = cnt;      // slots [have, cnt) were handed out by the counting pass; filled by insertAll
     }
@@ -489,7 +509,7 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
         uint32_t existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
         uint32_t required = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
         uint32_t needed = required - existing;
-        uint32_t base = atomicAdd(&c.ctl->dirCursor, nseg);
+        uint32_t base = atomicAdd(&c.bc->dirCursor, nseg);
         if ((uint64_t)base + nseg > scratch::DIR_CAP) { atomicOr(&c.ctl->errorFlags, ERR_DIR_OVERFLOW); continue; }
         c.voxelDir[n] = DirEntry{base, k0};
         Chunk* tail = node->voxelChunks ? reinterpret_cast<Chunk*>(c.voxelTail[n]) : nullptr;
@@ -512,12 +532,13 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
 }
 
 // ------------------------------------------------------------------------------------------
-// insertion: every point/voxel already owns (leaf, slot); the chunk directory turns that into
-// an address with two cached lookups (voxels.cu:540-639 insertPoints, 674-698 insertVoxels)
+// insertion: every point/voxel already owns (leaf, slot); the leaf's chunk row (points) or the
+// per-batch chunk directory (voxels) turns that into an address with two cached lookups
+// (voxels.cu:540-639 insertPoints, 674-698 insertVoxels walk slot/1000 list links instead)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ Point* slotAddress(const Ctx& c, const DirEntry* dir, uint32_t node, uint32_t slot) {
-    DirEntry d = dir[node];
-    Chunk* chunk = reinterpret_cast<Chunk*>(c.chunkDir[d.base + (slot / SIMLOD_POINTS_PER_CHUNK - d.k0)]);
+__device__ __forceinline__ Point* pointSlotAddress(const Ctx& c, uint32_t node, uint32_t slot) {
+    uint32_t row = c.leafRow[node];
+    Chunk* chunk = reinterpret_cast<Chunk*>(c.rows[(uint64_t)(row - 1) * scratch::ROW_SLOTS + slot / SIMLOD_POINTS_PER_CHUNK]);
     return &chunk->points[slot % SIMLOD_POINTS_PER_CHUNK];
 }
 
@@ -527,12 +548,14 @@ __device__ void insertAll(const Ctx& c, const Point* batch, uint32_t numBatch, u
     for (uint32_t i = tid; i < numBatch; i += stride) {
         uint4 pt = ldPoint(batch + i);
         uint32_t node = c.leafOf[i] & 0xffffffu;
-        stPoint(slotAddress(c, c.pointDir, node, c.slotOf[i]), pt);
+        if (c.leafRow[node] == 0) continue;               // only after an overflow flag
+        stPoint(pointSlotAddress(c, node, c.slotOf[i]), pt);
     }
     for (uint32_t j = tid; j < numSpilled; j += stride) {
         uint4 pt = *reinterpret_cast<const uint4*>(c.spilled + j);
         uint32_t node = c.leafOf[scratch::MAX_BATCH + j] & 0xffffffu;
-        stPoint(slotAddress(c, c.pointDir, node, c.slotOf[scratch::MAX_BATCH + j]), pt);
+        if (c.leafRow[node] == 0) continue;
+        stPoint(pointSlotAddress(c, node, c.slotOf[scratch::MAX_BATCH + j]), pt);
     }
     for (uint32_t b = tid; b < numVoxels; b += stride) {
         uint64_t key = c.vkey[b];
@@ -550,8 +573,14 @@ __device__ void insertAll(const Ctx& c, const Point* batch, uint32_t numBatch, u
         float vz = fpx::add(fpx::fma(nodeSize, fpx::u2f(Z), c.minz),
                             fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f((cell >> 14) & 127u), 0.5f)), 0.0078125f));
         uint4 v = make_uint4(__float_as_uint(vx), __float_as_uint(vy), __float_as_uint(vz), c.vcolor[b]);
-        stPoint(slotAddress(c, c.voxelDir, node, vslot), v);
+        DirEntry d = c.voxelDir[node];
+        Chunk* chunk = reinterpret_cast<Chunk*>(c.chunkDir[d.base + (vslot / SIMLOD_POINTS_PER_CHUNK - d.k0)]);
+        stPoint(&chunk->points[vslot % SIMLOD_POINTS_PER_CHUNK], v);
     }
+}
+
+__device__ __forceinline__ void clearBatchCounters(BatchCounters* b) {
+    b->numSpillTotal = 0; b->numSpilled = 0; b->numBacklog = 0; b->numDirtyLeaves = 0; b->numDirtyVox = 0; b->dirCursor = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -571,15 +600,17 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
     c.heap = reinterpret_cast<Heap*>(buffer_persistent);
     c.heapBytes = buffer_persistent;
     c.ctl = carve<Ctl>(buffer, scratch::OFF_CTL);
+    c.bc = &c.ctl->batch[0];
     c.firstChild = carve<uint32_t>(buffer, scratch::OFF_FIRSTCHILD);
     c.gridPtr = carve<uint64_t>(buffer, scratch::OFF_GRIDPTR);
-    c.pointTail = carve<uint64_t>(buffer, scratch::OFF_PTAIL);
+    c.leafRow = carve<uint32_t>(buffer, scratch::OFF_LEAFROW);
+    c.rows = carve<uint64_t>(buffer, scratch::OFF_ROWS);
+    c.rowFree = carve<uint32_t>(buffer, scratch::OFF_ROWFREE);
     c.voxelTail = carve<uint64_t>(buffer, scratch::OFF_VTAIL);
-    c.pointDir = carve<DirEntry>(buffer, scratch::OFF_PDIR);
     c.voxelDir = carve<DirEntry>(buffer, scratch::OFF_VDIR);
     c.dirtyLeaves = carve<uint32_t>(buffer, scratch::OFF_DIRTYLEAF);
     c.dirtyVox = carve<uint32_t>(buffer, scratch::OFF_DIRTYVOX);
-    c.spillingNodes = carve<uint32_t>(buffer, scratch::OFF_SPILLNODES);
+    c.spill = carve<SpillInfo>(buffer, scratch::OFF_SPILLINFO);
     c.chunkDir = carve<uint64_t>(buffer, scratch::OFF_CHUNKDIR);
     c.chunkQueue = carve<uint64_t>(buffer, scratch::OFF_QUEUE);
     c.leafOf = carve<uint32_t>(buffer, scratch::OFF_LEAFOF);
@@ -601,12 +632,15 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         c.ctl->numBatchesUploaded = *(volatile uint32_t*)numBatchesUploaded_volatile;   // one snapshot for all threads
         c.ctl->errorFlags = 0;
         c.ctl->elapsedNanos = 0;
-        c.ctl->numSpillTotal = 0; c.ctl->numSpilled = 0; c.ctl->numBacklog = 0;
-        c.ctl->numDirtyLeaves = 0; c.ctl->numDirtyVox = 0; c.ctl->dirCursor = 0; c.ctl->workCounter = 0;
+        c.ctl->memUsed = c.heap->offset;
+        clearBatchCounters(&c.ctl->batch[0]);
+        clearBatchCounters(&c.ctl->batch[1]);
         for (int i = 0; i < 8; i++) c.ctl->statCounters[i] = 0;
         if (stats->batchletIndex == 0) {       // fresh after the reset kernel: the tree is the root alone
             c.ctl->spilledTotal = 0; c.ctl->voxelsTotal = 0;
+            c.ctl->rowBump = 0; c.ctl->rowFreeCount = 0;
             c.firstChild[0] = 0;
+            c.leafRow[0] = 0;
             c.gridPtr[0] = (uint64_t)nodes[0].grid;
         }
     }
@@ -621,10 +655,11 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         const uint32_t ringSlot = batchIndex % SIMLOD_BATCH_STREAM_SIZE;
         const uint32_t batchSize = min(ldv(&batchSizes[ringSlot]), (uint32_t)SIMLOD_MAX_BATCH_SIZE);
         const Point* batch = points + (uint64_t)ringSlot * SIMLOD_MAX_BATCH_SIZE;
+        c.bc = &c.ctl->batch[batchIndex & 1];
+        BatchCounters* other = &c.ctl->batch[(batchIndex + 1) & 1];
 
         // capacity guard (voxels.cu:896-912): stop consuming batches 200 MB before the heap is full
-        const uint64_t memUsed = ldv(&c.heap->offset);
-        const bool memCapacityReached = memUsed + 200000000ull >= uniforms.persistentBufferCapacity;
+        const bool memCapacityReached = ldv(&c.ctl->memUsed) + 200000000ull >= uniforms.persistentBufferCapacity;
         if (first) stats->memCapacityReached = memCapacityReached ? 1 : 0;
         if (memCapacityReached) break;
 
@@ -636,25 +671,20 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         else               itemPass<true, true, true>(c, batch, batchSize, 0);
         grid.sync();
 
-        // ---- split rounds (voxels.cu:385-415 expand) ---------------------------------------
+        // ---- split rounds (voxels.cu:385-415 expand): 2 barriers each ------------------------
         uint32_t spillBegin = 0;
         for (int round = 0; round < 20; round++) {
-            const uint32_t spillEnd = min(ldv(&c.ctl->numSpillTotal), (uint32_t)scratch::SPILLNODE_CAP);
+            const uint32_t spillEnd = min(ldv(&c.bc->numSpillTotal), (uint32_t)scratch::SPILLNODE_CAP);
             if (spillEnd == spillBegin) break;
-            copySpilledPoints(c, spillBegin, spillEnd);
+            splitRound(c, spillBegin, spillEnd);
             grid.sync();
-            if (first) c.ctl->workCounter = 0;
-            splitNodes(c, spillBegin, spillEnd);
-            grid.sync();
-            clearGrids(c, spillBegin, spillEnd);
-            grid.sync();
-            const uint32_t numSpilled = min(ldv(&c.ctl->numSpilled), (uint32_t)scratch::SPILL_CAP);
+            const uint32_t numSpilled = min(ldv(&c.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
             if (deferSampling) itemPass<false, true, false>(c, batch, batchSize, numSpilled);
             else               itemPass<true, true, false>(c, batch, batchSize, numSpilled);
             grid.sync();
             spillBegin = spillEnd;
         }
-        const uint32_t numSpilled = min(ldv(&c.ctl->numSpilled), (uint32_t)scratch::SPILL_CAP);
+        const uint32_t numSpilled = min(ldv(&c.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
         if (deferSampling) {
             // the root was a leaf when the batch started: sample along the final paths, as the
             // reference does after expand() (voxels.cu:738-742)
@@ -664,26 +694,21 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
 
         // ---- chunk allocation for touched nodes --------------------------------------------
         allocateChunks(c, poolSize);
+        if (first) clearBatchCounters(other);           // the next batch's counter set is idle during this phase
         grid.sync();
 
-        // ---- insertion ---------------------------------------------------------------------
-        const uint32_t numVoxels = min(ldv(&c.ctl->numBacklog), (uint32_t)scratch::VOXEL_CAP);
-        insertAll(c, batch, batchSize, numSpilled, numVoxels);
+        // ---- insertion + bookkeeping (voxels.cu:925-949) --------------------------------------
+        const uint32_t numVoxels = min(ldv(&c.bc->numBacklog), (uint32_t)scratch::VOXEL_CAP);
         if (first) {
             uint64_t allocated = ldv(&stats->numAllocatedChunks);
             if (allocated > poolSize) stats->chunkPoolSize = allocated;        // voxels.cu:535-537
-        }
-        grid.sync();
-
-        // ---- bookkeeping (voxels.cu:925-949) -----------------------------------------------
-        if (first) {
             stats->batchletIndex = batchIndex + 1;
             stats->numPointsProcessed += batchSize;
             c.ctl->spilledTotal += numSpilled; c.ctl->voxelsTotal += numVoxels;
+            c.ctl->memUsed = ldv(&c.heap->offset);
             c.ctl->elapsedNanos = globaltimer() - tStart;
-            c.ctl->numSpillTotal = 0; c.ctl->numSpilled = 0; c.ctl->numBacklog = 0;
-            c.ctl->numDirtyLeaves = 0; c.ctl->numDirtyVox = 0; c.ctl->dirCursor = 0; c.ctl->workCounter = 0;
         }
+        insertAll(c, batch, batchSize, numSpilled, numVoxels);
         grid.sync();
         const float elapsedMs = float(ldv(&c.ctl->elapsedNanos)) / 1000000.0f;
         if (elapsedMs > 10.0f) break;          // MAX_PROCESSING_TIME (voxels.cu:22,940)

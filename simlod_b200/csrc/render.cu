@@ -34,9 +34,11 @@ struct CudaPrint;
 // the same offsets; the area the reference uses for 100 000 Node copies holds our queues.
 namespace rbuf {
 constexpr uint64_t OFF_CTL       = 0;
-constexpr uint64_t OFF_ITEMS     = 4096;
+constexpr uint64_t OFF_VISLIST   = 4096;                           // u32 node indices of the LOD cut
+constexpr uint64_t VIS_CAP       = 263168;
+constexpr uint64_t OFF_ITEMS     = OFF_VISLIST + VIS_CAP * 4;
 constexpr uint64_t OFF_FB        = 31200144;                       // 15 200 000 + 7*16 + 32 + 16 000 000
-constexpr uint64_t ITEM_CAP      = (OFF_FB - OFF_ITEMS) / 16;      // ~1.95 M chunk items = 1.9 G samples
+constexpr uint64_t ITEM_CAP      = (OFF_FB - OFF_ITEMS) / 16;      // ~1.88 M chunk items = 1.9 G samples
 }
 
 struct WorkItem { uint64_t chunk; uint32_t count; uint32_t level; };   // 16 B
@@ -129,31 +131,16 @@ __device__ void computeVisibilityFlags(const Uniforms& u, Node* nodes, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------
-// visibility, pass 2: LOD cut (render.cu:906-933) -> chunk-granular work items
+// visibility, pass 2: LOD cut (render.cu:906-933). Emits the indices of the nodes to draw; a
+// second step turns every drawn node into chunk-granular work items (one thread per node walks
+// its two chunk lists — all lists are walked concurrently).
 // ------------------------------------------------------------------------------------------
-__device__ void emitNode(RCtl* ctl, WorkItem* items, const Node* node) {
+__device__ __forceinline__ void makeVisible(RCtl* ctl, uint32_t* visList, const Node* nodes, const Node* node) {
     uint32_t numPoints = node->numPoints, numVoxels = node->numVoxels;
-    atomicAdd(&ctl->numVisibleNodes, 1u);
+    uint32_t v = atomicAdd(&ctl->numVisibleNodes, 1u);
+    visList[v] = (uint32_t)(node - nodes);
     if (numPoints > 0) { atomicAdd(&ctl->numVisibleLeaves, 1u); atomicAdd(&ctl->numVisiblePoints, numPoints); }
     else if (numVoxels > 0) { atomicAdd(&ctl->numVisibleInner, 1u); atomicAdd(&ctl->numVisibleVoxels, numVoxels); }
-    uint32_t nP = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-    uint32_t nV = (numVoxels + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-    if (nP + nV == 0) return;
-    uint32_t base = atomicAdd(&ctl->numItems, nP + nV);
-    if ((uint64_t)base + nP + nV > rbuf::ITEM_CAP) { atomicOr(&ctl->overflow, 1u); return; }
-    uint32_t level = node->level;
-    const Chunk* chunk = node->points;
-    for (uint32_t k = 0, left = numPoints; k < nP && chunk; k++, chunk = chunk->next) {
-        uint32_t cnt = left < SIMLOD_POINTS_PER_CHUNK ? left : SIMLOD_POINTS_PER_CHUNK;
-        items[base + k] = WorkItem{(uint64_t)chunk, cnt, level};
-        left -= cnt;
-    }
-    chunk = node->voxelChunks;
-    for (uint32_t k = 0, left = numVoxels; k < nV && chunk; k++, chunk = chunk->next) {
-        uint32_t cnt = left < SIMLOD_POINTS_PER_CHUNK ? left : SIMLOD_POINTS_PER_CHUNK;
-        items[base + nP + k] = WorkItem{(uint64_t)chunk, cnt, level};
-        left -= cnt;
-    }
 }
 
 __device__ __forceinline__ bool isLeaf(const Node* node) {
@@ -163,7 +150,7 @@ __device__ __forceinline__ bool isLeaf(const Node* node) {
     return leaf;
 }
 
-__device__ void lodCut(RCtl* ctl, WorkItem* items, Node* nodes, uint32_t numNodes) {
+__device__ void lodCut(RCtl* ctl, uint32_t* visList, Node* nodes, uint32_t numNodes) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < numNodes; n += stride) {
         const Node* node = &nodes[n];
@@ -172,10 +159,44 @@ __device__ void lodCut(RCtl* ctl, WorkItem* items, Node* nodes, uint32_t numNode
             for (int i = 0; i < 8; i++) {
                 const Node* child = node->children[i];
                 if (child == nullptr || child->isLarge || !child->visible) continue;
-                emitNode(ctl, items, child);
+                makeVisible(ctl, visList, nodes, child);
             }
         } else if (node->visible) {
-            emitNode(ctl, items, node);
+            makeVisible(ctl, visList, nodes, node);
+        }
+    }
+}
+
+__device__ void emitItems(RCtl* ctl, WorkItem* items, const uint32_t* visList, const Node* nodes, uint32_t numVisible) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < numVisible; v += stride) {
+        const Node* node = &nodes[visList[v]];
+        uint32_t numPoints = node->numPoints, numVoxels = node->numVoxels;
+        uint32_t nP = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        uint32_t nV = (numVoxels + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        if (nP + nV == 0) continue;
+        uint32_t base = atomicAdd(&ctl->numItems, nP + nV);
+        if ((uint64_t)base + nP + nV > rbuf::ITEM_CAP) { atomicOr(&ctl->overflow, 1u); continue; }
+        uint32_t level = node->level;
+        const Chunk* cp = node->points;
+        const Chunk* cv = node->voxelChunks;
+        uint32_t leftP = numPoints, leftV = numVoxels;
+        // both lists advance in the same loop: the two dependent-load chains overlap
+        for (uint32_t k = 0; k < max(nP, nV); k++) {
+            if (k < nP && cp) {
+                uint32_t cnt = leftP < SIMLOD_POINTS_PER_CHUNK ? leftP : SIMLOD_POINTS_PER_CHUNK;
+                items[base + k] = WorkItem{(uint64_t)cp, cnt, level};
+                leftP -= cnt; cp = cp->next;
+            } else if (k < nP) {
+                items[base + k] = WorkItem{0, 0, level};
+            }
+            if (k < nV && cv) {
+                uint32_t cnt = leftV < SIMLOD_POINTS_PER_CHUNK ? leftV : SIMLOD_POINTS_PER_CHUNK;
+                items[base + nP + k] = WorkItem{(uint64_t)cv, cnt, level};
+                leftV -= cnt; cv = cv->next;
+            } else if (k < nV) {
+                items[base + nP + k] = WorkItem{0, 0, level};
+            }
         }
     }
 }
@@ -239,6 +260,7 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     uint8_t* base = reinterpret_cast<uint8_t*>(buffer);
     RCtl* ctl = reinterpret_cast<RCtl*>(base + rbuf::OFF_CTL);
     WorkItem* items = reinterpret_cast<WorkItem*>(base + rbuf::OFF_ITEMS);
+    uint32_t* visList = reinterpret_cast<uint32_t*>(base + rbuf::OFF_VISLIST);
     uint64_t* framebuffer = reinterpret_cast<uint64_t*>(base + rbuf::OFF_FB);
 
     const int width = fpx::f2i(uniforms.width), height = fpx::f2i(uniforms.height);
@@ -277,7 +299,9 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
 
     computeVisibilityFlags(uniforms, nodes, numNodes, cubeSize, uniforms.boxMin[0], uniforms.boxMin[1], uniforms.boxMin[2]);
     grid.sync();
-    lodCut(ctl, items, nodes, numNodes);
+    lodCut(ctl, visList, nodes, numNodes);
+    grid.sync();
+    emitItems(ctl, items, visList, nodes, min(ldv(&ctl->numVisibleNodes), (uint32_t)rbuf::VIS_CAP));
     grid.sync();
 
     const uint32_t numItems = min(ldv(&ctl->numItems), (uint32_t)rbuf::ITEM_CAP);
