@@ -52,6 +52,8 @@ constexpr uint64_t SPILLNODE_CAP  = 100000;            // voxels.cu:847
 
 constexpr uint64_t ROW_CAP        = 65536;             // leaves that hold points at the same time (x 64 chunk slots)
 constexpr uint64_t ROW_SLOTS      = 64;                // chunk pointers per leaf row (a leaf holds <= 50 chunks)
+constexpr uint64_t VOXEL_SHARED   = 1ull << 20;        // tail of the voxel backlog shared by all blocks (overflow of a block's own segment)
+constexpr uint64_t BLOCK_CAP      = 4096;              // per-block cursor slots (grid sizes up to 4096 blocks)
 
 constexpr uint64_t align256(uint64_t x) { return (x + 255) & ~255ull; }
 constexpr uint64_t OFF_CTL        = 0;
@@ -63,7 +65,8 @@ constexpr uint64_t OFF_VDIR       = align256(OFF_VTAIL + NODE_CAP * 8);
 constexpr uint64_t OFF_DIRTYLEAF  = align256(OFF_VDIR + NODE_CAP * 8);
 constexpr uint64_t OFF_DIRTYVOX   = align256(OFF_DIRTYLEAF + NODE_CAP * 4);
 constexpr uint64_t OFF_SPILLINFO  = align256(OFF_DIRTYVOX + NODE_CAP * 4);
-constexpr uint64_t OFF_ROWFREE    = align256(OFF_SPILLINFO + SPILLNODE_CAP * 32);
+constexpr uint64_t OFF_BLOCKCUR   = align256(OFF_SPILLINFO + SPILLNODE_CAP * 32);
+constexpr uint64_t OFF_ROWFREE    = align256(OFF_BLOCKCUR + BLOCK_CAP * 4);
 constexpr uint64_t OFF_ROWS       = align256(OFF_ROWFREE + ROW_CAP * 4);
 constexpr uint64_t OFF_CHUNKDIR   = align256(OFF_ROWS + ROW_CAP * ROW_SLOTS * 8);
 constexpr uint64_t OFF_QUEUE      = align256(OFF_CHUNKDIR + DIR_CAP * 8);
@@ -89,7 +92,7 @@ enum : uint32_t {   // Ctl::errorFlags, mirrored into Stats::dbg
 struct BatchCounters {              // one set per batch parity: batch b uses set b & 1, the other one is cleared meanwhile
     uint32_t numSpillTotal;        // spilling nodes found so far in this batch (monotonic)
     uint32_t numSpilled;           // spilled points in this batch
-    uint32_t numBacklog;           // voxels created in this batch
+    uint32_t numBacklog;           // voxels of this batch that went to the shared overflow part of the backlog
     uint32_t numDirtyLeaves;
     uint32_t numDirtyVox;
     uint32_t dirCursor;
@@ -108,6 +111,8 @@ struct Ctl {
     uint64_t spilledTotal;         // @80 spilled (re-inserted) points since the last reset: the `s` of the roofline's 32*s bytes
     uint64_t voxelsTotal;          // @88 voxels created since the last reset (incl. leaf-root voxels)
     BatchCounters batch[2];        // @96
+    uint64_t phaseNanos[8];        // @160 time per phase since reset, by the grid's first thread (%globaltimer):
+                                   //      0 count+sample, 1 split round, 2 re-walk, 3 deferred sampling, 4 allocate, 5 insert, 6 stats, 7 launch prologue
 };
 static_assert(offsetof(Ctl, spilledTotal) == 80, "bench.py reads Ctl::spilledTotal at byte 80");
 
@@ -142,6 +147,8 @@ struct Ctx {
     uint32_t*  dirtyLeaves;
     uint32_t*  dirtyVox;
     SpillInfo* spill;
+    uint32_t*  blockCursor;   // per block: entries of its own backlog segment filled in this batch
+    uint32_t   segCap;        // entries per block segment
     uint64_t*  chunkDir;
     uint64_t*  chunkQueue;
     uint32_t*  leafOf;        // item -> leaf node | level << 24
@@ -203,6 +210,89 @@ template <typename T>
 __device__ __forceinline__ T* carve(uint32_t* buffer, uint64_t off) { return reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(buffer) + off); }
 
 // ------------------------------------------------------------------------------------------
+// block-local voxel bookkeeping. A created voxel needs (a) a slot in its node's voxel list =
+// numVoxels++ and (b) a backlog entry. For a coherent scan these are two very hot global
+// addresses (the upper nodes' counters, the backlog cursor); same-address atomics serialise in L2
+// and were 2/3 of the counting pass. Instead every block owns a segment of the backlog and a
+// 64-entry node -> count table in shared memory; winners take a block-local rank, and when the
+// block has finished its pass it adds each node's count to numVoxels ONCE and patches the entries
+// it wrote with the returned base.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t VOXTAB_SIZE = 64;
+constexpr uint32_t VOXTAB_EMPTY = 0xffffffffu;
+__shared__ uint32_t sh_tabKey[VOXTAB_SIZE];
+__shared__ uint32_t sh_tabCount[VOXTAB_SIZE];
+__shared__ uint32_t sh_tabBase[VOXTAB_SIZE];
+__shared__ uint32_t sh_cursor;        // next free entry of this block's backlog segment
+__shared__ uint32_t sh_passStart;     // first entry written in the current pass
+
+__device__ __forceinline__ void voxelPassBegin(const Ctx& c, bool firstPassOfBatch) {
+    if (threadIdx.x < VOXTAB_SIZE) { sh_tabKey[threadIdx.x] = VOXTAB_EMPTY; sh_tabCount[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) { sh_cursor = firstPassOfBatch ? 0u : c.blockCursor[blockIdx.x]; sh_passStart = sh_cursor; }
+    __syncthreads();
+}
+
+// shared fall-back (block table or block segment full): global atomics, final key at once
+__device__ __noinline__ void recordVoxelShared(const Ctx& c, uint32_t node, uint32_t cell, uint32_t color) {
+    uint32_t vslot = atomicAdd(&c.nodes[node].numVoxels, 1u);
+    if (vslot == ldv(&c.nodes[node].numVoxelsStored)) { uint32_t d = atomicAdd(&c.bc->numDirtyVox, 1u); c.dirtyVox[d] = node; }
+    uint32_t b = atomicAdd(&c.bc->numBacklog, 1u);
+    if (b < scratch::VOXEL_SHARED) {
+        uint64_t at = scratch::VOXEL_CAP - scratch::VOXEL_SHARED + b;
+        c.vkey[at] = (uint64_t)cell | ((uint64_t)node << 21) | ((uint64_t)vslot << 41);
+        c.vcolor[at] = color;
+    } else {
+        atomicOr(&c.ctl->errorFlags, ERR_VOXEL_OVERFLOW);
+    }
+}
+
+__device__ __forceinline__ void recordVoxel(const Ctx& c, uint32_t node, uint32_t cell, uint32_t color) {
+    uint32_t h = (node * 0x9E3779B1u) >> 26;
+    uint32_t slot = VOXTAB_EMPTY;
+    for (uint32_t probe = 0; probe < VOXTAB_SIZE; probe++) {
+        uint32_t s = (h + probe) & (VOXTAB_SIZE - 1);
+        uint32_t k = atomicCAS(&sh_tabKey[s], VOXTAB_EMPTY, node);
+        if (k == VOXTAB_EMPTY || k == node) { slot = s; break; }
+    }
+    if (slot == VOXTAB_EMPTY) { recordVoxelShared(c, node, cell, color); return; }
+    uint32_t idx = atomicAdd(&sh_cursor, 1u);
+    if (idx >= c.segCap) { recordVoxelShared(c, node, cell, color); return; }
+    uint32_t rank = atomicAdd(&sh_tabCount[slot], 1u);
+    uint64_t at = (uint64_t)blockIdx.x * c.segCap + idx;
+    c.vkey[at] = (uint64_t)cell | ((uint64_t)slot << 21) | ((uint64_t)rank << 41);      // node/slot patched in voxelPassEnd
+    c.vcolor[at] = color;
+}
+
+__device__ __forceinline__ void voxelPassEnd(const Ctx& c) {
+    __syncthreads();
+    if (threadIdx.x < VOXTAB_SIZE) {
+        uint32_t node = sh_tabKey[threadIdx.x], cnt = sh_tabCount[threadIdx.x];
+        if (node != VOXTAB_EMPTY && cnt > 0) {
+            uint32_t base = atomicAdd(&c.nodes[node].numVoxels, cnt);
+            if (base == ldv(&c.nodes[node].numVoxelsStored)) {           // first voxels of this node in this batch
+                uint32_t d = atomicAdd(&c.bc->numDirtyVox, 1u);
+                c.dirtyVox[d] = node;
+            }
+            sh_tabBase[threadIdx.x] = base;
+        }
+    }
+    __syncthreads();
+    const uint32_t endIdx = min(sh_cursor, c.segCap);
+    for (uint32_t e = sh_passStart + threadIdx.x; e < endIdx; e += blockDim.x) {
+        uint64_t at = (uint64_t)blockIdx.x * c.segCap + e;
+        uint64_t k = c.vkey[at];
+        uint32_t slot = (uint32_t)(k >> 21) & (VOXTAB_SIZE - 1);
+        uint32_t rank = (uint32_t)(k >> 41);
+        c.vkey[at] = (k & 0x1fffffull) | ((uint64_t)sh_tabKey[slot] << 21) | ((uint64_t)(sh_tabBase[slot] + rank) << 41);
+    }
+    if (threadIdx.x == 0) {
+        c.blockCursor[blockIdx.x] = endIdx;
+        if (endIdx > sh_passStart) atomicAdd(reinterpret_cast<unsigned long long*>(&c.ctl->voxelsTotal), (unsigned long long)(endIdx - sh_passStart));
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
 // the per-point walk: descend from (node, level) to the leaf; optionally voxel-sample every
 // node on the way that owns an occupancy grid; optionally count the point into the leaf.
 // Warp-synchronous: all 32 lanes call it together, `valid` masks lanes without an item.
@@ -215,64 +305,39 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
     const uint32_t lane = laneId();
     const uint32_t ltmask = lanemaskLt();
     Coords q = quantize(c, pt);
-    bool walking = valid;
-
-    while (__any_sync(FULL, walking)) {
-        if (walking && level >= SIMLOD_MAX_DEPTH) walking = false;     // voxels.cu:169 loop bound: level-20 node is the leaf
-        if (SAMPLE) {
-            bool won = false;
-            uint32_t cell = 0;
-            if (walking) {
+    // per-lane descent (no warp-level synchronisation inside: voxel bookkeeping is block-local)
+    if (valid) {
+        for (;;) {
+            if (level >= SIMLOD_MAX_DEPTH) break;                       // voxels.cu:169 loop bound: a level-20 node is the leaf
+            if (SAMPLE) {
                 uint64_t g = c.gridPtr[node];
                 if (g != 0) {
-                    cell = cellAt(q, level);
+                    uint32_t cell = cellAt(q, level);
                     uint32_t* word = reinterpret_cast<uint32_t*>(g) + (cell >> 5);
                     uint32_t bit = 1u << (cell & 31u);
-                    uint32_t seen = *word;                               // non-atomic pre-test (voxels.cu:93-94)
+                    // non-atomic pre-test (voxels.cu:93-94). Bits are only ever set during a pass, so a set bit
+                    // seen through the (non-coherent) L1 is final; a clear one may be stale and is confirmed
+                    // in L2 before paying for an atomic on what is, for coherent scans, a very hot address.
+                    uint32_t seen = *word;
+                    if ((seen & bit) == 0) seen = __ldcg(word);
                     if ((seen & bit) == 0) {
-                        uint32_t old = atomicOr(word, bit);
-                        won = (old & bit) == 0;
+                        // neighbouring points hit the same cell: one atomic per distinct cell among the converged lanes
+                        uint32_t active = __activemask();
+                        uint32_t peers = __match_any_sync(active, (uint64_t)(uintptr_t)word * 32ull + (cell & 31u));
+                        if (lane == (uint32_t)__ffs(peers) - 1u) {
+                            uint32_t old = atomicOr(word, bit);
+                            if ((old & bit) == 0) recordVoxel(c, node, cell, pt.w);
+                        }
                     }
                 }
             }
-            uint32_t winMask = __ballot_sync(FULL, won);
-            if (won) {
-                // numVoxels: one atomic per distinct node in the warp; backlog cursor: one per warp
-                uint32_t peers = __match_any_sync(winMask, node);
-                uint32_t leader = __ffs(peers) - 1;
-                uint32_t base = 0;
-                if (lane == leader) {
-                    base = atomicAdd(&c.nodes[node].numVoxels, (uint32_t)__popc(peers));
-                    if (base == ldv(&c.nodes[node].numVoxelsStored)) {   // first voxel of this node in this batch
-                        uint32_t d = atomicAdd(&c.bc->numDirtyVox, 1u);
-                        c.dirtyVox[d] = node;
-                    }
-                }
-                base = __shfl_sync(peers, base, leader);
-                uint32_t vslot = base + __popc(peers & ltmask);
-                uint32_t wleader = __ffs(winMask) - 1;
-                uint32_t bbase = 0;
-                if (lane == wleader) bbase = atomicAdd(&c.bc->numBacklog, (uint32_t)__popc(winMask));
-                bbase = __shfl_sync(winMask, bbase, wleader);
-                uint32_t b = bbase + __popc(winMask & ltmask);
-                if (b < scratch::VOXEL_CAP) {
-                    c.vkey[b] = (uint64_t)cell | ((uint64_t)node << 21) | ((uint64_t)vslot << 41);
-                    c.vcolor[b] = pt.w;
-                } else {
-                    atomicOr(&c.ctl->errorFlags, ERR_VOXEL_OVERFLOW);
-                }
-            }
-        }
-        if (walking) {
             uint32_t fc = c.firstChild[node];
-            if (fc == 0) {
-                walking = false;
-            } else {
-                node = fc + childIndexAt(q, level);
-                level++;
-            }
+            if (fc == 0) break;
+            node = fc + childIndexAt(q, level);
+            level++;
         }
     }
+    __syncwarp();
 
     leafPacked = node | (level << 24);
     if (COUNT) {
@@ -327,10 +392,17 @@ template <bool SAMPLE, bool COUNT, bool FRESH>
 __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, uint32_t numSpilled) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    // batch points
-    for (uint32_t base = tid - laneId(); base < numBatch; base += stride) {
+    if (SAMPLE) voxelPassBegin(c, FRESH);
+    // batch points: every block owns one contiguous run of the batch (scans are spatially coherent, so
+    // all iterations of a block revisit the same upper-level nodes and occupancy words: L1 hits)
+    // (re-walk passes touch a few contiguous runs of items, so they stay grid-strided to spread those runs)
+    const uint32_t perBlock = FRESH ? (((numBatch + gridDim.x - 1) / gridDim.x + 31u) & ~31u) : numBatch;
+    const uint32_t blockFirst = FRESH ? blockIdx.x * perBlock : blockIdx.x * blockDim.x;
+    const uint32_t blockEnd = FRESH ? min(numBatch, blockFirst + perBlock) : numBatch;
+    const uint32_t step = FRESH ? blockDim.x : stride;
+    for (uint32_t base = blockFirst + (threadIdx.x - laneId()); base < blockEnd; base += step) {
         uint32_t i = base + laneId();
-        bool valid = i < numBatch;
+        bool valid = i < blockEnd;
         uint32_t node = 0, level = 0;
         if (!FRESH && valid) {
             uint32_t lp = c.leafOf[i];
@@ -342,6 +414,9 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
         uint32_t lp = 0, slot = 0;
         walk<SAMPLE, COUNT>(c, valid, pt, node, level, lp, slot);
         if (valid && COUNT) { c.leafOf[i] = lp; c.slotOf[i] = slot; }
+#if defined(EXP_NO_COUNT) || defined(EXP_DESCEND_ONLY)
+        if (valid && lp == 0xffffffffu) c.slotOf[i] = lp;     // keep the walk alive for the optimiser
+#endif
     }
     // spilled points (always carry a cached start node: the leaf they were spilled from)
     for (uint32_t base = tid - laneId(); base < numSpilled; base += stride) {
@@ -359,6 +434,7 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
         walk<SAMPLE, COUNT>(c, valid, pt, node, level, lp, slot);
         if (valid && COUNT) { c.leafOf[scratch::MAX_BATCH + j] = lp; c.slotOf[scratch::MAX_BATCH + j] = slot; }
     }
+    if (SAMPLE) voxelPassEnd(c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -542,7 +618,28 @@ __device__ __forceinline__ Point* pointSlotAddress(const Ctx& c, uint32_t node, 
     return &chunk->points[slot % SIMLOD_POINTS_PER_CHUNK];
 }
 
-__device__ void insertAll(const Ctx& c, const Point* batch, uint32_t numBatch, uint32_t numSpilled, uint32_t numVoxels) {
+__device__ __forceinline__ void insertVoxel(const Ctx& c, uint64_t at) {
+    uint64_t key = c.vkey[at];
+    uint32_t cell = (uint32_t)(key & 0x1fffffu);
+    uint32_t node = (uint32_t)((key >> 21) & 0xfffffu);
+    uint32_t vslot = (uint32_t)(key >> 41);
+    const Node* nd = &c.nodes[node];
+    uint32_t level = nd->level, X = nd->X, Y = nd->Y, Z = nd->Z;
+    // cell centre in world space (voxels.cu:103-114; instruction sequence: see fpmath.cuh)
+    float nodeSize = fpx::mul_ftz(fpx::ex2(-fpx::u2f(level)), c.size);
+    float vx = fpx::add(fpx::fma(nodeSize, fpx::u2f(X), c.minx),
+                        fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f(cell & 127u), 0.5f)), 0.0078125f));
+    float vy = fpx::add(fpx::fma(nodeSize, fpx::u2f(Y), c.miny),
+                        fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f((cell >> 7) & 127u), 0.5f)), 0.0078125f));
+    float vz = fpx::add(fpx::fma(nodeSize, fpx::u2f(Z), c.minz),
+                        fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f((cell >> 14) & 127u), 0.5f)), 0.0078125f));
+    uint4 v = make_uint4(__float_as_uint(vx), __float_as_uint(vy), __float_as_uint(vz), c.vcolor[at]);
+    DirEntry d = c.voxelDir[node];
+    Chunk* chunk = reinterpret_cast<Chunk*>(c.chunkDir[d.base + (vslot / SIMLOD_POINTS_PER_CHUNK - d.k0)]);
+    stPoint(&chunk->points[vslot % SIMLOD_POINTS_PER_CHUNK], v);
+}
+
+__device__ void insertAll(const Ctx& c, const Point* batch, uint32_t numBatch, uint32_t numSpilled, uint32_t numSharedVoxels) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t i = tid; i < numBatch; i += stride) {
@@ -557,26 +654,10 @@ __device__ void insertAll(const Ctx& c, const Point* batch, uint32_t numBatch, u
         if (c.leafRow[node] == 0) continue;
         stPoint(pointSlotAddress(c, node, c.slotOf[scratch::MAX_BATCH + j]), pt);
     }
-    for (uint32_t b = tid; b < numVoxels; b += stride) {
-        uint64_t key = c.vkey[b];
-        uint32_t cell = (uint32_t)(key & 0x1fffffu);
-        uint32_t node = (uint32_t)((key >> 21) & 0xfffffu);
-        uint32_t vslot = (uint32_t)(key >> 41);
-        const Node* nd = &c.nodes[node];
-        uint32_t level = nd->level, X = nd->X, Y = nd->Y, Z = nd->Z;
-        // cell centre in world space (voxels.cu:103-114; instruction sequence: see fpmath.cuh)
-        float nodeSize = fpx::mul_ftz(fpx::ex2(-fpx::u2f(level)), c.size);
-        float vx = fpx::add(fpx::fma(nodeSize, fpx::u2f(X), c.minx),
-                            fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f(cell & 127u), 0.5f)), 0.0078125f));
-        float vy = fpx::add(fpx::fma(nodeSize, fpx::u2f(Y), c.miny),
-                            fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f((cell >> 7) & 127u), 0.5f)), 0.0078125f));
-        float vz = fpx::add(fpx::fma(nodeSize, fpx::u2f(Z), c.minz),
-                            fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f((cell >> 14) & 127u), 0.5f)), 0.0078125f));
-        uint4 v = make_uint4(__float_as_uint(vx), __float_as_uint(vy), __float_as_uint(vz), c.vcolor[b]);
-        DirEntry d = c.voxelDir[node];
-        Chunk* chunk = reinterpret_cast<Chunk*>(c.chunkDir[d.base + (vslot / SIMLOD_POINTS_PER_CHUNK - d.k0)]);
-        stPoint(&chunk->points[vslot % SIMLOD_POINTS_PER_CHUNK], v);
-    }
+    // voxels: this block's own backlog segment, then the shared overflow part
+    const uint32_t own = c.blockCursor[blockIdx.x];
+    for (uint32_t e = threadIdx.x; e < own; e += blockDim.x) insertVoxel(c, (uint64_t)blockIdx.x * c.segCap + e);
+    for (uint32_t b = tid; b < numSharedVoxels; b += stride) insertVoxel(c, scratch::VOXEL_CAP - scratch::VOXEL_SHARED + b);
 }
 
 __device__ __forceinline__ void clearBatchCounters(BatchCounters* b) {
@@ -611,6 +692,8 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
     c.dirtyLeaves = carve<uint32_t>(buffer, scratch::OFF_DIRTYLEAF);
     c.dirtyVox = carve<uint32_t>(buffer, scratch::OFF_DIRTYVOX);
     c.spill = carve<SpillInfo>(buffer, scratch::OFF_SPILLINFO);
+    c.blockCursor = carve<uint32_t>(buffer, scratch::OFF_BLOCKCUR);
+    c.segCap = gridDim.x <= scratch::BLOCK_CAP ? (uint32_t)((scratch::VOXEL_CAP - scratch::VOXEL_SHARED) / gridDim.x) : 0u;
     c.chunkDir = carve<uint64_t>(buffer, scratch::OFF_CHUNKDIR);
     c.chunkQueue = carve<uint64_t>(buffer, scratch::OFF_QUEUE);
     c.leafOf = carve<uint32_t>(buffer, scratch::OFF_LEAFOF);
@@ -638,6 +721,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         for (int i = 0; i < 8; i++) c.ctl->statCounters[i] = 0;
         if (stats->batchletIndex == 0) {       // fresh after the reset kernel: the tree is the root alone
             c.ctl->spilledTotal = 0; c.ctl->voxelsTotal = 0;
+            for (int i = 0; i < 8; i++) c.ctl->phaseNanos[i] = 0;
             c.ctl->rowBump = 0; c.ctl->rowFreeCount = 0;
             c.firstChild[0] = 0;
             c.leafRow[0] = 0;
@@ -645,6 +729,9 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         }
     }
     grid.sync();
+    uint64_t tPhase = tStart;
+#define PHASE_DONE(k) do { if (first) { uint64_t _t = globaltimer(); c.ctl->phaseNanos[k] += _t - tPhase; tPhase = _t; } } while (0)
+    PHASE_DONE(7);
 
     const uint32_t numBatchesUploaded = ldv(&c.ctl->numBatchesUploaded);
     const uint32_t firstBatch = ldv(&stats->batchletIndex);
@@ -667,9 +754,18 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         const uint64_t poolSize = ldv(&stats->chunkPoolSize);
 
         // ---- pass 1: count (+ sample) every batch point ------------------------------------
+#if defined(EXP_NO_SAMPLE)
+        itemPass<false, true, true>(c, batch, batchSize, 0);
+#elif defined(EXP_NO_COUNT)
+        itemPass<true, false, true>(c, batch, batchSize, 0);
+#elif defined(EXP_DESCEND_ONLY)
+        itemPass<false, false, true>(c, batch, batchSize, 0);
+#else
         if (deferSampling) itemPass<false, true, true>(c, batch, batchSize, 0);
         else               itemPass<true, true, true>(c, batch, batchSize, 0);
+#endif
         grid.sync();
+        PHASE_DONE(0);
 
         // ---- split rounds (voxels.cu:385-415 expand): 2 barriers each ------------------------
         uint32_t spillBegin = 0;
@@ -678,10 +774,12 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             if (spillEnd == spillBegin) break;
             splitRound(c, spillBegin, spillEnd);
             grid.sync();
+            PHASE_DONE(1);
             const uint32_t numSpilled = min(ldv(&c.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
             if (deferSampling) itemPass<false, true, false>(c, batch, batchSize, numSpilled);
             else               itemPass<true, true, false>(c, batch, batchSize, numSpilled);
             grid.sync();
+            PHASE_DONE(2);
             spillBegin = spillEnd;
         }
         const uint32_t numSpilled = min(ldv(&c.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
@@ -690,15 +788,21 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             // reference does after expand() (voxels.cu:738-742)
             itemPass<true, false, true>(c, batch, batchSize, numSpilled);
             grid.sync();
+            PHASE_DONE(3);
         }
 
+#if defined(EXP_EXTRA_SYNCS)
+        for (int e = 0; e < 10; e++) grid.sync();
+        PHASE_DONE(3);
+#endif
         // ---- chunk allocation for touched nodes --------------------------------------------
         allocateChunks(c, poolSize);
         if (first) clearBatchCounters(other);           // the next batch's counter set is idle during this phase
         grid.sync();
+        PHASE_DONE(4);
 
         // ---- insertion + bookkeeping (voxels.cu:925-949) --------------------------------------
-        const uint32_t numVoxels = min(ldv(&c.bc->numBacklog), (uint32_t)scratch::VOXEL_CAP);
+        const uint32_t numVoxels = min(ldv(&c.bc->numBacklog), (uint32_t)scratch::VOXEL_SHARED);     // shared overflow part only
         if (first) {
             uint64_t allocated = ldv(&stats->numAllocatedChunks);
             if (allocated > poolSize) stats->chunkPoolSize = allocated;        // voxels.cu:535-537
@@ -710,6 +814,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         }
         insertAll(c, batch, batchSize, numSpilled, numVoxels);
         grid.sync();
+        PHASE_DONE(5);
         const float elapsedMs = float(ldv(&c.ctl->elapsedNanos)) / 1000000.0f;
         if (elapsedMs > 10.0f) break;          // MAX_PROCESSING_TIME (voxels.cu:22,940)
     }
@@ -739,6 +844,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         }
     }
     grid.sync();
+    PHASE_DONE(6);
     if (first) {
         stats->numInner = ldv(&c.ctl->statCounters[0]);
         stats->numLeaves = ldv(&c.ctl->statCounters[1]);

@@ -1,0 +1,22 @@
+"""Per-phase device time of kernel_construct over a full bench-like run (developer tool)."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from simlod_b200 import SimLOD
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 36
+batches, mn, mx = bench.generate_batches(K, list(range(K)))
+sim = SimLOD(1920, 1080, persistent_bytes=8 << 30)
+sim.set_box(mn, mx)
+n = K * bench.BATCH
+dptr = sim.device_alloc(n * 16)
+sim.memcpy_htod(dptr, np.concatenate(batches).view(np.uint8))
+for rep in range(2):
+    sim.reset(); sim.flush_l2()
+    kms, tms = sim.insert_device(dptr, n)
+    ph = sim.memcpy_dtoh(sim.buffers().momentary + 160, 64).view(np.uint64) / 1e3
+    names = ["count+sample", "split", "rewalk", "deferred", "alloc", "insert", "stats", "prologue"]
+    print("kernel ms %.3f total ms %.3f Mpts/s %.1f" % (kms, tms, n / kms / 1e3))
+    print("phase us:", {k: round(float(v), 1) for k, v in zip(names, ph)}, "sum", round(float(ph.sum()), 1), flush=True)
+sim.close()
