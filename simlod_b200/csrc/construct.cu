@@ -305,7 +305,18 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
     const uint32_t lane = laneId();
     const uint32_t ltmask = lanemaskLt();
     Coords q = quantize(c, pt);
-    // per-lane descent (no warp-level synchronisation inside: voxel bookkeeping is block-local)
+    // per-lane descent (no warp-level synchronisation inside: voxel bookkeeping is block-local).
+    // atomicOr results are not needed to continue the descent, so up to 3 of them stay in flight
+    // per lane and are only looked at when the leaf has been reached (or a 4th one is issued).
+    uint32_t pending = 0;
+    uint32_t old0 = 0, old1 = 0, old2 = 0, key0 = 0, key1 = 0, key2 = 0;      // key = node | (cell & 31) << 20 ... see below
+    uint32_t cel0 = 0, cel1 = 0, cel2 = 0;
+    auto settle = [&]() {
+        if (pending > 0 && (old0 & (1u << (cel0 & 31u))) == 0) recordVoxel(c, key0, cel0, pt.w);
+        if (pending > 1 && (old1 & (1u << (cel1 & 31u))) == 0) recordVoxel(c, key1, cel1, pt.w);
+        if (pending > 2 && (old2 & (1u << (cel2 & 31u))) == 0) recordVoxel(c, key2, cel2, pt.w);
+        pending = 0;
+    };
     if (valid) {
         for (;;) {
             if (level >= SIMLOD_MAX_DEPTH) break;                       // voxels.cu:169 loop bound: a level-20 node is the leaf
@@ -315,18 +326,19 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
                     uint32_t cell = cellAt(q, level);
                     uint32_t* word = reinterpret_cast<uint32_t*>(g) + (cell >> 5);
                     uint32_t bit = 1u << (cell & 31u);
-                    // non-atomic pre-test (voxels.cu:93-94). Bits are only ever set during a pass, so a set bit
-                    // seen through the (non-coherent) L1 is final; a clear one may be stale and is confirmed
-                    // in L2 before paying for an atomic on what is, for coherent scans, a very hot address.
+                    // non-atomic pre-test (voxels.cu:93-94): a set bit seen through the (non-coherent) L1 is final
                     uint32_t seen = *word;
-                    if ((seen & bit) == 0) seen = __ldcg(word);
                     if ((seen & bit) == 0) {
                         // neighbouring points hit the same cell: one atomic per distinct cell among the converged lanes
                         uint32_t active = __activemask();
                         uint32_t peers = __match_any_sync(active, (uint64_t)(uintptr_t)word * 32ull + (cell & 31u));
                         if (lane == (uint32_t)__ffs(peers) - 1u) {
+                            if (pending == 3) settle();
                             uint32_t old = atomicOr(word, bit);
-                            if ((old & bit) == 0) recordVoxel(c, node, cell, pt.w);
+                            if (pending == 0) { old0 = old; key0 = node; cel0 = cell; }
+                            else if (pending == 1) { old1 = old; key1 = node; cel1 = cell; }
+                            else { old2 = old; key2 = node; cel2 = cell; }
+                            pending++;
                         }
                     }
                 }
@@ -336,6 +348,7 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
             node = fc + childIndexAt(q, level);
             level++;
         }
+        if (SAMPLE) settle();
     }
     __syncwarp();
 
@@ -525,85 +538,143 @@ __device__ void splitRound(const Ctx& c, uint32_t begin, uint32_t end) {
 // ------------------------------------------------------------------------------------------
 // chunk allocation for the nodes touched by this batch (voxels.cu:485-538, 641-672)
 // ------------------------------------------------------------------------------------------
+// block-wide exclusive prefix sum of one value per thread (256 threads); returns the block total
+__device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t& total) {
+    __shared__ uint32_t sh_warpSum[8];
+    __shared__ uint32_t sh_total;
+    const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+    __syncthreads();                       // protects sh_* against the previous call
+    if (lane == 31) sh_warpSum[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int w = 0; w < 8; w++) { uint32_t t = sh_warpSum[w]; sh_warpSum[w] = run; run += t; } sh_total = run; }
+    __syncthreads();
+    total = sh_total;
+    return sh_warpSum[warp] + incl - v;
+}
+
+// The reference lets every node thread bump numAllocatedChunks / the heap offset once per chunk
+// (voxels.cu:505-511). All dirty nodes of a batch sit in one or two blocks here, so a block adds its
+// whole demand with ONE atomic per counter and hands out sub-ranges by prefix sum: the same totals,
+// the same pooled-vs-fresh split (indices >= chunkPoolSize are fresh), a handful of atomics.
 __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
+    __shared__ uint64_t sh_a0, sh_freshOff, sh_firstFresh;
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t numDirtyLeaves = ldv(&c.bc->numDirtyLeaves);
     const uint32_t numDirtyVox = ldv(&c.bc->numDirtyVox);
 
-    for (uint32_t d = tid; d < numDirtyLeaves; d += stride) {
-        uint32_t n = c.dirtyLeaves[d];
-        if (c.firstChild[n] != 0) continue;                 // became an inner node in this batch
-        Node* node = &c.nodes[n];
-        uint32_t cnt = node->counter, have = node->numPoints;
-        if (cnt <= have) continue;
-        uint32_t existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-        uint32_t required = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-        uint32_t needed = required - existing;
-        if (needed > 0) {
-            if (required > scratch::ROW_SLOTS) { atomicOr(&c.ctl->errorFlags, ERR_ROW_OVERFLOW); continue; }
-            uint32_t row = c.leafRow[n];
-            if (row == 0) {                                 // first chunk of this leaf: take a row (recycled first)
-                uint32_t f = atomicSub(&c.ctl->rowFreeCount, 1u);
-                if (f >= 1 && f <= scratch::ROW_CAP) {
-                    row = c.rowFree[f - 1];
-                } else {
-                    atomicAdd(&c.ctl->rowFreeCount, 1u);
-                    uint32_t r = atomicAdd(&c.ctl->rowBump, 1u);
-                    if (r >= scratch::ROW_CAP) { atomicOr(&c.ctl->errorFlags, ERR_ROW_OVERFLOW); continue; }
-                    row = r + 1;
+    for (uint32_t first = blockIdx.x * blockDim.x; first < numDirtyLeaves; first += stride) {      // block-uniform trip count
+        const uint32_t d = first + threadIdx.x;
+        uint32_t n = 0, cnt = 0, have = 0, existing = 0, needed = 0;
+        Node* node = nullptr;
+        bool live = false;
+        if (d < numDirtyLeaves) {
+            n = c.dirtyLeaves[d];
+            if (c.firstChild[n] == 0) {                       // else: became an inner node in this batch
+                node = &c.nodes[n];
+                cnt = node->counter; have = node->numPoints;
+                if (cnt > have) {
+                    live = true;
+                    existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+                    uint32_t required = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+                    needed = required - existing;
+                    if (required > scratch::ROW_SLOTS) { atomicOr(&c.ctl->errorFlags, ERR_ROW_OVERFLOW); needed = 0; live = false; }
                 }
-                c.leafRow[n] = row;
-            }
-            uint64_t* slots = c.rows + (uint64_t)(row - 1) * scratch::ROW_SLOTS;
-            Chunk* tail = existing ? reinterpret_cast<Chunk*>(slots[existing - 1]) : nullptr;
-            uint64_t a0 = atomicAdd(reinterpret_cast<unsigned long long*>(&c.stats->numAllocatedChunks), (unsigned long long)needed);
-            uint64_t firstFresh = a0 > poolSize ? a0 : poolSize;          // indices >= poolSize are new heap chunks (voxels.cu:509-515)
-            uint64_t numFresh = a0 + needed > firstFresh ? a0 + needed - firstFresh : 0;
-            uint64_t freshOff = 0;
-            if (numFresh) freshOff = atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)(numFresh * SIMLOD_CHUNK_STRIDE));
-            for (uint32_t t = 0; t < needed; t++) {
-                uint64_t idx = a0 + t;
-                Chunk* chunk = idx < poolSize ? reinterpret_cast<Chunk*>(c.chunkQueue[idx])
-                                              : reinterpret_cast<Chunk*>(c.heapBytes + freshOff + (idx - firstFresh) * SIMLOD_CHUNK_STRIDE);
-                chunk->next = nullptr;
-                if (tail) tail->next = chunk; else node->points = chunk;
-                tail = chunk;
-                slots[existing + t] = (uint64_t)chunk;
             }
         }
-        node->numPoints = cnt;      // slots [have, cnt) were handed out by the counting pass; filled by insertAll
+        uint32_t total = 0;
+        const uint32_t offset = blockExclusiveScan(needed, total);
+        if (threadIdx.x == 0 && total > 0) {
+            uint64_t a0 = atomicAdd(reinterpret_cast<unsigned long long*>(&c.stats->numAllocatedChunks), (unsigned long long)total);
+            uint64_t firstFresh = a0 > poolSize ? a0 : poolSize;          // indices >= poolSize are new heap chunks (voxels.cu:509-515)
+            uint64_t numFresh = a0 + total > firstFresh ? a0 + total - firstFresh : 0;
+            sh_a0 = a0; sh_firstFresh = firstFresh;
+            sh_freshOff = numFresh ? atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)(numFresh * SIMLOD_CHUNK_STRIDE)) : 0;
+        }
+        __syncthreads();
+        if (live) {
+            if (needed > 0) {
+                uint32_t row = c.leafRow[n];
+                if (row == 0) {                                 // first chunk of this leaf: take a row (recycled first)
+                    uint32_t f = atomicSub(&c.ctl->rowFreeCount, 1u);
+                    if (f >= 1 && f <= scratch::ROW_CAP) {
+                        row = c.rowFree[f - 1];
+                    } else {
+                        atomicAdd(&c.ctl->rowFreeCount, 1u);
+                        uint32_t r = atomicAdd(&c.ctl->rowBump, 1u);
+                        if (r >= scratch::ROW_CAP) { atomicOr(&c.ctl->errorFlags, ERR_ROW_OVERFLOW); row = 0; }
+                        else row = r + 1;
+                    }
+                    c.leafRow[n] = row;
+                }
+                if (row != 0) {
+                    uint64_t* slots = c.rows + (uint64_t)(row - 1) * scratch::ROW_SLOTS;
+                    Chunk* tail = existing ? reinterpret_cast<Chunk*>(slots[existing - 1]) : nullptr;
+                    const uint64_t a0 = sh_a0 + offset, firstFresh = sh_firstFresh, freshOff = sh_freshOff;
+                    for (uint32_t t = 0; t < needed; t++) {
+                        uint64_t idx = a0 + t;
+                        Chunk* chunk = idx < poolSize ? reinterpret_cast<Chunk*>(c.chunkQueue[idx])
+                                                      : reinterpret_cast<Chunk*>(c.heapBytes + freshOff + (idx - firstFresh) * SIMLOD_CHUNK_STRIDE);
+                        chunk->next = nullptr;
+                        if (tail) tail->next = chunk; else node->points = chunk;
+                        tail = chunk;
+                        slots[existing + t] = (uint64_t)chunk;
+                    }
+                }
+            }
+            node->numPoints = cnt;      // slots [have, cnt) were handed out by the counting pass; filled by insertAll
+        }
     }
 
-    for (uint32_t d = tid; d < numDirtyVox; d += stride) {
-        uint32_t n = c.dirtyVox[d];
-        Node* node = &c.nodes[n];
-        uint32_t cnt = node->numVoxels, have = node->numVoxelsStored;
-        if (cnt <= have) continue;
-        uint32_t k0 = have / SIMLOD_POINTS_PER_CHUNK, k1 = (cnt - 1) / SIMLOD_POINTS_PER_CHUNK;
-        uint32_t nseg = k1 - k0 + 1;
-        uint32_t existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-        uint32_t required = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-        uint32_t needed = required - existing;
-        uint32_t base = atomicAdd(&c.bc->dirCursor, nseg);
-        if ((uint64_t)base + nseg > scratch::DIR_CAP) { atomicOr(&c.ctl->errorFlags, ERR_DIR_OVERFLOW); continue; }
-        c.voxelDir[n] = DirEntry{base, k0};
-        Chunk* tail = node->voxelChunks ? reinterpret_cast<Chunk*>(c.voxelTail[n]) : nullptr;
-        uint32_t j = 0;
-        if (have % SIMLOD_POINTS_PER_CHUNK != 0) c.chunkDir[base + j++] = (uint64_t)tail;
-        if (needed > 0) {
-            // voxel chunks are never recycled: always fresh heap memory (voxels.cu:652-666)
-            uint64_t freshOff = atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)((uint64_t)needed * SIMLOD_CHUNK_STRIDE));
-            for (uint32_t t = 0; t < needed; t++) {
-                Chunk* chunk = reinterpret_cast<Chunk*>(c.heapBytes + freshOff + (uint64_t)t * SIMLOD_CHUNK_STRIDE);
-                chunk->next = nullptr;
-                if (tail) tail->next = chunk; else node->voxelChunks = chunk;
-                tail = chunk;
-                c.chunkDir[base + j++] = (uint64_t)chunk;
+    for (uint32_t first = blockIdx.x * blockDim.x; first < numDirtyVox; first += stride) {
+        const uint32_t d = first + threadIdx.x;
+        uint32_t n = 0, cnt = 0, have = 0, existing = 0, needed = 0, nseg = 0, k0 = 0;
+        Node* node = nullptr;
+        bool live = false;
+        if (d < numDirtyVox) {
+            n = c.dirtyVox[d];
+            node = &c.nodes[n];
+            cnt = node->numVoxels; have = node->numVoxelsStored;
+            if (cnt > have) {
+                live = true;
+                k0 = have / SIMLOD_POINTS_PER_CHUNK;
+                nseg = (cnt - 1) / SIMLOD_POINTS_PER_CHUNK - k0 + 1;
+                existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+                needed = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK - existing;
             }
-            c.voxelTail[n] = (uint64_t)tail;
         }
-        node->numVoxelsStored = cnt;
+        uint32_t totalNeeded = 0, totalSeg = 0;
+        const uint32_t offNeeded = blockExclusiveScan(needed, totalNeeded);
+        const uint32_t offSeg = blockExclusiveScan(nseg, totalSeg);
+        if (threadIdx.x == 0) {
+            // voxel chunks are never recycled: always fresh heap memory (voxels.cu:652-666)
+            sh_freshOff = totalNeeded ? atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)((uint64_t)totalNeeded * SIMLOD_CHUNK_STRIDE)) : 0;
+            sh_a0 = totalSeg ? atomicAdd(&c.bc->dirCursor, totalSeg) : 0;
+        }
+        __syncthreads();
+        if (live) {
+            const uint32_t base = (uint32_t)sh_a0 + offSeg;
+            if ((uint64_t)base + nseg > scratch::DIR_CAP) { atomicOr(&c.ctl->errorFlags, ERR_DIR_OVERFLOW); }
+            else {
+                c.voxelDir[n] = DirEntry{base, k0};
+                Chunk* tail = node->voxelChunks ? reinterpret_cast<Chunk*>(c.voxelTail[n]) : nullptr;
+                uint32_t j = 0;
+                if (have % SIMLOD_POINTS_PER_CHUNK != 0) c.chunkDir[base + j++] = (uint64_t)tail;
+                const uint64_t freshOff = sh_freshOff + (uint64_t)offNeeded * SIMLOD_CHUNK_STRIDE;
+                for (uint32_t t = 0; t < needed; t++) {
+                    Chunk* chunk = reinterpret_cast<Chunk*>(c.heapBytes + freshOff + (uint64_t)t * SIMLOD_CHUNK_STRIDE);
+                    chunk->next = nullptr;
+                    if (tail) tail->next = chunk; else node->voxelChunks = chunk;
+                    tail = chunk;
+                    c.chunkDir[base + j++] = (uint64_t)chunk;
+                }
+                if (needed > 0) c.voxelTail[n] = (uint64_t)tail;
+                node->numVoxelsStored = cnt;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -612,8 +683,7 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
 // per-batch chunk directory (voxels) turns that into an address with two cached lookups
 // (voxels.cu:540-639 insertPoints, 674-698 insertVoxels walk slot/1000 list links instead)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ Point* pointSlotAddress(const Ctx& c, uint32_t node, uint32_t slot) {
-    uint32_t row = c.leafRow[node];
+__device__ __forceinline__ Point* pointSlotAddress(const Ctx& c, uint32_t row, uint32_t slot) {
     Chunk* chunk = reinterpret_cast<Chunk*>(c.rows[(uint64_t)(row - 1) * scratch::ROW_SLOTS + slot / SIMLOD_POINTS_PER_CHUNK]);
     return &chunk->points[slot % SIMLOD_POINTS_PER_CHUNK];
 }
@@ -642,21 +712,49 @@ __device__ __forceinline__ void insertVoxel(const Ctx& c, uint64_t at) {
 __device__ void insertAll(const Ctx& c, const Point* batch, uint32_t numBatch, uint32_t numSpilled, uint32_t numSharedVoxels) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t i = tid; i < numBatch; i += stride) {
-        uint4 pt = ldPoint(batch + i);
-        uint32_t node = c.leafOf[i] & 0xffffffu;
-        if (c.leafRow[node] == 0) continue;               // only after an overflow flag
-        stPoint(pointSlotAddress(c, node, c.slotOf[i]), pt);
+    // two independent items per iteration: the three dependent lookups (item -> leaf row -> chunk) of one
+    // overlap with those of the other
+    for (uint32_t i = tid; i < numBatch; i += 2 * stride) {
+        const uint32_t i2 = i + stride;
+        const bool has2 = i2 < numBatch;
+        uint4 p1 = ldPoint(batch + i);
+        uint4 p2 = has2 ? ldPoint(batch + i2) : make_uint4(0, 0, 0, 0);
+        uint32_t n1 = c.leafOf[i] & 0xffffffu, s1 = c.slotOf[i];
+        uint32_t n2 = has2 ? (c.leafOf[i2] & 0xffffffu) : 0u, s2 = has2 ? c.slotOf[i2] : 0u;
+        uint32_t r1 = c.leafRow[n1], r2 = has2 ? c.leafRow[n2] : 0u;
+        if (r1) stPoint(pointSlotAddress(c, r1, s1), p1);
+        if (r2) stPoint(pointSlotAddress(c, r2, s2), p2);
     }
     for (uint32_t j = tid; j < numSpilled; j += stride) {
         uint4 pt = *reinterpret_cast<const uint4*>(c.spilled + j);
         uint32_t node = c.leafOf[scratch::MAX_BATCH + j] & 0xffffffu;
-        if (c.leafRow[node] == 0) continue;
-        stPoint(pointSlotAddress(c, node, c.slotOf[scratch::MAX_BATCH + j]), pt);
+        uint32_t row = c.leafRow[node];
+        if (row) stPoint(pointSlotAddress(c, row, c.slotOf[scratch::MAX_BATCH + j]), pt);
     }
-    // voxels: this block's own backlog segment, then the shared overflow part
-    const uint32_t own = c.blockCursor[blockIdx.x];
-    for (uint32_t e = threadIdx.x; e < own; e += blockDim.x) insertVoxel(c, (uint64_t)blockIdx.x * c.segCap + e);
+    // voxels: the per-block backlog segments are uneven, so every block first builds the prefix sums of
+    // the segment fills in shared memory and the whole grid then strides over the concatenation
+    __shared__ uint32_t sh_segStart[1025];
+    if (gridDim.x <= 1024) {
+        uint32_t total = 0;
+        for (uint32_t b0 = 0; b0 < gridDim.x; b0 += blockDim.x) {
+            uint32_t b = b0 + threadIdx.x;
+            uint32_t v = b < gridDim.x ? c.blockCursor[b] : 0u;
+            uint32_t chunkTotal = 0;
+            uint32_t off = blockExclusiveScan(v, chunkTotal);
+            if (b < gridDim.x) sh_segStart[b] = total + off;
+            total += chunkTotal;
+        }
+        if (threadIdx.x == 0) sh_segStart[gridDim.x] = total;
+        __syncthreads();
+        for (uint32_t v = tid; v < total; v += stride) {
+            uint32_t lo = 0, hi = gridDim.x;                     // last segment with start <= v
+            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (sh_segStart[mid] <= v) lo = mid; else hi = mid; }
+            insertVoxel(c, (uint64_t)lo * c.segCap + (v - sh_segStart[lo]));
+        }
+    } else {
+        const uint32_t own = c.blockCursor[blockIdx.x];
+        for (uint32_t e = threadIdx.x; e < own; e += blockDim.x) insertVoxel(c, (uint64_t)blockIdx.x * c.segCap + e);
+    }
     for (uint32_t b = tid; b < numSharedVoxels; b += stride) insertVoxel(c, scratch::VOXEL_CAP - scratch::VOXEL_SHARED + b);
 }
 
