@@ -293,6 +293,74 @@ __device__ __forceinline__ void voxelPassEnd(const Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// block-local leaf counting. A scan is spatially coherent, so at any moment most of the grid
+// counts into the same handful of leaves, and one atomicAdd(counter) per warp per iteration
+// (what the reference does, voxels.cu:203-218) makes those counters the hottest addresses of the
+// pass — with the returned value on every warp's critical path. Here a warp takes a block-local
+// rank from a shared-memory table instead; when the block has finished its pass it adds each
+// leaf's total to the global counter once (where the spill / first-touch detection now happens)
+// and turns the provisional ranks of its items into slots.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t PROVISIONAL = 0x80000000u;
+__shared__ uint32_t sh_leafKey[VOXTAB_SIZE];
+__shared__ uint32_t sh_leafCount[VOXTAB_SIZE];
+__shared__ uint32_t sh_leafBase[VOXTAB_SIZE];
+
+// the global step: add `cnt` points to a leaf's counter; first-touch and spill detection (voxels.cu:203-218)
+__device__ __noinline__ uint32_t countGlobal(const Ctx& c, uint32_t node, uint32_t level, uint32_t cnt) {
+    Node* leaf = &c.nodes[node];
+    uint32_t old = atomicAdd(&leaf->counter, cnt);
+    uint32_t stored = ldv(&leaf->numPoints);
+    if (old == stored) {                                     // first points of this leaf in this batch
+        uint32_t d = atomicAdd(&c.bc->numDirtyLeaves, 1u);
+        c.dirtyLeaves[d] = node;
+    }
+    if (old <= SIMLOD_MAX_POINTS_PER_NODE && old + cnt > SIMLOD_MAX_POINTS_PER_NODE) {
+        // this leaf spills (voxels.cu:211-217). Reserve everything its split needs right here, so the
+        // split round is one phase: room in the spill buffer, 8 node slots, the occupancy grid.
+        uint32_t s = atomicAdd(&c.bc->numSpillTotal, 1u);
+        if (s < scratch::SPILLNODE_CAP) {
+            SpillInfo info;
+            info.node = node;
+            info.stored = stored;
+            info.level = level;
+            info.row = c.leafRow[node];
+            info.base = stored ? atomicAdd(&c.bc->numSpilled, stored) : 0u;
+            if ((uint64_t)info.base + stored > scratch::SPILL_CAP) atomicOr(&c.ctl->errorFlags, ERR_SPILL_OVERFLOW);
+            info.childBase = atomicAdd(&c.stats->numNodes, 8u);                                // voxels.cu:317
+            if (info.childBase + 8 > scratch::NODE_CAP) atomicOr(&c.ctl->errorFlags, ERR_NODE_OVERFLOW);
+            uint64_t g = c.gridPtr[node];
+            if (g == 0) g = (uint64_t)(c.heapBytes + atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)SIMLOD_GRID_STRIDE));   // voxels.cu:363-365
+            info.grid = g;
+            c.spill[s] = info;
+        } else {
+            atomicOr(&c.ctl->errorFlags, ERR_SPILLNODE_OVERFLOW);
+        }
+    }
+    return old;
+}
+
+__device__ __forceinline__ uint32_t tabFind(const uint32_t* keys, uint32_t key) {
+    uint32_t h = (key * 0x9E3779B1u) >> 26;
+    for (uint32_t probe = 0; probe < VOXTAB_SIZE; probe++) {
+        uint32_t s = (h + probe) & (VOXTAB_SIZE - 1);
+        uint32_t k = keys[s];
+        if (k == key) return s;
+        if (k == VOXTAB_EMPTY) break;
+    }
+    return VOXTAB_EMPTY;
+}
+__device__ __forceinline__ uint32_t tabInsert(uint32_t* keys, uint32_t key) {
+    uint32_t h = (key * 0x9E3779B1u) >> 26;
+    for (uint32_t probe = 0; probe < VOXTAB_SIZE; probe++) {
+        uint32_t s = (h + probe) & (VOXTAB_SIZE - 1);
+        uint32_t k = atomicCAS(&keys[s], VOXTAB_EMPTY, key);
+        if (k == VOXTAB_EMPTY || k == key) return s;
+    }
+    return VOXTAB_EMPTY;
+}
+
+// ------------------------------------------------------------------------------------------
 // the per-point walk: descend from (node, level) to the leaf; optionally voxel-sample every
 // node on the way that owns an occupancy grid; optionally count the point into the leaf.
 // Warp-synchronous: all 32 lanes call it together, `valid` masks lanes without an item.
@@ -356,44 +424,17 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
     if (COUNT) {
         uint32_t vmask = __ballot_sync(FULL, valid);
         if (valid) {
-            // warp-aggregated leaf counter (voxels.cu:203-218)
             uint32_t peers = __match_any_sync(vmask, node);
             uint32_t leader = __ffs(peers) - 1;
             uint32_t cnt = __popc(peers);
-            uint32_t old = 0;
+            uint32_t r = 0;
             if (lane == leader) {
-                Node* leaf = &c.nodes[node];
-                old = atomicAdd(&leaf->counter, cnt);
-                uint32_t stored = ldv(&leaf->numPoints);
-                if (old == stored) {                                     // first point of this leaf in this batch
-                    uint32_t d = atomicAdd(&c.bc->numDirtyLeaves, 1u);
-                    c.dirtyLeaves[d] = node;
-                }
-                if (old <= SIMLOD_MAX_POINTS_PER_NODE && old + cnt > SIMLOD_MAX_POINTS_PER_NODE) {
-                    // this leaf spills (voxels.cu:211-217). Reserve everything its split needs right here, so the
-                    // split round is one phase: room in the spill buffer, 8 node slots, the occupancy grid.
-                    uint32_t s = atomicAdd(&c.bc->numSpillTotal, 1u);
-                    if (s < scratch::SPILLNODE_CAP) {
-                        SpillInfo info;
-                        info.node = node;
-                        info.stored = stored;
-                        info.level = level;
-                        info.row = c.leafRow[node];
-                        info.base = stored ? atomicAdd(&c.bc->numSpilled, stored) : 0u;
-                        if ((uint64_t)info.base + stored > scratch::SPILL_CAP) atomicOr(&c.ctl->errorFlags, ERR_SPILL_OVERFLOW);
-                        info.childBase = atomicAdd(&c.stats->numNodes, 8u);                                // voxels.cu:317
-                        if (info.childBase + 8 > scratch::NODE_CAP) atomicOr(&c.ctl->errorFlags, ERR_NODE_OVERFLOW);
-                        uint64_t g = c.gridPtr[node];
-                        if (g == 0) g = (uint64_t)(c.heapBytes + atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)SIMLOD_GRID_STRIDE));   // voxels.cu:363-365
-                        info.grid = g;
-                        c.spill[s] = info;
-                    } else {
-                        atomicOr(&c.ctl->errorFlags, ERR_SPILLNODE_OVERFLOW);
-                    }
-                }
+                uint32_t t = tabInsert(sh_leafKey, node);
+                if (t != VOXTAB_EMPTY) r = atomicAdd(&sh_leafCount[t], cnt) | PROVISIONAL;     // block-local rank
+                else                   r = countGlobal(c, node, level, cnt);                    // table full: final slot at once
             }
-            old = __shfl_sync(peers, old, leader);
-            slot = old + __popc(peers & ltmask);
+            r = __shfl_sync(peers, r, leader);
+            slot = r + __popc(peers & ltmask);
         }
     }
 }
@@ -405,7 +446,8 @@ template <bool SAMPLE, bool COUNT, bool FRESH>
 __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, uint32_t numSpilled) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (SAMPLE) voxelPassBegin(c, FRESH);
+    if (COUNT && threadIdx.x < VOXTAB_SIZE) { sh_leafKey[threadIdx.x] = VOXTAB_EMPTY; sh_leafCount[threadIdx.x] = 0; }
+    if (SAMPLE) voxelPassBegin(c, FRESH); else __syncthreads();
     // batch points: every block owns one contiguous run of the batch (scans are spatially coherent, so
     // all iterations of a block revisit the same upper-level nodes and occupancy words: L1 hits)
     // (re-walk passes touch a few contiguous runs of items, so they stay grid-strided to spread those runs)
@@ -448,6 +490,26 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
         if (valid && COUNT) { c.leafOf[scratch::MAX_BATCH + j] = lp; c.slotOf[scratch::MAX_BATCH + j] = slot; }
     }
     if (SAMPLE) voxelPassEnd(c);
+    if (COUNT) {
+        // flush the block's leaf table: one global add per distinct leaf, then provisional ranks -> slots
+        __syncthreads();
+        if (threadIdx.x < VOXTAB_SIZE) {
+            uint32_t leaf = sh_leafKey[threadIdx.x], cnt = sh_leafCount[threadIdx.x];
+            if (leaf != VOXTAB_EMPTY && cnt > 0) sh_leafBase[threadIdx.x] = countGlobal(c, leaf, c.nodes[leaf].level, cnt);
+        }
+        __syncthreads();
+        for (uint32_t base = blockFirst + (threadIdx.x - laneId()); base < blockEnd; base += step) {
+            uint32_t i = base + laneId();
+            if (i < blockEnd) {
+                uint32_t sl = c.slotOf[i];
+                if (sl & PROVISIONAL) c.slotOf[i] = sh_leafBase[tabFind(sh_leafKey, c.leafOf[i] & 0xffffffu)] + (sl & ~PROVISIONAL);
+            }
+        }
+        for (uint32_t j = tid; j < numSpilled; j += stride) {
+            uint32_t sl = c.slotOf[scratch::MAX_BATCH + j];
+            if (sl & PROVISIONAL) c.slotOf[scratch::MAX_BATCH + j] = sh_leafBase[tabFind(sh_leafKey, c.leafOf[scratch::MAX_BATCH + j] & 0xffffffu)] + (sl & ~PROVISIONAL);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -628,7 +690,8 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
         }
     }
 
-    for (uint32_t first = blockIdx.x * blockDim.x; first < numDirtyVox; first += stride) {
+    // (served from the other end of the grid, so that leaf and voxel-node allocation run side by side)
+    for (uint32_t first = (gridDim.x - 1 - blockIdx.x) * blockDim.x; first < numDirtyVox; first += stride) {
         const uint32_t d = first + threadIdx.x;
         uint32_t n = 0, cnt = 0, have = 0, existing = 0, needed = 0, nseg = 0, k0 = 0;
         Node* node = nullptr;
