@@ -439,6 +439,50 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA staging of the batch. In a first-visit pass every block streams its contiguous run of the
+// batch through two 16 KB shared-memory stages with 1-D bulk copies (cp.async.bulk ... mbarrier::
+// complete_tx, SASS: UBLKCP): one elected thread issues the copy of the next 1024-point tile while
+// the block walks the current one, so the HBM latency of the batch read leaves the critical path
+// and no registers or LSU slots are spent on it. Threads then read their point with one LDS.128.
+// ------------------------------------------------------------------------------------------
+#ifndef SIMLOD_NO_TMA
+#define SIMLOD_TMA 1
+#else
+#define SIMLOD_TMA 0
+#endif
+constexpr uint32_t TILE_POINTS = 1024;
+#if SIMLOD_TMA
+__shared__ __align__(128) uint4 sh_tile[2][TILE_POINTS];
+__shared__ __align__(8) uint64_t sh_tileBar[2];
+
+__device__ __forceinline__ void tileBarInit() {
+    if (threadIdx.x == 0) {
+        uint32_t b0 = (uint32_t)__cvta_generic_to_shared(&sh_tileBar[0]), b1 = (uint32_t)__cvta_generic_to_shared(&sh_tileBar[1]);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void tileLoad(uint32_t stage, const Point* src, uint32_t numPoints) {
+    uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sh_tileBar[stage]);
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sh_tile[stage][0]);
+    uint32_t bytes = numPoints * 16u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tileWait(uint32_t stage, uint32_t parity) {
+    uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sh_tileBar[stage]);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+#endif
+
 // one pass over batch points (ring slot) followed by the spilled points of this batch
 //   FRESH  : items start at the root (first visit); otherwise only items whose cached leaf has
 //            been split since are walked on, starting at that (now inner) node
@@ -455,6 +499,31 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
     const uint32_t blockFirst = FRESH ? blockIdx.x * perBlock : blockIdx.x * blockDim.x;
     const uint32_t blockEnd = FRESH ? min(numBatch, blockFirst + perBlock) : numBatch;
     const uint32_t step = FRESH ? blockDim.x : stride;
+#if SIMLOD_TMA
+    if (FRESH) {
+        const uint32_t runLen = blockFirst < blockEnd ? blockEnd - blockFirst : 0u;
+        const uint32_t numTiles = (runLen + TILE_POINTS - 1) / TILE_POINTS;
+        tileBarInit();
+        if (threadIdx.x == 0 && numTiles > 0) tileLoad(0, batch + blockFirst, min(TILE_POINTS, runLen));
+        for (uint32_t t = 0; t < numTiles; t++) {
+            const uint32_t tileFirst = blockFirst + t * TILE_POINTS;
+            if (threadIdx.x == 0 && t + 1 < numTiles)      // stage (t+1)&1 was drained at the barrier that ended iteration t-1
+                tileLoad((t + 1) & 1, batch + tileFirst + TILE_POINTS, min(TILE_POINTS, blockEnd - (tileFirst + TILE_POINTS)));
+            tileWait(t & 1, (t >> 1) & 1);
+#pragma unroll 1
+            for (uint32_t k = 0; k < TILE_POINTS / 256; k++) {
+                const uint32_t idx = k * 256 + threadIdx.x;
+                const uint32_t i = tileFirst + idx;
+                const bool valid = i < blockEnd;
+                uint4 pt = valid ? sh_tile[t & 1][idx] : make_uint4(0, 0, 0, 0);
+                uint32_t lp = 0, slot = 0;
+                walk<SAMPLE, COUNT>(c, valid, pt, 0, 0, lp, slot);
+                if (valid && COUNT) { c.leafOf[i] = lp; c.slotOf[i] = slot; }
+            }
+            __syncthreads();
+        }
+    } else
+#endif
     for (uint32_t base = blockFirst + (threadIdx.x - laneId()); base < blockEnd; base += step) {
         uint32_t i = base + laneId();
         bool valid = i < blockEnd;
@@ -464,14 +533,12 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
             node = lp & 0xffffffu; level = lp >> 24;
             valid = c.firstChild[node] != 0 && level < SIMLOD_MAX_DEPTH;
         }
+        if (!FRESH && !__any_sync(0xffffffffu, valid)) continue;
         uint4 pt = make_uint4(0, 0, 0, 0);
         if (valid) pt = ldPoint(batch + i);
         uint32_t lp = 0, slot = 0;
         walk<SAMPLE, COUNT>(c, valid, pt, node, level, lp, slot);
         if (valid && COUNT) { c.leafOf[i] = lp; c.slotOf[i] = slot; }
-#if defined(EXP_NO_COUNT) || defined(EXP_DESCEND_ONLY)
-        if (valid && lp == 0xffffffffu) c.slotOf[i] = lp;     // keep the walk alive for the optimiser
-#endif
     }
     // spilled points (always carry a cached start node: the leaf they were spilled from)
     for (uint32_t base = tid - laneId(); base < numSpilled; base += stride) {

@@ -97,6 +97,7 @@ struct SimlodContext {
     int numSMs = 0;
     CUstream streamMain = nullptr, streamUpload = nullptr;
     CUevent evStart = nullptr, evEnd = nullptr, evTotalStart = nullptr, evTotalEnd = nullptr;
+    CUevent evBurst[8][2] = {};        // event pairs for launches enqueued back to back
     SimlodConfig cfg{};
     SimlodUniforms uniforms{};
     SimlodBuffers buf{};
@@ -193,6 +194,21 @@ int publishBatch(SimlodContext* ctx, uint32_t slot, uint32_t count) {
     return SIMLOD_OK;
 }
 
+// enqueue one kernel_construct launch between the event pair `slot` without waiting for it
+int enqueueConstruct(SimlodContext* ctx, int slot) {
+    SimlodUniforms u = ctx->uniforms;
+    u.frameCounter = ctx->frameCounter;
+    CUdeviceptr ring = ctx->buf.ring, momentary = ctx->buf.momentary, persistent = ctx->buf.persistent, nodes = ctx->buf.nodes,
+                stats = ctx->buf.stats, frameStart = ctx->frameStart, cudaprint = ctx->cudaprint,
+                nbu = ctx->numBatchesUploaded, bs = ctx->batchSizes;
+    void* args[] = {&u, &ring, &momentary, &persistent, &nodes, &stats, &frameStart, &cudaprint, &nbu, &bs};   // main.cpp:374-382
+    CU(D(cuEventRecord)(ctx->evBurst[slot][0], ctx->streamMain));
+    CU(D(cuLaunchCooperativeKernel)(ctx->programs[SIMLOD_PROGRAM_CONSTRUCT].fn, ctx->constructBlocks, 1, 1, 256, 1, 1, 0, ctx->streamMain, args));
+    CU(D(cuEventRecord)(ctx->evBurst[slot][1], ctx->streamMain));
+    ctx->launches++;
+    return SIMLOD_OK;
+}
+
 int launchConstruct(SimlodContext* ctx, float* ms) {
     SimlodUniforms u = ctx->uniforms;
     u.frameCounter = ctx->frameCounter;
@@ -237,6 +253,7 @@ int simlod_create(const SimlodConfig* config, SimlodContext** out) {
     CU(D(cuEventCreate)(&ctx->evEnd, CU_EVENT_DEFAULT));
     CU(D(cuEventCreate)(&ctx->evTotalStart, CU_EVENT_DEFAULT));
     CU(D(cuEventCreate)(&ctx->evTotalEnd, CU_EVENT_DEFAULT));
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 2; j++) CU(D(cuEventCreate)(&ctx->evBurst[i][j], CU_EVENT_DEFAULT));
 
     // programs (main.cpp:603-626)
     for (int p = 0; p < 3; p++) {
@@ -319,6 +336,7 @@ void simlod_destroy(SimlodContext* ctx) {
         if (ctx->evEnd) D(cuEventDestroy)(ctx->evEnd);
         if (ctx->evTotalStart) D(cuEventDestroy)(ctx->evTotalStart);
         if (ctx->evTotalEnd) D(cuEventDestroy)(ctx->evTotalEnd);
+        for (int i = 0; i < 8; i++) for (int j = 0; j < 2; j++) if (ctx->evBurst[i][j]) D(cuEventDestroy)(ctx->evBurst[i][j]);
         if (ctx->streamMain) D(cuStreamDestroy)(ctx->streamMain);
         if (ctx->streamUpload) D(cuStreamDestroy)(ctx->streamUpload);
         D(cuDevicePrimaryCtxRelease)(ctx->device);
@@ -425,10 +443,18 @@ static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr
             if (rc) return rc;
             next++;
         }
-        float ms = 0.0f;
-        rc = launchConstruct(ctx, &ms); if (rc) return rc;
-        total += ms;
+        // The reference launches updateOctree once per frame while uploads stream in (main.cpp:1176-1180).
+        // Without a frame to draw in between, launches are enqueued back to back — each consumes at most
+        // 20 batches or 10 ms — and Stats is read once per burst.
+        const uint32_t pendingBatches = ctx->uploaded - ctx->processed;
+        int burst = (int)std::min<uint32_t>(8u, std::max<uint32_t>(1u, (pendingBatches + 19u) / 20u + 1u));
+        for (int k = 0; k < burst; k++) { rc = enqueueConstruct(ctx, k); if (rc) return rc; }
         rc = readStats(ctx); if (rc) return rc;
+        for (int k = 0; k < burst; k++) {
+            float ms = 0.0f;
+            CU(D(cuEventElapsedTime)(&ms, ctx->evBurst[k][0], ctx->evBurst[k][1]));
+            total += ms;
+        }
         if (ctx->hStats->memCapacityReached) return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed);
     }
     CU(D(cuEventRecord)(ctx->evTotalEnd, ctx->streamMain));
