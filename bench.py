@@ -316,7 +316,8 @@ def main():
                        "octree": {k: totals[k] for k in ("numNodes", "numInner", "numLeaves", "numPoints", "numVoxels", "allocatedBytes_persistent")},
                        "construct_blocks": info1["construct_blocks"], "datagen_s": round(t_gen, 1)},
             "roofline": {"bound": "hbm", "kernel": "kernel_construct", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 5), "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "frac": round(achieved / peak, 5),
+                         "traffic": round((traffic or {}).get("dram_bytes_per_batch", 0) * K / n_launch) if traffic else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_point": round(alg_bytes / npts, 3), "spilled_fraction_s": round(s_frac, 4),
                          "voxels_per_point_v": round(v_frac, 4), "launches": launches,

@@ -447,7 +447,7 @@ static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr
         // Without a frame to draw in between, launches are enqueued back to back — each consumes at most
         // 20 batches or 10 ms — and Stats is read once per burst.
         const uint32_t pendingBatches = ctx->uploaded - ctx->processed;
-        int burst = (int)std::min<uint32_t>(8u, std::max<uint32_t>(1u, (pendingBatches + 19u) / 20u + 1u));
+        int burst = (int)std::min<uint32_t>(8u, std::max<uint32_t>(1u, (pendingBatches + 19u) / 20u));
         for (int k = 0; k < burst; k++) { rc = enqueueConstruct(ctx, k); if (rc) return rc; }
         rc = readStats(ctx); if (rc) return rc;
         for (int k = 0; k < burst; k++) {
