@@ -134,6 +134,72 @@ def recorded_traffic():
     return None
 
 
+def bench_las(batches, mn, mx, device):
+    """LAS format-2 records (26 B/point) -> 16-byte points: device decode with the records resident in HBM, end to end
+    from pinned host memory, and the reference's own CPU loader (oracle/_ref/libref_las.so = LasLoader.cpp) beside it."""
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle
+    from simlod_b200 import SimLOD, data
+    nb = min(8, len(batches))
+    scale, offset = (0.001, 0.001, 0.001), (0.0, 0.0, 0.0)
+    recs = [data.las_records(b, 2, scale, offset) for b in batches[:nb]]
+    bpp = recs[0].shape[1]
+    n = nb * BATCH
+    sim = SimLOD(320, 176, device=device, persistent_bytes=1 << 30)
+    out = {"format": 2, "bytes_per_point": bpp, "points": n}
+    try:
+        sim.set_box(mn, mx)
+        layout = sim.las_layout(bpp, 2, scale, offset)
+        dptr = sim.device_alloc(n * bpp)
+        hptr = sim.host_alloc(n * bpp)
+        host = np.ctypeslib.as_array((ctypes.c_uint8 * (n * bpp)).from_address(hptr))
+        host[:] = np.concatenate(recs).reshape(-1)
+        sim.memcpy_htod(dptr, host)
+        for mode in ("device", "host"):
+            best = None
+            for rep in range(3):
+                sim.reset(); sim.flush_l2(); sim.synchronize()
+                t0 = time.perf_counter()
+                for k in range(nb):
+                    if mode == "device":
+                        sim.upload_batch_las_device(dptr + k * BATCH * bpp, BATCH, layout)
+                    else:
+                        sim._check(sim._lib.simlod_upload_batch_las(sim._ctx, hptr + k * BATCH * bpp, BATCH, ctypes.byref(layout)))
+                sim.synchronize()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            key = "value" if mode == "device" else "e2e"
+            out[key] = {"value": round(n / best / 1e6, 1), "unit": "Mpoints/s",
+                        "how": "records resident in HBM" if mode == "device" else "records in pinned host memory, H2D inside the timed region"}
+        got = sim.ring_slot(nb - 1, 1000)
+        want = oracle.decode_las(recs[nb - 1][:1000], 1000, bpp, 2, scale, offset)
+        assert (got == want).all()
+        out["roofline"] = {"bound": "hbm", "algorithmic_bytes_per_point": bpp + 16,
+                           "achieved_gbs": round(out["value"]["value"] * 1e6 * (bpp + 16) / 1e9, 1)}
+    finally:
+        sim.close()
+    if oracle.ref_las() is not None:
+        d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        path = os.path.join(d, "simlod_bench_%d.las" % os.getpid())
+        try:
+            data.write_las(path, np.concatenate(batches[:nb]), 2, scale, offset)
+            threads = min(32, os.cpu_count() or 1)
+            def load(k):
+                return oracle.ref_las_load(path, k * (n // (nb * 4)), n // (nb * 4))
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(load, range(4)))                      # page cache warm-up
+                t0 = time.perf_counter()
+                list(ex.map(load, range(nb * 4)))
+                dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": round(n / dt / 1e6, 1), "unit": "Mpoints/s", "cores": threads, "kind": "reference",
+                                   "sample": "loadLasNative (LasLoader.cpp compiled from /root/reference) on %d M points from tmpfs, %d x 250k-point reads" % (n // 1000000, nb * 4)}
+        finally:
+            if os.path.exists(path):
+                os.remove(path)
+    return out
+
+
 def run_reference(args, rank, world):
     """The reference's algorithm on the host cores: oracle port (the reference has no CPU octree
     builder to compile; its kernels need a GPU). One step = one full 1 M-point batch."""
@@ -281,6 +347,14 @@ def main():
     finally:
         sampler.stop()
 
+    # ---- "next" row: LAS record decode, rank 0 at N = 1 ------------------------------
+    las = None
+    if rank == 0 and world == 1:
+        try:
+            las = bench_las(batches, mn, mx, local_rank)
+        except Exception as e:          # the row is reported, never fatal for the headline
+            las = {"error": repr(e)}
+
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample -----------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -333,6 +407,8 @@ def main():
             line["cpu_baseline"] = cpu
         if render:
             line["render"] = render
+        if las:
+            line["las_decode"] = las
         print(json.dumps(line), flush=True)
     sim.close()
     if world > 1:

@@ -86,6 +86,21 @@ int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t c
 // same with the whole point set resident in device memory (batches are copied device-to-device)
 int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms, float* total_ms);
 
+// LAS front end. The reference decodes LAS point records on CPU threads
+// (loadLasNative, LasLoader.cpp:169-226) and uploads 16-byte points; here the raw records are uploaded
+// and decoded on the device straight into the next ring slot, then published like any batch.
+// `format` selects the RGB offset as the reference does (2 -> 20, 3/5 -> 28, 7 -> 30, else no colour);
+// x = double(X) * scale + (offset + translation), narrowed to float (LasLoader.cpp:199-210).
+typedef struct SimlodLasLayout {
+    uint32_t bytes_per_point;       // LasHeader::bytesPerPoint (<= 96)
+    uint32_t format;                // LasHeader::format
+    double   scale[3];
+    double   offset[3];
+    double   translation[3];        // the host passes -min (main.cpp:868-873), so that boxMin = 0
+} SimlodLasLayout;
+int simlod_upload_batch_las(SimlodContext* ctx, const void* host_records, uint32_t count, const SimlodLasLayout* layout);
+int simlod_upload_batch_las_device(SimlodContext* ctx, uint64_t device_records, uint32_t count, const SimlodLasLayout* layout);
+
 // renderCUDA (main.cpp:465-546): one cooperative launch of kernel_render into the surface.
 int simlod_render(SimlodContext* ctx, float* kernel_ms);
 
@@ -121,6 +136,8 @@ int simlod_get_launch_info(SimlodContext* ctx, uint64_t* launches, uint32_t* con
 // MUFU.RCP(x) as the device computes it (the one float a CPU restatement cannot derive when the
 // octree cube size is not a power of two; see oracle/)
 int simlod_device_rcp(SimlodContext* ctx, float x, float* out);
+// wait for everything this context has enqueued (uploads, decodes, launches)
+int simlod_synchronize(SimlodContext* ctx);
 // flush the L2 cache by overwriting a scratch buffer larger than it (bench hygiene)
 int simlod_flush_l2(SimlodContext* ctx);
 

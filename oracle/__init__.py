@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "liboracle.so")
 REF_DIR = os.path.join(_HERE, "_ref")
 REF_CUBINS = {0: os.path.join(REF_DIR, "ref_construct.cubin"), 1: os.path.join(REF_DIR, "ref_render.cubin"),
               2: os.path.join(REF_DIR, "ref_reset.cubin")}
+REF_LAS_LIB = os.path.join(REF_DIR, "libref_las.so")
 REF_MOMENTARY_BYTES = 420_000_000      # the reference carves 408 800 192 B out of its 300 MB buffer
 
 POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("color", "<u4")])
@@ -66,6 +67,7 @@ def lib():
         L.oracle_check_voxel_colors.argtypes = [vp, vp]
         L.canon_render.argtypes = [vp, vp, vp, C.POINTER(RenderStats)]
         L.canon_flags.argtypes = [vp, vp]
+        L.oracle_decode_las.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -162,3 +164,35 @@ def compare_canon(a, b, what="octree"):
 
 def compare_stats(a, b, fields=STATS_FIELDS):
     return ["Stats.%s: %d != %d" % (f, getattr(a, f), getattr(b, f)) for f in fields if int(getattr(a, f)) != int(getattr(b, f))]
+
+
+# ---- LAS decode -------------------------------------------------------------------
+def decode_las(records, count, bytes_per_point, fmt, scale, offset, translation=(0.0, 0.0, 0.0)):
+    """CPU restatement of the parse loop of loadLasNative (oracle.cpp:oracle_decode_las)."""
+    rec = np.ascontiguousarray(records, dtype=np.uint8)
+    out = np.empty(count, dtype=POINT_DTYPE)
+    sc, of, tr = (np.asarray(v, dtype=np.float64) for v in (scale, offset, translation))
+    lib().oracle_decode_las(rec.ctypes.data, count, bytes_per_point, fmt, sc.ctypes.data, of.ctypes.data, tr.ctypes.data, out.ctypes.data)
+    return out
+
+
+_ref_las = None
+
+
+def ref_las():
+    """The reference's own LasLoader.cpp compiled into oracle/_ref/libref_las.so (None if not built)."""
+    global _ref_las
+    if _ref_las is None and os.path.exists(REF_LAS_LIB):
+        L = C.CDLL(REF_LAS_LIB)
+        L.ref_las_load.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.ref_las_header.argtypes = [C.c_char_p] + [C.c_void_p] * 8
+        _ref_las = L
+    return _ref_las
+
+
+def ref_las_load(path, first, count, translation=(0.0, 0.0, 0.0)):
+    """loadLasNative of the reference (CPU): returns `count` 16-byte points."""
+    out = np.zeros(count, dtype=POINT_DTYPE)
+    tr = np.asarray(translation, dtype=np.float64)
+    ref_las().ref_las_load(path.encode(), first, count, out.ctypes.data, tr.ctypes.data)
+    return out

@@ -596,3 +596,30 @@ void canon_flags(void* h, uint8_t* out) {
 }
 
 }  // extern "C"
+
+// ---- LAS record decode: restatement of loadLasNative's parse loop, LasLoader.cpp:176-225 ----
+extern "C" void oracle_decode_las(const uint8_t* records, uint64_t numPoints, uint32_t bytesPerPoint, uint32_t format,
+                                  const double* scale, const double* offset, const double* translation, SimlodPoint* out) {
+    uint64_t offsetRgb = 0;                                   // :179-188
+    if (format == 2) offsetRgb = 20; else if (format == 3) offsetRgb = 28;
+    if (format == 5) offsetRgb = 28;
+    if (format == 7) offsetRgb = 30;
+    const double ox = offset[0] + translation[0], oy = offset[1] + translation[1], oz = offset[2] + translation[2];   // :199-201
+    for (uint64_t i = 0; i < numPoints; i++) {
+        const uint8_t* src = records + bytesPerPoint * i;
+        int32_t XYZ[3];
+        memcpy(XYZ, src, 12);
+        SimlodPoint p;
+        volatile double mx = double(XYZ[0]) * scale[0], my = double(XYZ[1]) * scale[1], mz = double(XYZ[2]) * scale[2];   // no contraction
+        p.x = (float)(mx + ox); p.y = (float)(my + oy); p.z = (float)(mz + oz);                                            // :206-208
+        uint32_t color = 0xff000000u;                         // alpha (and colour without RGB) is uninitialised in the reference: compared under a mask
+        if (offsetRgb > 0) {
+            uint16_t rgb[3];
+            memcpy(rgb, src + offsetRgb, 6);
+            uint32_t r = rgb[0] > 255 ? rgb[0] / 256 : rgb[0], g = rgb[1] > 255 ? rgb[1] / 256 : rgb[1], b = rgb[2] > 255 ? rgb[2] / 256 : rgb[2];   // :212-217
+            color |= r | (g << 8) | (b << 16);
+        }
+        p.color = color;
+        out[i] = p;
+    }
+}

@@ -89,6 +89,11 @@ class Config(C.Structure):
     ]
 
 
+class LasLayout(C.Structure):
+    _fields_ = [("bytes_per_point", C.c_uint32), ("format", C.c_uint32), ("scale", C.c_double * 3), ("offset", C.c_double * 3),
+                ("translation", C.c_double * 3)]
+
+
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "nodes", "nodes_bytes", "persistent", "persistent_bytes", "momentary", "momentary_bytes",
@@ -101,10 +106,10 @@ assert C.sizeof(Uniforms) == 480 and C.sizeof(Stats) == 112
 EXPORTS = [
     "simlod_create", "simlod_destroy", "simlod_last_error", "simlod_use_module", "simlod_set_uniforms",
     "simlod_get_uniforms", "simlod_reset", "simlod_upload_batch", "simlod_upload_batch_device",
-    "simlod_update_octree", "simlod_insert", "simlod_insert_device", "simlod_render", "simlod_get_stats",
+    "simlod_upload_batch_las", "simlod_upload_batch_las_device", "simlod_update_octree", "simlod_insert", "simlod_insert_device", "simlod_render", "simlod_get_stats",
     "simlod_read_framebuffer", "simlod_read_surface", "simlod_get_buffers", "simlod_memcpy_dtoh",
     "simlod_memcpy_htod", "simlod_host_alloc", "simlod_host_free", "simlod_device_alloc", "simlod_device_free",
-    "simlod_get_launch_info", "simlod_device_rcp", "simlod_flush_l2",
+    "simlod_get_launch_info", "simlod_device_rcp", "simlod_synchronize", "simlod_flush_l2",
 ]
 
 _lib = None
@@ -129,6 +134,8 @@ def load_library():
         "simlod_reset": [vp],
         "simlod_upload_batch": [vp, vp, u32],
         "simlod_upload_batch_device": [vp, u64, u32],
+        "simlod_upload_batch_las": [vp, vp, u32, C.POINTER(LasLayout)],
+        "simlod_upload_batch_las_device": [vp, u64, u32, C.POINTER(LasLayout)],
         "simlod_update_octree": [vp, C.POINTER(C.c_float)],
         "simlod_insert": [vp, vp, u64, C.POINTER(C.c_float), C.POINTER(C.c_float)],
         "simlod_insert_device": [vp, u64, u64, C.POINTER(C.c_float), C.POINTER(C.c_float)],
@@ -146,6 +153,7 @@ def load_library():
         "simlod_get_launch_info": [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)],
         "simlod_device_rcp": [vp, C.c_float, C.POINTER(C.c_float)],
         "simlod_flush_l2": [vp],
+        "simlod_synchronize": [vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -277,6 +285,24 @@ class SimLOD:
     def upload_batch_device(self, device_ptr, count):
         self._check(self._lib.simlod_upload_batch_device(self._ctx, int(device_ptr), int(count)))
 
+    @staticmethod
+    def las_layout(bytes_per_point, fmt, scale, offset, translation=(0.0, 0.0, 0.0)):
+        return LasLayout(bytes_per_point, fmt, (C.c_double * 3)(*scale), (C.c_double * 3)(*offset), (C.c_double * 3)(*translation))
+
+    def upload_batch_las(self, records, count, layout):
+        """Upload `count` raw LAS point records (uint8 array) and decode them on the device into the next ring slot."""
+        rec = np.ascontiguousarray(records, dtype=np.uint8)
+        assert rec.nbytes >= count * layout.bytes_per_point
+        self._check(self._lib.simlod_upload_batch_las(self._ctx, rec.ctypes.data, int(count), C.byref(layout)))
+
+    def upload_batch_las_device(self, device_ptr, count, layout):
+        self._check(self._lib.simlod_upload_batch_las_device(self._ctx, int(device_ptr), int(count), C.byref(layout)))
+
+    def ring_slot(self, slot, count):
+        """Read back `count` points of ring slot `slot` (tests)."""
+        b = self.buffers()
+        return self.memcpy_dtoh(b.ring + slot * MAX_BATCH_SIZE * 16, count * 16).view(POINT_DTYPE)
+
     def update_octree(self):
         ms = C.c_float(0)
         self._check(self._lib.simlod_update_octree(self._ctx, C.byref(ms)))
@@ -383,6 +409,9 @@ class SimLOD:
         out = C.c_float()
         self._check(self._lib.simlod_device_rcp(self._ctx, float(x), C.byref(out)))
         return np.float32(out.value)
+
+    def synchronize(self):
+        self._check(self._lib.simlod_synchronize(self._ctx))
 
     def flush_l2(self):
         self._check(self._lib.simlod_flush_l2(self._ctx))

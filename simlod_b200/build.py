@@ -21,7 +21,7 @@ NVCC = os.path.join(CUDA, "bin", "nvcc")
 BIN2C = os.path.join(CUDA, "bin", "bin2c")
 LIB = os.path.join(ROOT, "simlod_b200", "libsimlod_b200.so")
 CUBIN_DIR = os.path.join(ROOT, "simlod_b200", "cubin")
-PROGRAMS = ["construct", "render", "reset", "util"]
+PROGRAMS = ["construct", "render", "reset", "util", "las"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -90,6 +90,13 @@ def build_oracle(force=False):
         if force or not _newer(tool, [tool_src]):
             _run(["g++", "-O1", "-std=c++17", tool_src, "-I" + os.path.join(CUDA, "include"), "-L" + os.path.join(CUDA, "lib64"),
                   "-lnvrtc", "-lnvJitLink", "-Wl,-rpath," + os.path.join(CUDA, "lib64"), "-o", tool])
+        # the reference's CPU LAS loader: LasLoader.cpp compiles from its own single source file
+        las = os.path.join(refdir, "libref_las.so")
+        shim = os.path.join(odir, "ref_las_shim.cpp")
+        if force or not _newer(las, [shim]):
+            po = os.path.join(ref_root, "modules", "progressive_octree")
+            _run(["g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-w", "-I" + po, "-I" + os.path.join(ref_root, "include"),
+                  "-I" + os.path.join(ref_root, "libs", "fmt", "include"), os.path.join(po, "LasLoader.cpp"), shim, "-o", las])
         outs = [os.path.join(refdir, n) for n in ("ref_construct.cubin", "ref_render.cubin", "ref_reset.cubin")]
         if force or not all(os.path.exists(o) for o in outs):
             _run([tool, ref_root, refdir, "100"], cwd=odir)

@@ -25,6 +25,7 @@ extern const unsigned char simlod_cubin_construct[];
 extern const unsigned char simlod_cubin_render[];
 extern const unsigned char simlod_cubin_reset[];
 extern const unsigned char simlod_cubin_util[];
+extern const unsigned char simlod_cubin_las[];
 }
 
 namespace {
@@ -106,7 +107,9 @@ struct SimlodContext {
     CUsurfObject surface = 0;
     SimlodStats* hStats = nullptr;     // pinned
     Program programs[3];
-    CUmodule utilModule = nullptr;
+    CUmodule utilModule = nullptr, lasModule = nullptr;
+    CUfunction fnLas = nullptr;
+    CUdeviceptr lasStaging = 0;        // raw LAS records of the batch being decoded
     CUfunction fnRcp = nullptr, fnFill = nullptr;
     uint32_t uploaded = 0;             // batches published to the device
     uint32_t processed = 0;            // Stats::batchletIndex as last read
@@ -263,6 +266,8 @@ int simlod_create(const SimlodConfig* config, SimlodContext** out) {
     CU(D(cuModuleLoadData)(&ctx->utilModule, simlod_cubin_util));
     CU(D(cuModuleGetFunction)(&ctx->fnRcp, ctx->utilModule, "simlod_util_rcp"));
     CU(D(cuModuleGetFunction)(&ctx->fnFill, ctx->utilModule, "simlod_util_fill"));
+    CU(D(cuModuleLoadData)(&ctx->lasModule, simlod_cubin_las));
+    CU(D(cuModuleGetFunction)(&ctx->fnLas, ctx->lasModule, "simlod_las_decode"));
 
     // buffers (main.cpp:552-586)
     SimlodBuffers& b = ctx->buf;
@@ -332,6 +337,8 @@ void simlod_destroy(SimlodContext* ctx) {
         if (ctx->hStats) D(cuMemFreeHost)(ctx->hStats);
         for (int p = 0; p < 3; p++) if (ctx->programs[p].module) D(cuModuleUnload)(ctx->programs[p].module);
         if (ctx->utilModule) D(cuModuleUnload)(ctx->utilModule);
+        if (ctx->lasModule) D(cuModuleUnload)(ctx->lasModule);
+        if (ctx->lasStaging) D(cuMemFree)(ctx->lasStaging);
         if (ctx->evStart) D(cuEventDestroy)(ctx->evStart);
         if (ctx->evEnd) D(cuEventDestroy)(ctx->evEnd);
         if (ctx->evTotalStart) D(cuEventDestroy)(ctx->evTotalStart);
@@ -418,6 +425,50 @@ int simlod_upload_batch(SimlodContext* ctx, const SimlodPoint* host_points, uint
 int simlod_upload_batch_device(SimlodContext* ctx, uint64_t device_points, uint32_t count) {
     if (!device_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
     return uploadCommon(ctx, nullptr, (CUdeviceptr)device_points, count);
+}
+
+static int uploadLasCommon(SimlodContext* ctx, const void* host, CUdeviceptr dev, uint32_t count, const SimlodLasLayout* layout) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!layout) return fail(SIMLOD_ERR_INVALID, "null layout");
+    if (count > SLOT_POINTS) return fail(SIMLOD_ERR_INVALID, "batch of %u points exceeds the ring slot size of %llu", count, (unsigned long long)SLOT_POINTS);
+    if (layout->bytes_per_point < 12 || layout->bytes_per_point > 96) return fail(SIMLOD_ERR_INVALID, "unsupported LAS record size %u", layout->bytes_per_point);
+    uint32_t offsetRgb = 0;                                   // LasLoader.cpp:179-188
+    if (layout->format == 2) offsetRgb = 20; else if (layout->format == 3) offsetRgb = 28;
+    if (layout->format == 5) offsetRgb = 28;
+    if (layout->format == 7) offsetRgb = 30;
+    if (offsetRgb && offsetRgb + 6 > layout->bytes_per_point) return fail(SIMLOD_ERR_INVALID, "LAS format %u does not fit %u-byte records", layout->format, layout->bytes_per_point);
+    if (ctx->uploaded - ctx->processed >= RING_SLOTS) {
+        rc = readStats(ctx); if (rc) return rc;
+        if (ctx->uploaded - ctx->processed >= RING_SLOTS) return fail(SIMLOD_ERR_RING_FULL, "all %llu ring slots hold unprocessed batches", (unsigned long long)RING_SLOTS);
+    }
+    uint32_t slot = ctx->uploaded % RING_SLOTS;
+    CUdeviceptr dst = ctx->buf.ring + (uint64_t)slot * SLOT_POINTS * sizeof(SimlodPoint);
+    if (count) {
+        CUdeviceptr records = dev;
+        if (host) {
+            if (!ctx->lasStaging) CU(D(cuMemAlloc)(&ctx->lasStaging, (size_t)SLOT_POINTS * 96));
+            records = ctx->lasStaging;                        // reused batch after batch: copy and decode are ordered by the upload stream
+            CU(D(cuMemcpyHtoDAsync)(records, host, (size_t)count * layout->bytes_per_point, ctx->streamUpload));
+        }
+        uint64_t numPoints = count;
+        uint32_t bpp = layout->bytes_per_point;
+        double sx = layout->scale[0], sy = layout->scale[1], sz = layout->scale[2];
+        double ox = layout->offset[0] + layout->translation[0], oy = layout->offset[1] + layout->translation[1], oz = layout->offset[2] + layout->translation[2];   // LasLoader.cpp:199-201
+        void* args[] = {&records, &numPoints, &bpp, &offsetRgb, &sx, &sy, &sz, &ox, &oy, &oz, &dst};
+        unsigned blocks = (unsigned)std::min<uint64_t>((count + 255) / 256, (uint64_t)ctx->numSMs * 8);
+        CU(D(cuLaunchKernel)(ctx->fnLas, blocks, 1, 1, 256, 1, 1, 0, ctx->streamUpload, args, nullptr));
+        ctx->launches++;
+    }
+    return publishBatch(ctx, slot, count);
+}
+
+int simlod_upload_batch_las(SimlodContext* ctx, const void* host_records, uint32_t count, const SimlodLasLayout* layout) {
+    if (!host_records && count) return fail(SIMLOD_ERR_INVALID, "null records");
+    return uploadLasCommon(ctx, host_records, 0, count, layout);
+}
+int simlod_upload_batch_las_device(SimlodContext* ctx, uint64_t device_records, uint32_t count, const SimlodLasLayout* layout) {
+    if (!device_records && count) return fail(SIMLOD_ERR_INVALID, "null records");
+    return uploadLasCommon(ctx, nullptr, (CUdeviceptr)device_records, count, layout);
 }
 
 int simlod_update_octree(SimlodContext* ctx, float* kernel_ms) {
@@ -576,6 +627,13 @@ int simlod_device_rcp(SimlodContext* ctx, float x, float* out) {
     ctx->launches++;
     CU(D(cuStreamSynchronize)(ctx->streamMain));
     CU(D(cuMemcpyDtoH)(out, dst, 4));
+    return SIMLOD_OK;
+}
+
+int simlod_synchronize(SimlodContext* ctx) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    CU(D(cuStreamSynchronize)(ctx->streamUpload));
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
     return SIMLOD_OK;
 }
 

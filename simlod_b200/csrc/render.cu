@@ -42,10 +42,9 @@ constexpr uint64_t OFF_FB        = 31200144;                       // 15 200 000
 static_assert(OFF_ITEMS + ITEM_CAP * 8 <= OFF_FB, "render scratch overlaps the framebuffer");
 }
 
-// One work item = one chunk of <= 1000 samples, packed into a single 64-bit word so that publishing it
-// is ONE naturally atomic store (no fence between payload and flag):
+// One work item = one chunk of <= 1000 samples, packed into a single 64-bit word:
 //   [63:20] chunk address >> 4 (chunks are 16-byte aligned)   [19:10] sample count (1..1000)   [9:5] node level
-// 0 = not published yet; ITEM_EMPTY = published, nothing to draw.
+// ITEM_EMPTY = nothing to draw (list shorter than the counters say).
 typedef uint64_t WorkItem;
 constexpr WorkItem ITEM_EMPTY = ~0ull;
 __device__ __forceinline__ WorkItem packItem(const void* chunk, uint32_t count, uint32_t level) {
@@ -56,14 +55,10 @@ __device__ __forceinline__ uint32_t itemCount(WorkItem w) { return (uint32_t)(w 
 __device__ __forceinline__ uint32_t itemLevel(WorkItem w) { return (uint32_t)(w >> 5) & 31u; }
 
 struct RCtl {
-    uint32_t numItems;           // item slots reserved so far (a node reserves all its chunks at once)
+    uint32_t numItems;
     uint32_t head[3];            // queue heads: single pass / HQS depth pass / HQS colour pass
     uint32_t numVisibleNodes, numVisiblePoints, numVisibleVoxels, numVisibleInner, numVisibleLeaves;
     uint32_t overflow;
-    uint32_t walkHead;           // next entry of the visible-node list to be walked
-    uint32_t nodesReserved;      // visible nodes whose items have been reserved
-    uint32_t prevNumItems;       // survives in the render buffer: how many items the previous frame published
-    uint32_t magic;              // marks prevNumItems as ours (the reference kernel, if swapped in, overwrites this area)
 };
 
 __constant__ uint32_t SPECTRAL[8] = {0x4f3ed5, 0x436df4, 0x61aefd, 0x8be0fe, 0x98f5e6, 0xa4ddab, 0xa5c266, 0xbd8832};
@@ -183,83 +178,43 @@ __device__ void lodCut(RCtl* ctl, uint32_t* visList, Node* nodes, uint32_t numNo
     }
 }
 
-// ---- chunk items: produced while they are consumed -------------------------------------------------
+// ---- chunk items ----------------------------------------------------------------------------------
 // Chunk lists are singly linked, so the k-th chunk of a node is k dependent loads away (the reference
-// makes every thread of a block walk the list, render.cu:116-121). Walking all lists first and drawing
-// afterwards leaves the GPU idle for ~50 hops x DRAM latency. Instead a warp that takes a visible node
-// reserves item slots for all its chunks at once and publishes each item (one 64-bit store) as soon as
-// the walk reaches it; warps without a node to walk are already drawing the published items. The item
-// array is zeroed at frame start.
-__device__ void walkNode(RCtl* ctl, WorkItem* items, const Node* node) {
-    // lane 0 walks the point chunks, lane 1 the voxel chunks: the two pointer chains overlap
-    const uint32_t lane = laneId();
-    uint32_t numPoints = node->numPoints, numVoxels = node->numVoxels;
-    uint32_t nP = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-    uint32_t nV = (numVoxels + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-    uint32_t base = 0;
-    if (lane == 0) {
-        base = atomicAdd(&ctl->numItems, nP + nV);
-        __threadfence();
-        atomicAdd(&ctl->nodesReserved, 1u);
-    }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if ((uint64_t)base + nP + nV > rbuf::ITEM_CAP) {
-        // over capacity: the node is dropped, but slots it reserved inside the queue must still be published (as empty)
-        if (lane == 0) atomicOr(&ctl->overflow, 1u);
-        for (uint64_t k = (uint64_t)base + lane; k < rbuf::ITEM_CAP; k += 32) *reinterpret_cast<volatile WorkItem*>(&items[k]) = ITEM_EMPTY;
-        return;
-    }
-    if (lane < 2) {
-        const uint32_t level = node->level;
-        const Chunk* chunk = lane == 0 ? node->points : node->voxelChunks;
-        uint32_t n = lane == 0 ? nP : nV, left = lane == 0 ? numPoints : numVoxels;
-        volatile WorkItem* out = items + base + (lane == 0 ? 0 : nP);
-        for (uint32_t k = 0; k < n; k++) {
-            uint32_t cnt = left < SIMLOD_POINTS_PER_CHUNK ? left : SIMLOD_POINTS_PER_CHUNK;
-            out[k] = chunk ? packItem(chunk, cnt, level) : ITEM_EMPTY;
-            left -= cnt;
-            if (chunk) chunk = chunk->next;
-        }
-    }
-    __syncwarp();
-}
-
-// every warp: first walk visible nodes while any remain, then draw items until all are consumed
-template <typename F>
-__device__ __forceinline__ void walkAndDraw(RCtl* ctl, WorkItem* items, const uint32_t* visList, const Node* nodes, uint32_t numVisible, F&& f) {
-    const uint32_t lane = laneId();
-    for (;;) {
-        uint32_t v = 0;
-        if (lane == 0) v = atomicAdd(&ctl->walkHead, 1u);
-        v = __shfl_sync(0xffffffffu, v, 0);
-        if (v >= numVisible) break;
-        walkNode(ctl, items, &nodes[visList[v]]);
-    }
-    uint32_t knownTail = 0;          // lane 0: a lower bound of the final number of items
-    for (;;) {
-        WorkItem w = 0;
-        if (lane == 0) {
-            uint32_t it = atomicAdd(&ctl->head[0], 1u);
-            bool exists = it < knownTail;
-            while (!exists) {
-                uint32_t reserved = ldv(&ctl->nodesReserved);                  // read BEFORE the tail: reserved == all => tail final
-                knownTail = min(ldv(&ctl->numItems), (uint32_t)rbuf::ITEM_CAP);
-                if (it < knownTail) exists = true;
-                else if (reserved >= numVisible) break;
-                else __nanosleep(256);                                          // back off: walkers need the memory system
+// makes every thread of a block walk the list, render.cu:116-121). Here one thread per drawn node
+// walks its two lists once — all nodes concurrently, both chains of a node interleaved — and emits one
+// packed item per chunk; the draw pass then runs at chunk granularity over the whole grid.
+// (Measured alternative, kept out: publishing items while other warps already draw them saves the
+// walk on frames with > 10 M samples but costs 20 % on small frames; see profiles/r01/render_notes.md.)
+__device__ void emitItems(RCtl* ctl, WorkItem* items, const uint32_t* visList, const Node* nodes, uint32_t numVisible) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < numVisible; v += stride) {
+        const Node* node = &nodes[visList[v]];
+        uint32_t numPoints = node->numPoints, numVoxels = node->numVoxels;
+        uint32_t nP = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        uint32_t nV = (numVoxels + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        if (nP + nV == 0) continue;
+        uint32_t base = atomicAdd(&ctl->numItems, nP + nV);
+        if ((uint64_t)base + nP + nV > rbuf::ITEM_CAP) { atomicOr(&ctl->overflow, 1u); continue; }
+        uint32_t level = node->level;
+        const Chunk* cp = node->points;
+        const Chunk* cv = node->voxelChunks;
+        uint32_t leftP = numPoints, leftV = numVoxels;
+        for (uint32_t k = 0; k < max(nP, nV); k++) {
+            if (k < nP) {
+                uint32_t cnt = leftP < SIMLOD_POINTS_PER_CHUNK ? leftP : SIMLOD_POINTS_PER_CHUNK;
+                items[base + k] = cp ? packItem(cp, cnt, level) : ITEM_EMPTY;
+                leftP -= cnt; if (cp) cp = cp->next;
             }
-            if (exists) { while ((w = *reinterpret_cast<volatile WorkItem*>(&items[it])) == 0) __nanosleep(128); }
+            if (k < nV) {
+                uint32_t cnt = leftV < SIMLOD_POINTS_PER_CHUNK ? leftV : SIMLOD_POINTS_PER_CHUNK;
+                items[base + nP + k] = cv ? packItem(cv, cnt, level) : ITEM_EMPTY;
+                leftV -= cnt; if (cv) cv = cv->next;
+            }
         }
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w == 0) break;                                   // no item `it` will ever exist
-        if (w == ITEM_EMPTY) continue;
-        const uint4* pts = itemChunk(w);
-        const uint32_t count = itemCount(w), level = itemLevel(w);
-        for (uint32_t i = lane; i < count; i += 32) f(pts[i], level);
     }
 }
 
-// later passes over the same frame's items (all published by then)
+// one pass over the frame's items: persistent warps pop chunk items with a single atomicAdd each
 template <typename F>
 __device__ __forceinline__ void forEachSample(const WorkItem* items, uint32_t numItems, uint32_t* head, F&& f) {
     const uint32_t lane = laneId();
@@ -329,19 +284,11 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     uint32_t* fb_color = fb_depth + (((uint64_t)numPixels * 4 + 15) & ~15ull) / 4;
     const bool hqs = uniforms.useHighQualityShading != 0;
 
-    // un-publish last frame's items: only as many as the previous frame of THIS kernel reserved, unless the
-    // bookkeeping looks foreign (another kernel used the buffer), then everything
-    {
-        uint32_t prev = ldv(&ctl->prevNumItems);
-        if (ldv(&ctl->magic) != 0x51d10dc5u || prev > rbuf::ITEM_CAP) prev = (uint32_t)rbuf::ITEM_CAP;
-        for (uint32_t i = gtid; i < (prev + 1) / 2; i += gstride) reinterpret_cast<ulonglong2*>(items)[i] = make_ulonglong2(0, 0);
-    }
     if (first) {
         *frameStartTimestamp = globaltimer();
         ctl->numItems = 0; ctl->head[0] = 0; ctl->head[1] = 0; ctl->head[2] = 0;
         ctl->numVisibleNodes = 0; ctl->numVisiblePoints = 0; ctl->numVisibleVoxels = 0;
         ctl->numVisibleInner = 0; ctl->numVisibleLeaves = 0; ctl->overflow = 0;
-        ctl->walkHead = 0; ctl->nodesReserved = 0;
     }
     // clear: depth = +inf (0x7f800000), colour = 0x00332211 (render.cu:1126-1131)
     {
@@ -368,13 +315,16 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     lodCut(ctl, visList, nodes, numNodes);
     grid.sync();
 
-    const uint32_t numVisible = min(ldv(&ctl->numVisibleNodes), (uint32_t)rbuf::VIS_CAP);
+    emitItems(ctl, items, visList, nodes, min(ldv(&ctl->numVisibleNodes), (uint32_t)rbuf::VIS_CAP));
+    grid.sync();
+
+    const uint32_t numItems = min(ldv(&ctl->numItems), (uint32_t)rbuf::ITEM_CAP);
     const Row* T = uniforms.transform.rows;
     const int pointSize = uniforms.pointSize;
 
     if (uniforms.showPoints && !hqs) {
         // single pass: depth|colour packed in 64 bits, atomicMin (render.cu:61-104,161-210)
-        walkAndDraw(ctl, items, visList, nodes, numVisible, [&](uint4 p, uint32_t level) {
+        forEachSample(items, numItems, &ctl->head[0], [&](uint4 p, uint32_t level) {
             Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
             if (!pr.inside) return;
             uint64_t encoded = ((uint64_t)__float_as_uint(pr.depth) << 32) | sampleColor(uniforms, p.w, level);
@@ -388,7 +338,7 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
         });
     } else if (uniforms.showPoints && hqs) {
         // pass 1: closest depth per pixel (render.cu:247-391)
-        walkAndDraw(ctl, items, visList, nodes, numVisible, [&](uint4 p, uint32_t level) {
+        forEachSample(items, numItems, &ctl->head[1], [&](uint4 p, uint32_t level) {
             Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
             if (!pr.inside || !(pr.depth > 0.0f)) return;
             uint32_t udepth = __float_as_uint(pr.depth);
@@ -402,7 +352,6 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
         });
         grid.sync();
         // pass 2: accumulate colours of samples within 1 % of the closest depth (render.cu:406-602)
-        const uint32_t numItems = min(ldv(&ctl->numItems), (uint32_t)rbuf::ITEM_CAP);
         forEachSample(items, numItems, &ctl->head[2], [&](uint4 p, uint32_t level) {
             Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
             if (!pr.inside || !(pr.depth > 0.0f)) return;
@@ -442,8 +391,6 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
         stats->numVisiblePoints = ldv(&ctl->numVisiblePoints);
         stats->numVisibleVoxels = ldv(&ctl->numVisibleVoxels);
         stats->frameID = (uint32_t)uniforms.frameCounter;
-        ctl->prevNumItems = min(ldv(&ctl->numItems), (uint32_t)rbuf::ITEM_CAP);
-        ctl->magic = 0x51d10dc5u;
     }
 
     // eye-dome lighting over 16x16 tiles (render.cu:1255-1325). Always on; covers

@@ -147,3 +147,52 @@ def shell(n_total, first=0, count=None, seed=1234, tiles_lat=64, tiles_lon=128):
 def batches(points, batch_size=1_000_000):
     for s in range(0, points.shape[0], batch_size):
         yield points[s:s + batch_size]
+
+
+# ---- LAS files (for the LAS front-end row) ------------------------------------------------------------
+LAS_RECORD_BYTES = {0: 20, 1: 28, 2: 26, 3: 34}
+LAS_RGB_OFFSET = {2: 20, 3: 28}
+
+
+def las_records(points, fmt=2, scale=(0.001, 0.001, 0.001), offset=(0.0, 0.0, 0.0), wide_colors=True):
+    """Raw LAS point records (uint8, n x bytesPerPoint) for 16-byte points: int32 XYZ = round((p - offset) / scale),
+    intensity/flags zero, RGB as 16-bit channels (x 257 when wide_colors, as most LAS writers do)."""
+    n = points.shape[0]
+    bpp = LAS_RECORD_BYTES[fmt]
+    rec = np.zeros((n, bpp), dtype=np.uint8)
+    for k, ax in enumerate("xyz"):
+        q = np.rint((points[ax].astype(np.float64) - offset[k]) / scale[k]).astype("<i4")
+        rec[:, 4 * k:4 * k + 4] = q.view(np.uint8).reshape(n, 4)
+    rec[:, 12:14] = (np.arange(n, dtype=np.uint32) & 0xFFFF).astype("<u2").view(np.uint8).reshape(n, 2)     # intensity: anything
+    if fmt in LAS_RGB_OFFSET:
+        o = LAS_RGB_OFFSET[fmt]
+        c = points["color"]
+        for k in range(3):
+            ch = ((c >> np.uint32(8 * k)) & np.uint32(0xFF)).astype(np.uint32)
+            ch16 = (ch * 257 if wide_colors else ch).astype("<u2")
+            rec[:, o + 2 * k:o + 2 * k + 2] = ch16.view(np.uint8).reshape(n, 2)
+    return rec
+
+
+def write_las(path, points, fmt=2, scale=(0.001, 0.001, 0.001), offset=(0.0, 0.0, 0.0), wide_colors=True):
+    """Minimal LAS 1.2 file with the header fields the reference reads (LasLoader.h:21-55)."""
+    import struct
+    rec = las_records(points, fmt, scale, offset, wide_colors)
+    n, bpp = rec.shape
+    hdr = bytearray(227)
+    hdr[0:4] = b"LASF"
+    hdr[24], hdr[25] = 1, 2
+    struct.pack_into("<H", hdr, 94, 227)
+    struct.pack_into("<I", hdr, 96, 227)
+    hdr[104] = fmt
+    struct.pack_into("<H", hdr, 105, bpp)
+    struct.pack_into("<I", hdr, 107, n)
+    struct.pack_into("<3d", hdr, 131, *scale)
+    struct.pack_into("<3d", hdr, 155, *offset)
+    mx = [float(points[a].max()) for a in "xyz"] if n else [0.0] * 3
+    mn = [float(points[a].min()) for a in "xyz"] if n else [0.0] * 3
+    struct.pack_into("<6d", hdr, 179, mx[0], mn[0], mx[1], mn[1], mx[2], mn[2])
+    with open(path, "wb") as f:
+        f.write(bytes(hdr))
+        f.write(rec.tobytes())
+    return rec
