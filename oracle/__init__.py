@@ -186,6 +186,9 @@ def ref_las():
         L = C.CDLL(REF_LAS_LIB)
         L.ref_las_load.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.ref_las_header.argtypes = [C.c_char_p] + [C.c_void_p] * 8
+        L.ref_las_bench.restype = C.c_double
+        L.ref_las_bench.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
+        L.ref_las_load_parallel.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
         _ref_las = L
     return _ref_las
 
@@ -196,3 +199,17 @@ def ref_las_load(path, first, count, translation=(0.0, 0.0, 0.0)):
     tr = np.asarray(translation, dtype=np.float64)
     ref_las().ref_las_load(path.encode(), first, count, out.ctypes.data, tr.ctypes.data)
     return out
+
+
+def ref_las_load_parallel(path, first, count, batch_points, threads, out=None, translation=(0.0, 0.0, 0.0)):
+    """The reference loader on `threads` host threads, one loadLasNative call per batch (as spawnLoader does)."""
+    out = np.zeros(count, dtype=POINT_DTYPE) if out is None else out
+    tr = np.asarray(translation, dtype=np.float64)
+    ref_las().ref_las_load_parallel(path.encode(), first, count, batch_points, out.ctypes.data, tr.ctypes.data, int(threads))
+    return out
+
+
+def ref_las_bench(path, count, batch_points, threads):
+    """Seconds the reference loader needs for `count` points with `threads` long-lived loader threads."""
+    out = np.zeros(count, dtype=POINT_DTYPE)
+    return ref_las().ref_las_bench(path.encode(), count, batch_points, out.ctypes.data, int(threads))

@@ -96,7 +96,7 @@ def build_oracle(force=False):
         if force or not _newer(las, [shim]):
             po = os.path.join(ref_root, "modules", "progressive_octree")
             _run(["g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-w", "-I" + po, "-I" + os.path.join(ref_root, "include"),
-                  "-I" + os.path.join(ref_root, "libs", "fmt", "include"), os.path.join(po, "LasLoader.cpp"), shim, "-o", las])
+                  "-I" + os.path.join(ref_root, "libs", "fmt", "include"), os.path.join(po, "LasLoader.cpp"), shim, "-o", las, "-pthread"])
         outs = [os.path.join(refdir, n) for n in ("ref_construct.cubin", "ref_render.cubin", "ref_reset.cubin")]
         if force or not all(os.path.exists(o) for o in outs):
             _run([tool, ref_root, refdir, "100"], cwd=odir)
