@@ -45,7 +45,7 @@ int fail(int code, const char* fmt, ...) {
 // and its exports inspected on a machine without a GPU driver; every entry point that touches
 // the device fails with SIMLOD_ERR_CUDA there. There is no other code path.
 // ------------------------------------------------------------------------------------------
-#define DRV_LIST(X) X(cuArray3DCreate) X(cuArrayDestroy) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuDeviceGet) X(cuDeviceGetAttribute) X(cuDevicePrimaryCtxRelease) X(cuDevicePrimaryCtxRetain) X(cuEventCreate) X(cuEventDestroy) X(cuEventElapsedTime) X(cuEventRecord) X(cuEventSynchronize) X(cuGetErrorString) X(cuInit) X(cuLaunchCooperativeKernel) X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree) X(cuMemFreeHost) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemcpy2D) X(cuMemcpyDtoDAsync) X(cuMemcpyDtoH) X(cuMemcpyDtoHAsync) X(cuMemcpyHtoD) X(cuMemcpyHtoDAsync) X(cuMemsetD32Async) X(cuMemsetD8) X(cuMemsetD8Async) X(cuModuleGetFunction) X(cuModuleLoadData) X(cuModuleUnload) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuSurfObjectCreate) X(cuSurfObjectDestroy)
+#define DRV_LIST(X) X(cuArray3DCreate) X(cuArrayDestroy) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuDeviceGet) X(cuDeviceGetAttribute) X(cuDevicePrimaryCtxRelease) X(cuDevicePrimaryCtxRetain) X(cuEventCreate) X(cuEventDestroy) X(cuEventElapsedTime) X(cuEventRecord) X(cuEventSynchronize) X(cuGetErrorString) X(cuInit) X(cuLaunchCooperativeKernel) X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree) X(cuMemFreeHost) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemcpy2D) X(cuMemcpyDtoDAsync) X(cuMemcpyDtoH) X(cuMemcpyDtoHAsync) X(cuMemcpyHtoD) X(cuMemcpyHtoDAsync) X(cuMemsetD32Async) X(cuMemsetD8) X(cuMemsetD8Async) X(cuModuleGetFunction) X(cuModuleLoadData) X(cuModuleUnload) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuSurfObjectCreate) X(cuSurfObjectDestroy)
 #define DRV_STR2(x) #x
 #define DRV_STR(x) DRV_STR2(x)
 struct DriverApi {
@@ -99,6 +99,7 @@ struct SimlodContext {
     CUstream streamMain = nullptr, streamUpload = nullptr;
     CUevent evStart = nullptr, evEnd = nullptr, evTotalStart = nullptr, evTotalEnd = nullptr;
     CUevent evBurst[8][2] = {};        // event pairs for launches enqueued back to back
+    CUevent evSlot[RING_SLOTS] = {};    // recorded on the upload stream when the batch in that ring slot has been published
     SimlodConfig cfg{};
     SimlodUniforms uniforms{};
     SimlodBuffers buf{};
@@ -194,6 +195,7 @@ int publishBatch(SimlodContext* ctx, uint32_t slot, uint32_t count) {
     CU(D(cuMemsetD32Async)(ctx->batchSizes + 4ull * slot, count, 1, ctx->streamUpload));
     ctx->uploaded++;
     CU(D(cuMemsetD32Async)(ctx->numBatchesUploaded, ctx->uploaded, 1, ctx->streamUpload));
+    CU(D(cuEventRecord)(ctx->evSlot[slot], ctx->streamUpload));
     return SIMLOD_OK;
 }
 
@@ -257,6 +259,7 @@ int simlod_create(const SimlodConfig* config, SimlodContext** out) {
     CU(D(cuEventCreate)(&ctx->evTotalStart, CU_EVENT_DEFAULT));
     CU(D(cuEventCreate)(&ctx->evTotalEnd, CU_EVENT_DEFAULT));
     for (int i = 0; i < 8; i++) for (int j = 0; j < 2; j++) CU(D(cuEventCreate)(&ctx->evBurst[i][j], CU_EVENT_DEFAULT));
+    for (uint64_t i = 0; i < RING_SLOTS; i++) CU(D(cuEventCreate)(&ctx->evSlot[i], CU_EVENT_DISABLE_TIMING));
 
     // programs (main.cpp:603-626)
     for (int p = 0; p < 3; p++) {
@@ -344,6 +347,7 @@ void simlod_destroy(SimlodContext* ctx) {
         if (ctx->evTotalStart) D(cuEventDestroy)(ctx->evTotalStart);
         if (ctx->evTotalEnd) D(cuEventDestroy)(ctx->evTotalEnd);
         for (int i = 0; i < 8; i++) for (int j = 0; j < 2; j++) if (ctx->evBurst[i][j]) D(cuEventDestroy)(ctx->evBurst[i][j]);
+        for (uint64_t i = 0; i < RING_SLOTS; i++) if (ctx->evSlot[i]) D(cuEventDestroy)(ctx->evSlot[i]);
         if (ctx->streamMain) D(cuStreamDestroy)(ctx->streamMain);
         if (ctx->streamUpload) D(cuStreamDestroy)(ctx->streamUpload);
         D(cuDevicePrimaryCtxRelease)(ctx->device);
@@ -499,7 +503,15 @@ static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr
         // 20 batches or 10 ms — and Stats is read once per burst.
         const uint32_t pendingBatches = ctx->uploaded - ctx->processed;
         int burst = (int)std::min<uint32_t>(8u, std::max<uint32_t>(1u, (pendingBatches + 19u) / 20u));
-        for (int k = 0; k < burst; k++) { rc = enqueueConstruct(ctx, k); if (rc) return rc; }
+        for (int k = 0; k < burst; k++) {
+            // launch k is meant to consume batches [processed + 20k, processed + 20(k+1)): let it start once the last
+            // of those that has been enqueued for upload is published, instead of snapshotting a half-filled ring
+            if (pendingBatches > 0) {
+                uint32_t lastWanted = std::min<uint32_t>(ctx->uploaded, ctx->processed + 20u * (uint32_t)(k + 1)) - 1u;
+                CU(D(cuStreamWaitEvent)(ctx->streamMain, ctx->evSlot[lastWanted % RING_SLOTS], 0));
+            }
+            rc = enqueueConstruct(ctx, k); if (rc) return rc;
+        }
         rc = readStats(ctx); if (rc) return rc;
         for (int k = 0; k < burst; k++) {
             float ms = 0.0f;
