@@ -441,8 +441,8 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
 
 // ------------------------------------------------------------------------------------------
 // TMA staging of the batch. In a first-visit pass every block streams its contiguous run of the
-// batch through two 16 KB shared-memory stages with 1-D bulk copies (cp.async.bulk ... mbarrier::
-// complete_tx, SASS: UBLKCP): one elected thread issues the copy of the next 1024-point tile while
+// batch through two 8 KB shared-memory stages with 1-D bulk copies (cp.async.bulk ... mbarrier::
+// complete_tx, SASS: UBLKCP): one elected thread issues the copy of the next 512-point tile while
 // the block walks the current one, so the HBM latency of the batch read leaves the critical path
 // and no registers or LSU slots are spent on it. Threads then read their point with one LDS.128.
 // ------------------------------------------------------------------------------------------
@@ -451,7 +451,7 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
 #else
 #define SIMLOD_TMA 0
 #endif
-constexpr uint32_t TILE_POINTS = 1024;
+constexpr uint32_t TILE_POINTS = 512;
 #if SIMLOD_TMA
 __shared__ __align__(128) uint4 sh_tile[2][TILE_POINTS];
 __shared__ __align__(8) uint64_t sh_tileBar[2];

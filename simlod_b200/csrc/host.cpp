@@ -502,12 +502,15 @@ static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr
         // Without a frame to draw in between, launches are enqueued back to back — each consumes at most
         // 20 batches or 10 ms — and Stats is read once per burst.
         const uint32_t pendingBatches = ctx->uploaded - ctx->processed;
-        int burst = (int)std::min<uint32_t>(8u, std::max<uint32_t>(1u, (pendingBatches + 19u) / 20u));
+        // A launch starts once the batches it is meant to consume are published (stream wait on the slot's event)
+        // instead of snapshotting a half-filled ring. Device-resident sources arrive far faster than they are
+        // consumed: gate on full 20-batch launches. Host sources arrive at PCIe speed, slower than the builder:
+        // gate on 2 batches so that insertion trails the upload closely.
+        const uint32_t gate = host ? 2u : 20u;
+        int burst = (int)std::min<uint32_t>(8u, std::max<uint32_t>(1u, (pendingBatches + gate - 1u) / gate));
         for (int k = 0; k < burst; k++) {
-            // launch k is meant to consume batches [processed + 20k, processed + 20(k+1)): let it start once the last
-            // of those that has been enqueued for upload is published, instead of snapshotting a half-filled ring
             if (pendingBatches > 0) {
-                uint32_t lastWanted = std::min<uint32_t>(ctx->uploaded, ctx->processed + 20u * (uint32_t)(k + 1)) - 1u;
+                uint32_t lastWanted = std::min<uint32_t>(ctx->uploaded, ctx->processed + gate * (uint32_t)(k + 1)) - 1u;
                 CU(D(cuStreamWaitEvent)(ctx->streamMain, ctx->evSlot[lastWanted % RING_SLOTS], 0));
             }
             rc = enqueueConstruct(ctx, k); if (rc) return rc;

@@ -258,3 +258,57 @@ def test_render_is_idempotent_and_does_not_modify_the_octree(sim):
     assert (a == b).all()
     cn2 = oracle.canon_from_image(*sim.download_octree())
     assert not oracle.compare_canon(cn, cn2)
+
+
+# ---- BASELINE.json full size (configs[1]: 36 M points streamed in 1 M-point batches): size-independent properties ----
+
+def test_full_size_36m_stream_invariants(sim):
+    import bench
+    K = 36
+    batches, mn, mx = bench.generate_batches(K, list(range(K)))
+    sim.set_box(mn, mx)
+    sim.reset()
+    # two ragged batches in the middle of the stream, the rest full
+    stream = batches[:10] + [batches[10][:123_457], batches[10][123_457:]] + batches[11:]
+    n = sum(len(b) for b in stream)
+    for b in stream:
+        sim.upload_batch(b)
+    while sim.stats().batchletIndex < len(stream):
+        sim.update_octree()
+    st = sim.stats()
+    assert st.dbg == 0 and st.memCapacityReached == 0
+    assert st.numPointsProcessed == n == K * 1_000_000 and st.numPoints == n and st.batchletIndex == len(stream)
+    nodes = sim.memcpy_dtoh(sim.buffers().nodes, st.numNodes * 152)
+    rec = np.frombuffer(nodes.tobytes(), dtype=np.dtype({
+        "names": ["child0", "counter", "numPoints", "level", "X", "Y", "Z", "grid", "points", "voxelChunks", "numVoxels", "numVoxelsStored"],
+        "formats": ["<u8", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u8", "<u8", "<u8", "<u4", "<u4"],
+        "offsets": [0, 64, 68, 72, 76, 80, 84, 120, 128, 136, 144, 148], "itemsize": 152}))
+    leaf = rec["child0"] == 0
+    inner = ~leaf
+    assert st.numNodes == len(rec) == 1 + 8 * int(inner.sum()) and st.numInner == int(inner.sum()) and st.numLeaves == int(leaf.sum())
+    assert int(rec["numPoints"][leaf].sum()) == n and (rec["numPoints"][inner] == 0).all() and (rec["points"][inner] == 0).all()
+    assert (rec["numPoints"][leaf] <= 50_000).all() and (rec["counter"][leaf] == rec["numPoints"][leaf]).all()
+    assert (rec["counter"][inner] > 50_000).all()                      # an inner node is a leaf that crossed the capacity once
+    assert (rec["grid"][inner] != 0).all() and (rec["grid"][leaf & (rec["level"] > 0)] == 0).all()
+    assert (rec["numVoxels"] == rec["numVoxelsStored"]).all() and (rec["numVoxels"][leaf & (rec["level"] > 0)] == 0).all()
+    assert (rec["numVoxels"][inner & (rec["level"] > 0)] <= 128 ** 3).all()
+    # keys are unique and every non-root node's parent exists and is inner
+    keys = (rec["level"].astype(np.uint64) << np.uint64(60)) | (rec["X"].astype(np.uint64) << np.uint64(40)) | (rec["Y"].astype(np.uint64) << np.uint64(20)) | rec["Z"].astype(np.uint64)
+    assert len(np.unique(keys)) == len(keys)
+    nz = rec["level"] > 0
+    pkeys = ((rec["level"][nz] - 1).astype(np.uint64) << np.uint64(60)) | ((rec["X"][nz] >> 1).astype(np.uint64) << np.uint64(40)) | ((rec["Y"][nz] >> 1).astype(np.uint64) << np.uint64(20)) | (rec["Z"][nz] >> 1).astype(np.uint64)
+    assert np.isin(pkeys, keys[inner]).all()
+    # chunk / heap accounting identities
+    chunks_points = int(((rec["numPoints"][leaf] + 999) // 1000).sum())
+    chunks_voxels = int(((rec["numVoxels"] + 999) // 1000).sum())
+    assert st.numAllocatedChunks == chunks_points == st.numChunksPoints and st.chunkPoolSize >= st.numAllocatedChunks
+    assert st.allocatedBytes_persistent == 16 + 262160 * int(inner.sum()) + 16032 * (st.chunkPoolSize + chunks_voxels)
+    assert st.numVoxels == int(rec["numVoxels"][inner].sum())
+    # rendering the full-size octree twice gives the same framebuffer, and a sane one
+    view, proj = camera.orbit_camera(width=sim.width, height=sim.height, **camera.MORRO_BIRD)
+    sim.set_camera(view, proj)
+    sim.render(); a = sim.framebuffer(); s1 = sim.stats()
+    sim.render(); b = sim.framebuffer()
+    assert (a == b).all() and s1.numVisibleNodes > 0
+    drawn = (a >> np.uint64(32)) != np.uint64(0x7f800000)
+    assert 0.05 < drawn.mean() <= 1.0
