@@ -107,7 +107,7 @@ struct Ctl {
     uint32_t rowBump;              // leaf rows handed out so far (persistent across launches)
     uint32_t rowFreeCount;         // entries on the row free stack (persistent)
     uint32_t statCounters[8];      // @32
-    uint64_t _reserved[2];         // @64
+    uint64_t voxelsByPass[2];      // @64 voxels created in first-visit passes / in re-walk passes since the last reset
     uint64_t spilledTotal;         // @80 spilled (re-inserted) points since the last reset: the `s` of the roofline's 32*s bytes
     uint64_t voxelsTotal;          // @88 voxels created since the last reset (incl. leaf-root voxels)
     BatchCounters batch[2];        // @96
@@ -263,7 +263,7 @@ __device__ __forceinline__ void recordVoxel(const Ctx& c, uint32_t node, uint32_
     c.vcolor[at] = color;
 }
 
-__device__ __forceinline__ void voxelPassEnd(const Ctx& c) {
+__device__ __forceinline__ void voxelPassEnd(const Ctx& c, bool freshPass) {
     __syncthreads();
     if (threadIdx.x < VOXTAB_SIZE) {
         uint32_t node = sh_tabKey[threadIdx.x], cnt = sh_tabCount[threadIdx.x];
@@ -287,7 +287,10 @@ __device__ __forceinline__ void voxelPassEnd(const Ctx& c) {
     }
     if (threadIdx.x == 0) {
         c.blockCursor[blockIdx.x] = endIdx;
-        if (endIdx > sh_passStart) atomicAdd(reinterpret_cast<unsigned long long*>(&c.ctl->voxelsTotal), (unsigned long long)(endIdx - sh_passStart));
+        if (endIdx > sh_passStart) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(&c.ctl->voxelsTotal), (unsigned long long)(endIdx - sh_passStart));
+            atomicAdd(reinterpret_cast<unsigned long long*>(&c.ctl->voxelsByPass[freshPass ? 0 : 1]), (unsigned long long)(endIdx - sh_passStart));
+        }
     }
     __syncthreads();
 }
@@ -556,7 +559,7 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
         walk<SAMPLE, COUNT>(c, valid, pt, node, level, lp, slot);
         if (valid && COUNT) { c.leafOf[scratch::MAX_BATCH + j] = lp; c.slotOf[scratch::MAX_BATCH + j] = slot; }
     }
-    if (SAMPLE) voxelPassEnd(c);
+    if (SAMPLE) voxelPassEnd(c, FRESH);
     if (COUNT) {
         // flush the block's leaf table: one global add per distinct leaf, then provisional ranks -> slots
         __syncthreads();
@@ -948,7 +951,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         clearBatchCounters(&c.ctl->batch[1]);
         for (int i = 0; i < 8; i++) c.ctl->statCounters[i] = 0;
         if (stats->batchletIndex == 0) {       // fresh after the reset kernel: the tree is the root alone
-            c.ctl->spilledTotal = 0; c.ctl->voxelsTotal = 0;
+            c.ctl->spilledTotal = 0; c.ctl->voxelsTotal = 0; c.ctl->voxelsByPass[0] = 0; c.ctl->voxelsByPass[1] = 0;
             for (int i = 0; i < 8; i++) c.ctl->phaseNanos[i] = 0;
             c.ctl->rowBump = 0; c.ctl->rowFreeCount = 0;
             c.firstChild[0] = 0;

@@ -312,3 +312,31 @@ def test_full_size_36m_stream_invariants(sim):
     assert (a == b).all() and s1.numVisibleNodes > 0
     drawn = (a >> np.uint64(32)) != np.uint64(0x7f800000)
     assert 0.05 < drawn.mean() <= 1.0
+
+
+def test_reference_launch_shape_one_block_per_sm():
+    """The unmodified reference host launches kernel_construct with numSMs blocks (main.cpp:370-371): the drop-in
+    must produce the same octree at that shape (and at any other cooperative grid)."""
+    pts, mn, mx = data.terrain(2_200_000)
+    batches = split(pts, [1_000_000, 999, 1_000_000, 199_001])
+    o = build_oracle(batches, (mn, mx), 0.0)   # rcp filled below
+    for per_sm in (1, 2):
+        s = SimLOD(640, 360, persistent_bytes=4 << 30, construct_blocks_per_sm=per_sm, render_blocks_per_sm=per_sm)
+        try:
+            assert s.launch_info()["construct_blocks"] == per_sm * s.launch_info()["num_sms"]
+            rcp = float(s.device_rcp(4800.0))
+            o = build_oracle(batches, (mn, mx), rcp)
+            s.set_box(mn, mx)
+            s.reset()
+            s.insert_batches(batches)
+            st = s.stats()
+            cn = oracle.canon_from_image(*s.download_octree())
+            assert st.dbg == 0
+            assert_same_octree(st, cn, o.stats(), o.canon(), "ours at %d block(s)/SM vs oracle" % per_sm)
+            assert o.check_voxel_colors(cn) == 0
+            view, proj = camera.autofocus(mx, 640, 360)
+            s.set_camera(view, proj)
+            s.render()
+            assert s.stats().numVisibleNodes > 0
+        finally:
+            s.close()

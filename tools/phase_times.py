@@ -18,5 +18,7 @@ for rep in range(2):
     ph = sim.memcpy_dtoh(sim.buffers().momentary + 160, 64).view(np.uint64) / 1e3
     names = ["count+sample", "split", "rewalk", "deferred", "alloc", "insert", "stats", "prologue"]
     print("kernel ms %.3f total ms %.3f Mpts/s %.1f" % (kms, tms, n / kms / 1e3))
+    vb = sim.memcpy_dtoh(sim.buffers().momentary + 64, 32).view(np.uint64)
+    print("voxels first-visit / re-walk:", int(vb[0]), int(vb[1]), "spilled", int(vb[2]), "total", int(vb[3]))
     print("phase us:", {k: round(float(v), 1) for k, v in zip(names, ph)}, "sum", round(float(ph.sum()), 1), flush=True)
 sim.close()
