@@ -198,6 +198,47 @@ def bench_las(batches, mn, mx, device):
     return out
 
 
+def bench_stream_file(batches, mn, mx, device):
+    """Second "next" row: .simlod file (tmpfs) -> loader threads -> pinned pool -> ring -> octree, with the reference's own
+    loadFileNative (SimlodLoader.cpp compiled from /root/reference) timed beside it on the host cores."""
+    import tempfile
+    import oracle
+    from simlod_b200 import SimLOD, data
+    nb = min(16, len(batches))
+    n = nb * BATCH
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(d, "simlod_bench_%d.simlod" % os.getpid())
+    out = {"points": n, "file_bytes": 24 + 16 * n}
+    try:
+        data.write_simlod(path, np.concatenate(batches[:nb]), mn, mx)
+        sim = SimLOD(320, 176, device=device, persistent_bytes=max(4 << 30, nb * (220 << 20)))
+        try:
+            best = None
+            for rep in range(3):
+                t0 = time.perf_counter()
+                got, kms, tms = sim.insert_simlod_file(path, loader_threads=8)
+                dt = time.perf_counter() - t0
+                assert got == n and sim.stats().numPoints == n
+                if best is None or dt < best[0]:
+                    best = (dt, kms, tms)
+            out["e2e"] = {"value": round(n / best[0] / 1e6, 1), "unit": "Mpoints/s", "how": "wall clock incl. reset, 8 loader threads, file in tmpfs",
+                          "device_ms": round(best[2], 3), "kernel_ms": round(best[1], 3)}
+        finally:
+            sim.close()
+        if oracle.ref_simlod() is not None:
+            best = None
+            for threads in sorted({1, min(8, os.cpu_count() or 1), os.cpu_count() or 1}):
+                dt_t = oracle.ref_simlod_bench(path, n, BATCH, threads)
+                if best is None or dt_t < best[0]:
+                    best = (dt_t, threads)
+            out["cpu_baseline"] = {"value": round(n / best[0] / 1e6, 1), "unit": "Mpoints/s", "cores": best[1], "kind": "reference",
+                                   "sample": "loadFileNative (SimlodLoader.cpp compiled from /root/reference), %d x 1M-point reads from tmpfs into host memory; best of 1 / 8 / all cores" % nb}
+    finally:
+        if os.path.exists(path):
+            os.remove(path)
+    return out
+
+
 def run_reference(args, rank, world):
     """The reference's algorithm on the host cores: oracle port (the reference has no CPU octree
     builder to compile; its kernels need a GPU). One step = one full 1 M-point batch."""
@@ -353,6 +394,13 @@ def main():
         except Exception as e:          # the row is reported, never fatal for the headline
             las = {"error": repr(e)}
 
+    stream = None
+    if rank == 0 and world == 1:
+        try:
+            stream = bench_stream_file(batches, mn, mx, local_rank)
+        except Exception as e:
+            stream = {"error": repr(e)}
+
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample -----------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -407,6 +455,8 @@ def main():
             line["render"] = render
         if las:
             line["las_decode"] = las
+        if stream:
+            line["stream_file"] = stream
         print(json.dumps(line), flush=True)
     sim.close()
     if world > 1:

@@ -86,6 +86,14 @@ int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t c
 // same with the whole point set resident in device memory (batches are copied device-to-device)
 int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms, float* total_ms);
 
+// Streaming front end for one `.simlod` file: reload() + spawnLoader + spawnUploader of
+// main.cpp:644-760, 811-958, 963-1063. The 24-byte header (6 x f32 min, max; tools/las2simlod.mjs:95-101)
+// gives the box (boxMin = 0, boxMax = max - min, main.cpp:312-313); the octree is reset; `loader_threads`
+// host threads read 1 000 000-point batches (loadFileNative, SimlodLoader.cpp:147-157) into a pool of pinned
+// slots (main.cpp:141-222) while the uploader publishes them IN FILE ORDER and update launches consume them.
+int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_threads, uint64_t* num_points,
+                              float* kernel_ms, float* total_ms);
+
 // LAS front end. The reference decodes LAS point records on CPU threads
 // (loadLasNative, LasLoader.cpp:169-226) and uploads 16-byte points; here the raw records are uploaded
 // and decoded on the device straight into the next ring slot, then published like any batch.

@@ -12,6 +12,7 @@ REF_DIR = os.path.join(_HERE, "_ref")
 REF_CUBINS = {0: os.path.join(REF_DIR, "ref_construct.cubin"), 1: os.path.join(REF_DIR, "ref_render.cubin"),
               2: os.path.join(REF_DIR, "ref_reset.cubin")}
 REF_LAS_LIB = os.path.join(REF_DIR, "libref_las.so")
+REF_SIMLOD_LIB = os.path.join(REF_DIR, "libref_simlod.so")
 REF_MOMENTARY_BYTES = 420_000_000      # the reference carves 408 800 192 B out of its 300 MB buffer
 
 POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("color", "<u4")])
@@ -213,3 +214,31 @@ def ref_las_bench(path, count, batch_points, threads):
     """Seconds the reference loader needs for `count` points with `threads` long-lived loader threads."""
     out = np.zeros(count, dtype=POINT_DTYPE)
     return ref_las().ref_las_bench(path.encode(), count, batch_points, out.ctypes.data, int(threads))
+
+
+# ---- .simlod loader (SURVEY.md §8f-1, §8d-ii) ---------------------------------------------------------
+_ref_simlod = None
+
+
+def ref_simlod():
+    """The reference's own SimlodLoader.cpp compiled into oracle/_ref/libref_simlod.so (None if not built)."""
+    global _ref_simlod
+    if _ref_simlod is None and os.path.exists(REF_SIMLOD_LIB):
+        L = C.CDLL(REF_SIMLOD_LIB)
+        L.ref_simlod_load.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.ref_simlod_bench.restype = C.c_double
+        L.ref_simlod_bench.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
+        _ref_simlod = L
+    return _ref_simlod
+
+
+def ref_simlod_load(path, first_point, count):
+    """loadFileNative of the reference: `count` points starting at point `first_point` of a .simlod file."""
+    out = np.zeros(count, dtype=POINT_DTYPE)
+    ref_simlod().ref_simlod_load(path.encode(), 24 + first_point * 16, count * 16, out.ctypes.data)
+    return out
+
+
+def ref_simlod_bench(path, count, batch_points, threads):
+    out = np.zeros(count, dtype=POINT_DTYPE)
+    return ref_simlod().ref_simlod_bench(path.encode(), count, batch_points, out.ctypes.data, int(threads))

@@ -106,7 +106,7 @@ assert C.sizeof(Uniforms) == 480 and C.sizeof(Stats) == 112
 EXPORTS = [
     "simlod_create", "simlod_destroy", "simlod_last_error", "simlod_use_module", "simlod_set_uniforms",
     "simlod_get_uniforms", "simlod_reset", "simlod_upload_batch", "simlod_upload_batch_device",
-    "simlod_upload_batch_las", "simlod_upload_batch_las_device", "simlod_update_octree", "simlod_insert", "simlod_insert_device", "simlod_render", "simlod_get_stats",
+    "simlod_upload_batch_las", "simlod_upload_batch_las_device", "simlod_insert_simlod_file", "simlod_update_octree", "simlod_insert", "simlod_insert_device", "simlod_render", "simlod_get_stats",
     "simlod_read_framebuffer", "simlod_read_surface", "simlod_get_buffers", "simlod_memcpy_dtoh",
     "simlod_memcpy_htod", "simlod_host_alloc", "simlod_host_free", "simlod_device_alloc", "simlod_device_free",
     "simlod_get_launch_info", "simlod_device_rcp", "simlod_synchronize", "simlod_flush_l2",
@@ -136,6 +136,7 @@ def load_library():
         "simlod_upload_batch_device": [vp, u64, u32],
         "simlod_upload_batch_las": [vp, vp, u32, C.POINTER(LasLayout)],
         "simlod_upload_batch_las_device": [vp, u64, u32, C.POINTER(LasLayout)],
+        "simlod_insert_simlod_file": [vp, C.c_char_p, C.c_int, C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(C.c_float)],
         "simlod_update_octree": [vp, C.POINTER(C.c_float)],
         "simlod_insert": [vp, vp, u64, C.POINTER(C.c_float), C.POINTER(C.c_float)],
         "simlod_insert_device": [vp, u64, u64, C.POINTER(C.c_float), C.POINTER(C.c_float)],
@@ -323,6 +324,14 @@ class SimLOD:
         kms, tms = C.c_float(0), C.c_float(0)
         self._check(self._lib.simlod_insert_device(self._ctx, int(device_ptr), int(count), C.byref(kms), C.byref(tms)))
         return kms.value, tms.value
+
+    def insert_simlod_file(self, path, loader_threads=4):
+        """reload() of the reference for one .simlod file: reset, stream the file through pinned slots with
+        `loader_threads` reader threads, insert. Returns (num_points, summed kernel ms, total device ms)."""
+        n, kms, tms = C.c_uint64(), C.c_float(), C.c_float()
+        self._check(self._lib.simlod_insert_simlod_file(self._ctx, path.encode(), int(loader_threads), C.byref(n), C.byref(kms), C.byref(tms)))
+        self._lib.simlod_get_uniforms(self._ctx, C.byref(self.uniforms))
+        return n.value, kms.value, tms.value
 
     def insert_batches(self, batches):
         """Insert explicit batches (each <= 1 M points), each followed by update launches until the

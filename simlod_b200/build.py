@@ -97,6 +97,13 @@ def build_oracle(force=False):
             po = os.path.join(ref_root, "modules", "progressive_octree")
             _run(["g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-w", "-I" + po, "-I" + os.path.join(ref_root, "include"),
                   "-I" + os.path.join(ref_root, "libs", "fmt", "include"), os.path.join(po, "LasLoader.cpp"), shim, "-o", las, "-pthread"])
+        # ... and its .simlod loader (SimlodLoader.cpp needs <cstdint> force-included)
+        sml = os.path.join(refdir, "libref_simlod.so")
+        shim2 = os.path.join(odir, "ref_simlod_shim.cpp")
+        if force or not _newer(sml, [shim2]):
+            po = os.path.join(ref_root, "modules", "progressive_octree")
+            _run(["g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-w", "-include", "cstdint", "-I" + po, "-I" + os.path.join(ref_root, "include"),
+                  "-I" + os.path.join(ref_root, "libs", "fmt", "include"), os.path.join(po, "SimlodLoader.cpp"), shim2, "-o", sml, "-pthread"])
         outs = [os.path.join(refdir, n) for n in ("ref_construct.cubin", "ref_render.cubin", "ref_reset.cubin")]
         if force or not all(os.path.exists(o) for o in outs):
             _run([tool, ref_root, refdir, "100"], cwd=odir)

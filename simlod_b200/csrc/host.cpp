@@ -13,6 +13,8 @@
 #include <cuda.h>
 #include <dlfcn.h>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -45,7 +47,7 @@ int fail(int code, const char* fmt, ...) {
 // and its exports inspected on a machine without a GPU driver; every entry point that touches
 // the device fails with SIMLOD_ERR_CUDA there. There is no other code path.
 // ------------------------------------------------------------------------------------------
-#define DRV_LIST(X) X(cuArray3DCreate) X(cuArrayDestroy) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuDeviceGet) X(cuDeviceGetAttribute) X(cuDevicePrimaryCtxRelease) X(cuDevicePrimaryCtxRetain) X(cuEventCreate) X(cuEventDestroy) X(cuEventElapsedTime) X(cuEventRecord) X(cuEventSynchronize) X(cuGetErrorString) X(cuInit) X(cuLaunchCooperativeKernel) X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree) X(cuMemFreeHost) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemcpy2D) X(cuMemcpyDtoDAsync) X(cuMemcpyDtoH) X(cuMemcpyDtoHAsync) X(cuMemcpyHtoD) X(cuMemcpyHtoDAsync) X(cuMemsetD32Async) X(cuMemsetD8) X(cuMemsetD8Async) X(cuModuleGetFunction) X(cuModuleLoadData) X(cuModuleUnload) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuSurfObjectCreate) X(cuSurfObjectDestroy)
+#define DRV_LIST(X) X(cuArray3DCreate) X(cuArrayDestroy) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuDeviceGet) X(cuDeviceGetAttribute) X(cuDevicePrimaryCtxRelease) X(cuDevicePrimaryCtxRetain) X(cuEventCreate) X(cuEventDestroy) X(cuEventElapsedTime) X(cuEventQuery) X(cuEventRecord) X(cuEventSynchronize) X(cuGetErrorString) X(cuInit) X(cuLaunchCooperativeKernel) X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree) X(cuMemFreeHost) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemcpy2D) X(cuMemcpyDtoDAsync) X(cuMemcpyDtoH) X(cuMemcpyDtoHAsync) X(cuMemcpyHtoD) X(cuMemcpyHtoDAsync) X(cuMemsetD32Async) X(cuMemsetD8) X(cuMemsetD8Async) X(cuModuleGetFunction) X(cuModuleLoadData) X(cuModuleUnload) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuSurfObjectCreate) X(cuSurfObjectDestroy)
 #define DRV_STR2(x) #x
 #define DRV_STR(x) DRV_STR2(x)
 struct DriverApi {
@@ -111,6 +113,8 @@ struct SimlodContext {
     CUmodule utilModule = nullptr, lasModule = nullptr;
     CUfunction fnLas = nullptr;
     CUdeviceptr lasStaging = 0;        // raw LAS records of the batch being decoded
+    void* pinnedPool = nullptr;        // POOL_SLOTS x 16 MB page-locked staging slots of the file streamer
+    CUevent evPool[8] = {};            // H2D copy out of pool slot i has been enqueued and completed
     CUfunction fnRcp = nullptr, fnFill = nullptr;
     uint32_t uploaded = 0;             // batches published to the device
     uint32_t processed = 0;            // Stats::batchletIndex as last read
@@ -342,6 +346,8 @@ void simlod_destroy(SimlodContext* ctx) {
         if (ctx->utilModule) D(cuModuleUnload)(ctx->utilModule);
         if (ctx->lasModule) D(cuModuleUnload)(ctx->lasModule);
         if (ctx->lasStaging) D(cuMemFree)(ctx->lasStaging);
+        if (ctx->pinnedPool) D(cuMemFreeHost)(ctx->pinnedPool);
+        for (int i = 0; i < 8; i++) if (ctx->evPool[i]) D(cuEventDestroy)(ctx->evPool[i]);
         if (ctx->evStart) D(cuEventDestroy)(ctx->evStart);
         if (ctx->evEnd) D(cuEventDestroy)(ctx->evEnd);
         if (ctx->evTotalStart) D(cuEventDestroy)(ctx->evTotalStart);
@@ -537,6 +543,117 @@ int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t c
 int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms, float* total_ms) {
     if (!device_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
     return insertCommon(ctx, nullptr, (CUdeviceptr)device_points, count, kernel_ms, total_ms);
+}
+
+// ---- streaming front end -------------------------------------------------------------
+int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_threads, uint64_t* num_points,
+                              float* kernel_ms, float* total_ms) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!path) return fail(SIMLOD_ERR_INVALID, "null path");
+    constexpr int POOL_SLOTS = 8;
+    const uint64_t slotBytes = SLOT_POINTS * sizeof(SimlodPoint);
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(SIMLOD_ERR_INVALID, "cannot open %s", path);
+    float hdr[6];
+    size_t got = fread(hdr, 1, sizeof(hdr), f);
+    fseek(f, 0, SEEK_END);
+    const uint64_t fileSize = (uint64_t)ftell(f);
+    fclose(f);
+    if (got != sizeof(hdr) || fileSize < 24) return fail(SIMLOD_ERR_INVALID, "%s is not a .simlod file", path);
+    const uint64_t numPoints = (fileSize - 24) / 16;                       // main.cpp:738
+    const uint64_t numBatches = (numPoints + SLOT_POINTS - 1) / SLOT_POINTS;
+    if (num_points) *num_points = numPoints;
+    for (int i = 0; i < 3; i++) { ctx->uniforms.boxMin[i] = 0.0f; ctx->uniforms.boxMax[i] = hdr[3 + i] - hdr[i]; }   // main.cpp:312-313
+    rc = simlod_reset(ctx); if (rc) return rc;                            // reload() -> reset
+    if (!ctx->pinnedPool) {
+        CU(D(cuMemHostAlloc)(&ctx->pinnedPool, (size_t)POOL_SLOTS * slotBytes, CU_MEMHOSTALLOC_PORTABLE));
+        for (int i = 0; i < POOL_SLOTS; i++) CU(D(cuEventCreate)(&ctx->evPool[i], CU_EVENT_DISABLE_TIMING));
+    }
+    // loaders: batch k goes to pool slot k % POOL_SLOTS once the copy of batch k - POOL_SLOTS has left it
+    std::vector<std::atomic<int>> loaded(numBatches);
+    for (auto& l : loaded) l.store(0);
+    std::atomic<int64_t> copiesDone{0};           // batches whose host->device copy has completed
+    std::atomic<uint64_t> nextBatch{0};
+    std::atomic<bool> abort{false};
+    const int nThreads = std::max(1, std::min(loader_threads, 64));
+    std::vector<std::thread> loaders;
+    const std::string file(path);
+    for (int t = 0; t < nThreads; t++) {
+        loaders.emplace_back([&, t]() {
+            FILE* fh = fopen(file.c_str(), "rb");
+            if (!fh) { abort.store(true); return; }
+            for (;;) {
+                uint64_t k = nextBatch.fetch_add(1);
+                if (k >= numBatches || abort.load()) break;
+                while (copiesDone.load() + POOL_SLOTS <= (int64_t)k && !abort.load()) std::this_thread::yield();
+                uint64_t first = k * SLOT_POINTS, n = std::min<uint64_t>(SLOT_POINTS, numPoints - first);
+                char* dst = (char*)ctx->pinnedPool + (k % POOL_SLOTS) * slotBytes;
+                fseeko(fh, (off_t)(24 + first * 16), SEEK_SET);
+                if (fread(dst, 16, n, fh) != n) abort.store(true);
+                loaded[k].store(1);
+            }
+            fclose(fh);
+        });
+    }
+    auto joinAll = [&]() { abort.store(true); for (auto& th : loaders) th.join(); };
+
+    float kernelTotal = 0.0f;
+    int pairInUse[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int nextPair = 0;
+    auto launch = [&](uint32_t lastWanted) -> int {
+        int k = nextPair; nextPair = (nextPair + 1) % 8;
+        if (pairInUse[k]) {            // the launch that used this pair is 8 launches old: collect its time
+            CUresult r = D(cuEventSynchronize)(ctx->evBurst[k][1]);
+            if (r != CUDA_SUCCESS) return fail(SIMLOD_ERR_CUDA, "event sync failed");
+            float ms = 0.0f; D(cuEventElapsedTime)(&ms, ctx->evBurst[k][0], ctx->evBurst[k][1]); kernelTotal += ms;
+        }
+        CUresult r = D(cuStreamWaitEvent)(ctx->streamMain, ctx->evSlot[lastWanted % RING_SLOTS], 0);
+        if (r != CUDA_SUCCESS) return fail(SIMLOD_ERR_CUDA, "stream wait failed");
+        int lrc = enqueueConstruct(ctx, k);
+        pairInUse[k] = 1;
+        return lrc;
+    };
+
+    rc = readStats(ctx); if (rc) { joinAll(); return rc; }
+    const uint32_t firstUploaded = ctx->uploaded;
+    CUresult cr = D(cuEventRecord)(ctx->evTotalStart, ctx->streamMain);
+    if (cr != CUDA_SUCCESS) { joinAll(); return fail(SIMLOD_ERR_CUDA, "event record failed"); }
+    int64_t copiesEnqueued = 0;
+    for (uint64_t k = 0; k < numBatches; k++) {
+        while (!loaded[k].load() && !abort.load()) std::this_thread::yield();
+        if (abort.load()) { joinAll(); return fail(SIMLOD_ERR_INVALID, "read error in %s", path); }
+        if (ctx->uploaded - ctx->processed >= RING_SLOTS - 1) { rc = readStats(ctx); if (rc) { joinAll(); return rc; } }   // back-pressure (main.cpp:1012)
+        uint64_t first = k * SLOT_POINTS;
+        uint32_t n = (uint32_t)std::min<uint64_t>(SLOT_POINTS, numPoints - first);
+        const SimlodPoint* src = (const SimlodPoint*)((char*)ctx->pinnedPool + (k % POOL_SLOTS) * slotBytes);
+        rc = uploadCommon(ctx, src, 0, n); if (rc) { joinAll(); return rc; }
+        cr = D(cuEventRecord)(ctx->evPool[k % POOL_SLOTS], ctx->streamUpload);
+        if (cr != CUDA_SUCCESS) { joinAll(); return fail(SIMLOD_ERR_CUDA, "event record failed"); }
+        copiesEnqueued++;
+        // pool slots whose copy has completed are handed back to the loaders (in order)
+        while (copiesDone.load() < copiesEnqueued && D(cuEventQuery)(ctx->evPool[copiesDone.load() % POOL_SLOTS]) == CUDA_SUCCESS) copiesDone.fetch_add(1);
+        if ((k & 1) == 1 || k + 1 == numBatches) { rc = launch(ctx->uploaded - 1); if (rc) { joinAll(); return rc; } }
+        // when all pool slots are in flight, wait for the oldest copy instead of spinning on the loaders
+        if (copiesEnqueued - copiesDone.load() >= POOL_SLOTS) {
+            D(cuEventSynchronize)(ctx->evPool[copiesDone.load() % POOL_SLOTS]);
+            while (copiesDone.load() < copiesEnqueued && D(cuEventQuery)(ctx->evPool[copiesDone.load() % POOL_SLOTS]) == CUDA_SUCCESS) copiesDone.fetch_add(1);
+        }
+    }
+    for (auto& th : loaders) th.join();
+    // drain: launches until every batch has been consumed
+    const uint32_t target = firstUploaded + (uint32_t)numBatches;
+    rc = readStats(ctx); if (rc) return rc;
+    while (ctx->processed < target) {
+        rc = launch(ctx->uploaded - 1); if (rc) return rc;
+        rc = readStats(ctx); if (rc) return rc;
+        if (ctx->hStats->memCapacityReached) return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed);
+    }
+    CU(D(cuEventRecord)(ctx->evTotalEnd, ctx->streamMain));
+    CU(D(cuEventSynchronize)(ctx->evTotalEnd));
+    for (int k = 0; k < 8; k++) if (pairInUse[k]) { float ms = 0.0f; D(cuEventElapsedTime)(&ms, ctx->evBurst[k][0], ctx->evBurst[k][1]); kernelTotal += ms; }
+    if (kernel_ms) *kernel_ms = kernelTotal;
+    if (total_ms) CU(D(cuEventElapsedTime)(total_ms, ctx->evTotalStart, ctx->evTotalEnd));
+    return SIMLOD_OK;
 }
 
 int simlod_render(SimlodContext* ctx, float* kernel_ms) {

@@ -196,3 +196,12 @@ def write_las(path, points, fmt=2, scale=(0.001, 0.001, 0.001), offset=(0.0, 0.0
         f.write(bytes(hdr))
         f.write(rec.tobytes())
     return rec
+
+
+def write_simlod(path, points, box_min, box_max):
+    """The .simlod container (tools/las2simlod.mjs:95-101,130-132): 6 x f32 (min, max) then 16-byte points, already
+    translated so that the box minimum is the origin."""
+    import struct
+    with open(path, "wb") as f:
+        f.write(struct.pack("<6f", *[float(v) for v in box_min], *[float(v) for v in box_max]))
+        f.write(np.ascontiguousarray(points).tobytes())
