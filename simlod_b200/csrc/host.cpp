@@ -114,7 +114,7 @@ struct SimlodContext {
     CUfunction fnLas = nullptr;
     CUdeviceptr lasStaging = 0;        // raw LAS records of the batch being decoded
     void* pinnedPool = nullptr;        // POOL_SLOTS x 16 MB page-locked staging slots of the file streamer
-    CUevent evPool[8] = {};            // H2D copy out of pool slot i has been enqueued and completed
+    CUevent evPool[32] = {};           // H2D copy out of pool slot i has been enqueued and completed
     CUfunction fnRcp = nullptr, fnFill = nullptr;
     uint32_t uploaded = 0;             // batches published to the device
     uint32_t processed = 0;            // Stats::batchletIndex as last read
@@ -347,7 +347,7 @@ void simlod_destroy(SimlodContext* ctx) {
         if (ctx->lasModule) D(cuModuleUnload)(ctx->lasModule);
         if (ctx->lasStaging) D(cuMemFree)(ctx->lasStaging);
         if (ctx->pinnedPool) D(cuMemFreeHost)(ctx->pinnedPool);
-        for (int i = 0; i < 8; i++) if (ctx->evPool[i]) D(cuEventDestroy)(ctx->evPool[i]);
+        for (int i = 0; i < 32; i++) if (ctx->evPool[i]) D(cuEventDestroy)(ctx->evPool[i]);
         if (ctx->evStart) D(cuEventDestroy)(ctx->evStart);
         if (ctx->evEnd) D(cuEventDestroy)(ctx->evEnd);
         if (ctx->evTotalStart) D(cuEventDestroy)(ctx->evTotalStart);
@@ -550,7 +550,7 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
                               float* kernel_ms, float* total_ms) {
     int rc = setCurrent(ctx); if (rc) return rc;
     if (!path) return fail(SIMLOD_ERR_INVALID, "null path");
-    constexpr int POOL_SLOTS = 8;
+    constexpr int POOL_SLOTS = 32;         // 512 MB page-locked (the reference: 200 x 16 MB, main.cpp:35)
     const uint64_t slotBytes = SLOT_POINTS * sizeof(SimlodPoint);
     FILE* f = fopen(path, "rb");
     if (!f) return fail(SIMLOD_ERR_INVALID, "cannot open %s", path);
