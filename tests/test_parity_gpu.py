@@ -340,3 +340,32 @@ def test_reference_launch_shape_one_block_per_sm():
             assert s.stats().numVisibleNodes > 0
         finally:
             s.close()
+
+
+def test_shell_and_incoherent_streams_vs_oracle(sim):
+    # config-4 geometry (sphere shell in latitude/longitude tile order) and a spatially incoherent stream
+    # (uniform random: many leaves fill at the same rate and split in the same batch)
+    pts, mn, mx = data.shell(2_400_000)
+    batches = list(data.batches(pts))
+    st, cn = build_gpu(sim, batches, (mn, mx))
+    o = build_oracle(batches, (mn, mx))
+    assert st.dbg == 0
+    assert_same_octree(st, cn, o.stats(), o.canon(), "shell: ours vs oracle")
+    assert o.check_voxel_colors(cn) == 0
+
+    pts, mn, mx = data.uniform_cube(3_000_000, size=2048.0, seed=77)
+    batches = list(data.batches(pts))
+    st, cn = build_gpu(sim, batches, (mn, mx))
+    o = build_oracle(batches, (mn, mx))
+    assert st.dbg == 0 and o.stats().droppedSpilledPoints == 0
+    assert_same_octree(st, cn, o.stats(), o.canon(), "uniform 3x1M: ours vs oracle")
+    assert o.check_voxel_colors(cn) == 0
+
+
+@needs_ref
+def test_shell_stream_vs_reference_kernels(sim):
+    pts, mn, mx = data.shell(2_400_000)
+    batches = list(data.batches(pts))
+    st, cn = build_gpu(sim, batches, (mn, mx))
+    st_r, cn_r = build_gpu(sim, batches, (mn, mx), reference=True)
+    assert_same_octree(st, cn, st_r, cn_r, "shell: ours vs reference kernels")
