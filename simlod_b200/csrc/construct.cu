@@ -985,16 +985,8 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         const uint64_t poolSize = ldv(&stats->chunkPoolSize);
 
         // ---- pass 1: count (+ sample) every batch point ------------------------------------
-#if defined(EXP_NO_SAMPLE)
-        itemPass<false, true, true>(c, batch, batchSize, 0);
-#elif defined(EXP_NO_COUNT)
-        itemPass<true, false, true>(c, batch, batchSize, 0);
-#elif defined(EXP_DESCEND_ONLY)
-        itemPass<false, false, true>(c, batch, batchSize, 0);
-#else
         if (deferSampling) itemPass<false, true, true>(c, batch, batchSize, 0);
         else               itemPass<true, true, true>(c, batch, batchSize, 0);
-#endif
         grid.sync();
         PHASE_DONE(0);
 
@@ -1022,10 +1014,6 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             PHASE_DONE(3);
         }
 
-#if defined(EXP_EXTRA_SYNCS)
-        for (int e = 0; e < 10; e++) grid.sync();
-        PHASE_DONE(3);
-#endif
         // ---- chunk allocation for touched nodes --------------------------------------------
         allocateChunks(c, poolSize);
         if (first) clearBatchCounters(other);           // the next batch's counter set is idle during this phase

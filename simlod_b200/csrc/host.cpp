@@ -12,6 +12,8 @@
 #include "../../include/simlod_b200.h"
 #include <cuda.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <algorithm>
 #include <atomic>
 #include <thread>
@@ -569,33 +571,44 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
         CU(D(cuMemHostAlloc)(&ctx->pinnedPool, (size_t)POOL_SLOTS * slotBytes, CU_MEMHOSTALLOC_PORTABLE));
         for (int i = 0; i < POOL_SLOTS; i++) CU(D(cuEventCreate)(&ctx->evPool[i], CU_EVENT_DISABLE_TIMING));
     }
-    // loaders: batch k goes to pool slot k % POOL_SLOTS once the copy of batch k - POOL_SLOTS has left it
-    std::vector<std::atomic<int>> loaded(numBatches);
+    // loaders: batch k goes to pool slot k % POOL_SLOTS once the copy of batch k - POOL_SLOTS has left it. The unit
+    // of work is a 1 MB piece of a batch, handed out in file order, so that all threads read the batch the uploader
+    // needs next (the reference reads one whole batch per thread, main.cpp:811-958: every batch then arrives late).
+    constexpr uint64_t PIECE_POINTS = 65536, PIECES = (SLOT_POINTS + PIECE_POINTS - 1) / PIECE_POINTS;
+    std::vector<std::atomic<int>> loaded(numBatches);          // pieces of batch k that have arrived
     for (auto& l : loaded) l.store(0);
     std::atomic<int64_t> copiesDone{0};           // batches whose host->device copy has completed
-    std::atomic<uint64_t> nextBatch{0};
+    std::atomic<uint64_t> nextPiece{0};
     std::atomic<bool> abort{false};
     const int nThreads = std::max(1, std::min(loader_threads, 64));
     std::vector<std::thread> loaders;
-    const std::string file(path);
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(SIMLOD_ERR_INVALID, "cannot open %s", path);
     for (int t = 0; t < nThreads; t++) {
-        loaders.emplace_back([&, t]() {
-            FILE* fh = fopen(file.c_str(), "rb");
-            if (!fh) { abort.store(true); return; }
+        loaders.emplace_back([&]() {
             for (;;) {
-                uint64_t k = nextBatch.fetch_add(1);
+                const uint64_t item = nextPiece.fetch_add(1);
+                const uint64_t k = item / PIECES, piece = item % PIECES;
                 if (k >= numBatches || abort.load()) break;
                 while (copiesDone.load() + POOL_SLOTS <= (int64_t)k && !abort.load()) std::this_thread::yield();
-                uint64_t first = k * SLOT_POINTS, n = std::min<uint64_t>(SLOT_POINTS, numPoints - first);
-                char* dst = (char*)ctx->pinnedPool + (k % POOL_SLOTS) * slotBytes;
-                fseeko(fh, (off_t)(24 + first * 16), SEEK_SET);
-                if (fread(dst, 16, n, fh) != n) abort.store(true);
-                loaded[k].store(1);
+                const uint64_t inBatch = std::min<uint64_t>(SLOT_POINTS, numPoints - k * SLOT_POINTS);
+                const uint64_t p0 = piece * PIECE_POINTS;
+                if (p0 < inBatch) {
+                    uint64_t bytes = std::min<uint64_t>(PIECE_POINTS, inBatch - p0) * 16;
+                    char* dst = (char*)ctx->pinnedPool + (k % POOL_SLOTS) * slotBytes + p0 * 16;
+                    off_t at = (off_t)(24 + (k * SLOT_POINTS + p0) * 16);
+                    while (bytes) {
+                        ssize_t r = pread(fd, dst, bytes, at);
+                        if (r <= 0) { abort.store(true); break; }
+                        dst += r; at += r; bytes -= (uint64_t)r;
+                    }
+                }
+                loaded[k].fetch_add(1);
             }
-            fclose(fh);
         });
     }
-    auto joinAll = [&]() { abort.store(true); for (auto& th : loaders) th.join(); };
+    const int allPieces = (int)PIECES;
+    auto joinAll = [&]() { abort.store(true); for (auto& th : loaders) th.join(); close(fd); };
 
     float kernelTotal = 0.0f;
     int pairInUse[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -620,7 +633,7 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
     if (cr != CUDA_SUCCESS) { joinAll(); return fail(SIMLOD_ERR_CUDA, "event record failed"); }
     int64_t copiesEnqueued = 0;
     for (uint64_t k = 0; k < numBatches; k++) {
-        while (!loaded[k].load() && !abort.load()) std::this_thread::yield();
+        while (loaded[k].load() < allPieces && !abort.load()) std::this_thread::yield();
         if (abort.load()) { joinAll(); return fail(SIMLOD_ERR_INVALID, "read error in %s", path); }
         if (ctx->uploaded - ctx->processed >= RING_SLOTS - 1) { rc = readStats(ctx); if (rc) { joinAll(); return rc; } }   // back-pressure (main.cpp:1012)
         uint64_t first = k * SLOT_POINTS;
@@ -640,6 +653,7 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
         }
     }
     for (auto& th : loaders) th.join();
+    close(fd);
     // drain: launches until every batch has been consumed
     const uint32_t target = firstUploaded + (uint32_t)numBatches;
     rc = readStats(ctx); if (rc) return rc;
