@@ -149,6 +149,26 @@ int simlod_synchronize(SimlodContext* ctx);
 // flush the L2 cache by overwriting a scratch buffer larger than it (bench hygiene)
 int simlod_flush_l2(SimlodContext* ctx);
 
+// ---- spatial exchange for ONE octree over several GPUs (no counterpart in the reference,
+// which builds on one GPU). Rank r owns the level-`level` cells c of the octree cube with owner[c] == r; a point's
+// cell is decided with the builder's own quantisation (voxels.cu:148-155, child index per level voxels.cu:171-179;
+// cell = child indices root first, 3 bits per level), against the box of simlod_set_uniforms.
+typedef struct SimlodPartitionPlan {
+    uint32_t level;               /* 1..3 */
+    uint32_t num_ranks;           /* 1..8 */
+    uint8_t owner[512];           /* [8^level] cell -> rank */
+} SimlodPartitionPlan;
+// pass 1: how many of the `count` points at device_points go to each rank (rank_counts[num_ranks]); cell_counts
+// (optional, [8^level]) receives the per-cell histogram used to plan owners. Synchronous.
+int simlod_partition_count(SimlodContext* ctx, uint64_t device_points, uint32_t count, const SimlodPartitionPlan* plan,
+                           uint64_t* rank_counts, uint64_t* cell_counts);
+// pass 2 (after pass 1 with the same points / count / plan): stable scatter. The k-th point of the batch that
+// belongs to rank d is stored at ((SimlodPoint*)dest_ptrs[d])[dest_offsets[d] + k]; dest_ptrs may be local device
+// memory or peer memory mapped over NVLink (the store stream IS the exchange). Asynchronous on the launch
+// stream: simlod_synchronize() before another rank may read.
+int simlod_partition_scatter(SimlodContext* ctx, uint64_t device_points, uint32_t count, const SimlodPartitionPlan* plan,
+                             const uint64_t* dest_ptrs, const uint64_t* dest_offsets);
+
 #ifdef __cplusplus
 }
 #endif

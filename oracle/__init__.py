@@ -69,6 +69,7 @@ def lib():
         L.canon_render.argtypes = [vp, vp, vp, C.POINTER(RenderStats)]
         L.canon_flags.argtypes = [vp, vp]
         L.oracle_decode_las.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+        L.oracle_partition_cells.argtypes = [vp, C.c_uint64, vp, vp, C.c_float, C.c_uint32, vp]
         _lib = L
     return _lib
 
@@ -163,6 +164,76 @@ def compare_canon(a, b, what="octree"):
     return diffs
 
 
+def _level_cell(rec, level):
+    """Level-`level` ancestor cell (child indices root first) of a canonical node record at level >= `level`."""
+    sh = int(rec["level"]) - level
+    x, y, z = int(rec["X"]) >> sh, int(rec["Y"]) >> sh, int(rec["Z"]) >> sh
+    cell = 0
+    for l in range(level):
+        b = level - 1 - l
+        cell = (cell << 3) | (((x >> b) & 1) << 2) | (((y >> b) & 1) << 1) | ((z >> b) & 1)
+    return cell
+
+
+def compare_merged(single, per_rank, level, owners):
+    """The forest a spatial exchange builds (per_rank[r] = canonical octree of rank r, which owns the level-`level`
+    cells c with owners[c] == r) against the single octree of the whole stream:
+      * every node of the single octree at level >= `level` exists on the owner of its cell with an identical
+        record (counters, chunk counts, hashes of the sorted points and voxel positions),
+      * whatever else a rank holds at those levels is an empty leaf (the 7 siblings a split creates),
+      * every node above `level` that is inner in the single octree: the ranks' voxel POSITION sets are disjoint
+        and their union is the single node's set.
+    Precondition (reported as a difference when violated): a node above `level` that is inner in the single octree
+    is inner on every rank that holds points below it, i.e. every rank's share of it exceeds the leaf capacity —
+    until then that rank still keeps the points in a leaf above `level`.
+    Returns a list of differences."""
+    diffs = []
+    fields = [f for f in RECORD_DTYPE.names if f not in ("nodeIndex", "_pad")]
+    key = lambda r: (int(r["level"]), int(r["X"]), int(r["Y"]), int(r["Z"]))
+    maps = [{key(r): i for i, r in enumerate(c.records)} for c in per_rank]
+    for i, rec in enumerate(single.records):
+        k = key(rec)
+        if k[0] >= level:
+            own = int(owners[_level_cell(rec, level)])
+            j = maps[own].get(k)
+            if j is None:
+                if int(rec["counter"]) or int(rec["numPoints"]):
+                    diffs.append("node %s missing on its owner %d" % (rec["name"], own))
+                continue
+            other = per_rank[own].records[j]
+            for f in fields:
+                if rec[f] != other[f]:
+                    diffs.append("node %s on rank %d differs in %s: %r != %r" % (rec["name"], own, f, other[f], rec[f]))
+            for r, m in enumerate(maps):
+                if r != own and k in m:
+                    o = per_rank[r].records[m[k]]
+                    if int(o["counter"]) or int(o["numPoints"]) or int(o["numVoxels"]) or not int(o["isLeaf"]):
+                        diffs.append("rank %d holds samples in node %s owned by rank %d" % (r, rec["name"], own))
+        elif not int(rec["isLeaf"]):
+            want = np.unique(np.stack([single.samples(i, voxels=True)[a] for a in "xyz"], axis=1), axis=0)
+            parts = []
+            for r, m in enumerate(maps):
+                if k in m and not int(per_rank[r].records[m[k]]["isLeaf"]):
+                    v = per_rank[r].samples(m[k], voxels=True)
+                    parts.append(np.unique(np.stack([v[a] for a in "xyz"], axis=1), axis=0))
+                elif k in m and int(per_rank[r].records[m[k]]["numPoints"]):
+                    diffs.append("precondition: node %s is inner in the single octree but still a leaf with %d points on rank %d"
+                                 % (rec["name"], int(per_rank[r].records[m[k]]["numPoints"]), r))
+            got = np.concatenate(parts) if parts else np.zeros((0, 3), np.float32)
+            uniq = np.unique(got, axis=0)
+            if len(uniq) != len(got):
+                diffs.append("node %s: the ranks' voxel sets overlap" % rec["name"])
+            if uniq.shape != want.shape or not np.array_equal(uniq, want):
+                diffs.append("node %s: union of the ranks' voxels (%d) != single octree's (%d)" % (rec["name"], len(uniq), len(want)))
+    # nothing but the single octree's nodes (or empty leaves) at level >= `level`
+    have = {key(r) for r in single.records}
+    for r, c in enumerate(per_rank):
+        for rec in c.records:
+            if int(rec["level"]) >= level and key(rec) not in have and (int(rec["counter"]) or int(rec["numPoints"])):
+                diffs.append("rank %d has an extra non-empty node %s" % (r, rec["name"]))
+    return diffs
+
+
 def compare_stats(a, b, fields=STATS_FIELDS):
     return ["Stats.%s: %d != %d" % (f, getattr(a, f), getattr(b, f)) for f in fields if int(getattr(a, f)) != int(getattr(b, f))]
 
@@ -175,6 +246,25 @@ def decode_las(records, count, bytes_per_point, fmt, scale, offset, translation=
     sc, of, tr = (np.asarray(v, dtype=np.float64) for v in (scale, offset, translation))
     lib().oracle_decode_las(rec.ctypes.data, count, bytes_per_point, fmt, sc.ctypes.data, of.ctypes.data, tr.ctypes.data, out.ctypes.data)
     return out
+
+
+# ---- spatial exchange ---------------------------------------------------------------
+def partition_cells(points, box_min, box_max, level, rcp_size=None):
+    """Level-`level` octree cell of every point (child indices root first), by the builder's quantisation."""
+    pts = np.ascontiguousarray(points, dtype=POINT_DTYPE)
+    mn, mx = np.asarray(box_min, dtype=np.float32), np.asarray(box_max, dtype=np.float32)
+    size = float(np.max(mx - mn))
+    rcp = np.float32(1.0) / np.float32(size) if rcp_size is None else np.float32(rcp_size)
+    out = np.empty(len(pts), dtype=np.uint32)
+    lib().oracle_partition_cells(pts.ctypes.data, len(pts), mn.ctypes.data, mx.ctypes.data, C.c_float(float(rcp)), level, out.ctypes.data)
+    return out
+
+
+def partition_stable(points, box_min, box_max, level, owners, num_ranks, rcp_size=None):
+    """[points owned by rank d, in input order] for d in range(num_ranks): what the scatter pass must produce."""
+    pts = np.ascontiguousarray(points, dtype=POINT_DTYPE)
+    dst = np.asarray(owners, dtype=np.uint8)[partition_cells(pts, box_min, box_max, level, rcp_size)]
+    return [pts[dst == d] for d in range(num_ranks)]
 
 
 _ref_las = None

@@ -623,3 +623,19 @@ extern "C" void oracle_decode_las(const uint8_t* records, uint64_t numPoints, ui
         out[i] = p;
     }
 }
+
+// ---- spatial exchange: the level-`level` octree cell a point descends into, with the builder's
+// own quantisation (voxels.cu:148-155) and child order (voxels.cu:171-179); cell = child indices root first.
+extern "C" void oracle_partition_cells(const SimlodPoint* pts, uint64_t n, const float* boxMin, const float* boxMax, float rcpSize,
+                                       uint32_t level, uint32_t* cells) {
+    Quantizer qz;
+    qz.minx = boxMin[0]; qz.miny = boxMin[1]; qz.minz = boxMin[2];
+    qz.size = std::max(std::max(boxMax[0] - boxMin[0], boxMax[1] - boxMin[1]), boxMax[2] - boxMin[2]);
+    qz.rcp = rcpSize;
+    for (uint64_t i = 0; i < n; i++) {
+        Coords q = qz(pts[i]);
+        uint32_t cell = 0;
+        for (uint32_t l = 0; l < level; l++) cell = (cell << 3) | childIndexAt(q, (int)l);
+        cells[i] = cell;
+    }
+}

@@ -94,6 +94,11 @@ class LasLayout(C.Structure):
                 ("translation", C.c_double * 3)]
 
 
+class PartitionPlan(C.Structure):
+    """SimlodPartitionPlan: the level-`level` cells of the octree cube and the rank that owns each."""
+    _fields_ = [("level", C.c_uint32), ("num_ranks", C.c_uint32), ("owner", C.c_uint8 * 512)]
+
+
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "nodes", "nodes_bytes", "persistent", "persistent_bytes", "momentary", "momentary_bytes",
@@ -110,6 +115,7 @@ EXPORTS = [
     "simlod_read_framebuffer", "simlod_read_surface", "simlod_get_buffers", "simlod_memcpy_dtoh",
     "simlod_memcpy_htod", "simlod_host_alloc", "simlod_host_free", "simlod_device_alloc", "simlod_device_free",
     "simlod_get_launch_info", "simlod_device_rcp", "simlod_synchronize", "simlod_flush_l2",
+    "simlod_partition_count", "simlod_partition_scatter",
 ]
 
 _lib = None
@@ -155,6 +161,8 @@ def load_library():
         "simlod_device_rcp": [vp, C.c_float, C.POINTER(C.c_float)],
         "simlod_flush_l2": [vp],
         "simlod_synchronize": [vp],
+        "simlod_partition_count": [vp, u64, u32, C.POINTER(PartitionPlan), C.POINTER(u64), C.POINTER(u64)],
+        "simlod_partition_scatter": [vp, u64, u32, C.POINTER(PartitionPlan), C.POINTER(u64), C.POINTER(u64)],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -424,3 +432,25 @@ class SimLOD:
 
     def flush_l2(self):
         self._check(self._lib.simlod_flush_l2(self._ctx))
+
+    # ---- spatial exchange (one octree over several GPUs) ----
+    @staticmethod
+    def partition_plan(level, owners, num_ranks):
+        owners = np.asarray(owners, dtype=np.uint8)
+        if owners.shape != (8 ** level,):
+            raise ValueError("need %d owners for level %d" % (8 ** level, level))
+        plan = PartitionPlan(level, num_ranks)
+        C.memmove(plan.owner, owners.ctypes.data, owners.size)
+        return plan
+
+    def partition_count(self, device_ptr, count, plan):
+        """(points per destination rank, points per level-`level` cell) of the batch at device_ptr."""
+        ranks = (C.c_uint64 * plan.num_ranks)()
+        cells = (C.c_uint64 * (8 ** plan.level))()
+        self._check(self._lib.simlod_partition_count(self._ctx, int(device_ptr), int(count), C.byref(plan), ranks, cells))
+        return np.array(ranks[:], dtype=np.uint64), np.array(cells[:], dtype=np.uint64)
+
+    def partition_scatter(self, device_ptr, count, plan, dest_ptrs, dest_offsets):
+        ptrs = (C.c_uint64 * plan.num_ranks)(*[int(p) for p in dest_ptrs])
+        offs = (C.c_uint64 * plan.num_ranks)(*[int(o) for o in dest_offsets])
+        self._check(self._lib.simlod_partition_scatter(self._ctx, int(device_ptr), int(count), C.byref(plan), ptrs, offs))

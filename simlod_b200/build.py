@@ -21,7 +21,7 @@ NVCC = os.path.join(CUDA, "bin", "nvcc")
 BIN2C = os.path.join(CUDA, "bin", "bin2c")
 LIB = os.path.join(ROOT, "simlod_b200", "libsimlod_b200.so")
 CUBIN_DIR = os.path.join(ROOT, "simlod_b200", "cubin")
-PROGRAMS = ["construct", "render", "reset", "util", "las"]
+PROGRAMS = ["construct", "render", "reset", "util", "las", "partition"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -29,6 +29,7 @@ extern const unsigned char simlod_cubin_construct[];
 extern const unsigned char simlod_cubin_render[];
 extern const unsigned char simlod_cubin_reset[];
 extern const unsigned char simlod_cubin_util[];
+extern const unsigned char simlod_cubin_partition[];
 extern const unsigned char simlod_cubin_las[];
 }
 
@@ -112,7 +113,11 @@ struct SimlodContext {
     CUsurfObject surface = 0;
     SimlodStats* hStats = nullptr;     // pinned
     Program programs[3];
-    CUmodule utilModule = nullptr, lasModule = nullptr;
+    CUmodule utilModule = nullptr, lasModule = nullptr, partitionModule = nullptr;
+    CUfunction fnPartCount = nullptr, fnPartScan = nullptr, fnPartScatter = nullptr;
+    CUdeviceptr partScratch = 0;       // blockHist | blockBase | totals | cellCounts of the spatial exchange
+    uint32_t partCount = 0xffffffffu;  // arguments of the last simlod_partition_count (pass 2 must match)
+    uint64_t partPoints = 0;
     CUfunction fnLas = nullptr;
     CUdeviceptr lasStaging = 0;        // raw LAS records of the batch being decoded
     void* pinnedPool = nullptr;        // POOL_SLOTS x 16 MB page-locked staging slots of the file streamer
@@ -277,6 +282,10 @@ int simlod_create(const SimlodConfig* config, SimlodContext** out) {
     CU(D(cuModuleGetFunction)(&ctx->fnFill, ctx->utilModule, "simlod_util_fill"));
     CU(D(cuModuleLoadData)(&ctx->lasModule, simlod_cubin_las));
     CU(D(cuModuleGetFunction)(&ctx->fnLas, ctx->lasModule, "simlod_las_decode"));
+    CU(D(cuModuleLoadData)(&ctx->partitionModule, simlod_cubin_partition));
+    CU(D(cuModuleGetFunction)(&ctx->fnPartCount, ctx->partitionModule, "simlod_partition_count"));
+    CU(D(cuModuleGetFunction)(&ctx->fnPartScan, ctx->partitionModule, "simlod_partition_scan"));
+    CU(D(cuModuleGetFunction)(&ctx->fnPartScatter, ctx->partitionModule, "simlod_partition_scatter"));
 
     // buffers (main.cpp:552-586)
     SimlodBuffers& b = ctx->buf;
@@ -346,6 +355,8 @@ void simlod_destroy(SimlodContext* ctx) {
         if (ctx->hStats) D(cuMemFreeHost)(ctx->hStats);
         for (int p = 0; p < 3; p++) if (ctx->programs[p].module) D(cuModuleUnload)(ctx->programs[p].module);
         if (ctx->utilModule) D(cuModuleUnload)(ctx->utilModule);
+        if (ctx->partitionModule) D(cuModuleUnload)(ctx->partitionModule);
+        if (ctx->partScratch) D(cuMemFree)(ctx->partScratch);
         if (ctx->lasModule) D(cuModuleUnload)(ctx->lasModule);
         if (ctx->lasStaging) D(cuMemFree)(ctx->lasStaging);
         if (ctx->pinnedPool) D(cuMemFreeHost)(ctx->pinnedPool);
@@ -792,6 +803,86 @@ int simlod_flush_l2(SimlodContext* ctx) {
     CU(D(cuLaunchKernel)(ctx->fnFill, (unsigned)(ctx->numSMs * 8), 1, 1, 256, 1, 1, 0, ctx->streamMain, args, nullptr));
     ctx->launches++;
     CU(D(cuStreamSynchronize)(ctx->streamMain));
+    return SIMLOD_OK;
+}
+
+// ---- spatial exchange; kernels in partition.cu ----------------------------------------
+namespace {
+constexpr uint32_t PART_MAX_RANKS = 8, PART_MAX_CELLS = 512, PART_BLOCK = 256;
+struct PartitionParams {             // mirrors partition.cu
+    float minx, miny, minz, size;
+    uint32_t level, numRanks, count, perBlock;
+    uint8_t owner[PART_MAX_CELLS];
+};
+struct ScatterTargets { uint64_t ptr[PART_MAX_RANKS]; uint64_t offset[PART_MAX_RANKS]; };
+
+int partitionSetup(SimlodContext* ctx, uint32_t count, const SimlodPartitionPlan* plan, PartitionParams* p, uint32_t* blocks) {
+    if (!plan) return fail(SIMLOD_ERR_INVALID, "null plan");
+    if (plan->level < 1 || plan->level > 3) return fail(SIMLOD_ERR_INVALID, "partition level %u outside 1..3", plan->level);
+    if (plan->num_ranks < 1 || plan->num_ranks > PART_MAX_RANKS) return fail(SIMLOD_ERR_INVALID, "partition over %u ranks (1..8)", plan->num_ranks);
+    const uint32_t numCells = 1u << (3 * plan->level);
+    for (uint32_t c = 0; c < numCells; c++)
+        if (plan->owner[c] >= plan->num_ranks) return fail(SIMLOD_ERR_INVALID, "cell %u is owned by rank %u of %u", c, plan->owner[c], plan->num_ranks);
+    const float sx = ctx->uniforms.boxMax[0] - ctx->uniforms.boxMin[0], sy = ctx->uniforms.boxMax[1] - ctx->uniforms.boxMin[1],
+                sz = ctx->uniforms.boxMax[2] - ctx->uniforms.boxMin[2];
+    p->minx = ctx->uniforms.boxMin[0]; p->miny = ctx->uniforms.boxMin[1]; p->minz = ctx->uniforms.boxMin[2];
+    p->size = std::max(std::max(sx, sy), sz);                                       // voxels.cu:860-863
+    p->level = plan->level; p->numRanks = plan->num_ranks; p->count = count;
+    *blocks = (uint32_t)ctx->numSMs * 4;
+    const uint32_t per = (count + *blocks - 1) / *blocks;
+    p->perBlock = std::max(PART_BLOCK, (per + PART_BLOCK - 1) / PART_BLOCK * PART_BLOCK);
+    memset(p->owner, 0, sizeof(p->owner));
+    memcpy(p->owner, plan->owner, numCells);
+    if (!ctx->partScratch) CU(D(cuMemAlloc)(&ctx->partScratch, (size_t)*blocks * PART_MAX_RANKS * 4 * 2 + PART_MAX_RANKS * 4 + PART_MAX_CELLS * 4));
+    return SIMLOD_OK;
+}
+}  // namespace
+
+int simlod_partition_count(SimlodContext* ctx, uint64_t device_points, uint32_t count, const SimlodPartitionPlan* plan,
+                           uint64_t* rank_counts, uint64_t* cell_counts) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!rank_counts) return fail(SIMLOD_ERR_INVALID, "null argument");
+    if (!device_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
+    PartitionParams p; uint32_t blocks = 0;
+    rc = partitionSetup(ctx, count, plan, &p, &blocks); if (rc) return rc;
+    CUdeviceptr pts = (CUdeviceptr)device_points;
+    CUdeviceptr blockHist = ctx->partScratch, blockBase = blockHist + (size_t)blocks * PART_MAX_RANKS * 4,
+                totals = blockBase + (size_t)blocks * PART_MAX_RANKS * 4, cells = totals + PART_MAX_RANKS * 4;
+    CU(D(cuMemsetD8Async)(cells, 0, PART_MAX_CELLS * 4, ctx->streamMain));
+    { void* args[] = {&p, &pts, &blockHist, &cells};
+      CU(D(cuLaunchKernel)(ctx->fnPartCount, blocks, 1, 1, PART_BLOCK, 1, 1, 0, ctx->streamMain, args, nullptr)); }
+    { void* args[] = {&blockHist, &blocks, &blockBase, &totals};
+      CU(D(cuLaunchKernel)(ctx->fnPartScan, 1, 1, 1, PART_BLOCK, 1, 1, 0, ctx->streamMain, args, nullptr)); }
+    ctx->launches += 2;
+    uint32_t host[PART_MAX_RANKS + PART_MAX_CELLS];
+    CU(D(cuMemcpyDtoHAsync)(host, totals, sizeof(host), ctx->streamMain));
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    for (uint32_t d = 0; d < plan->num_ranks; d++) rank_counts[d] = host[d];
+    if (cell_counts) for (uint32_t c = 0; c < (1u << (3 * plan->level)); c++) cell_counts[c] = host[PART_MAX_RANKS + c];
+    ctx->partCount = count; ctx->partPoints = device_points;
+    return SIMLOD_OK;
+}
+
+int simlod_partition_scatter(SimlodContext* ctx, uint64_t device_points, uint32_t count, const SimlodPartitionPlan* plan,
+                             const uint64_t* dest_ptrs, const uint64_t* dest_offsets) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!dest_ptrs || !dest_offsets) return fail(SIMLOD_ERR_INVALID, "null argument");
+    if (ctx->partCount != count || ctx->partPoints != device_points)
+        return fail(SIMLOD_ERR_INVALID, "simlod_partition_scatter must follow simlod_partition_count on the same batch");
+    PartitionParams p; uint32_t blocks = 0;
+    rc = partitionSetup(ctx, count, plan, &p, &blocks); if (rc) return rc;
+    ScatterTargets t;
+    memset(&t, 0, sizeof(t));
+    for (uint32_t d = 0; d < plan->num_ranks; d++) {
+        if (!dest_ptrs[d]) return fail(SIMLOD_ERR_INVALID, "null destination for rank %u", d);
+        t.ptr[d] = dest_ptrs[d]; t.offset[d] = dest_offsets[d];
+    }
+    CUdeviceptr pts = (CUdeviceptr)device_points;
+    CUdeviceptr blockBase = ctx->partScratch + (size_t)blocks * PART_MAX_RANKS * 4;
+    void* args[] = {&p, &t, &pts, &blockBase};
+    CU(D(cuLaunchKernel)(ctx->fnPartScatter, blocks, 1, 1, PART_BLOCK, 1, 1, 0, ctx->streamMain, args, nullptr));
+    ctx->launches++;
+    ctx->partCount = 0xffffffffu;
     return SIMLOD_OK;
 }
 

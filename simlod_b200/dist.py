@@ -81,3 +81,135 @@ def composite_framebuffers(fb, device="cpu"):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
     out = t.cpu().numpy().view(np.uint64) ^ np.uint64(1 << 63)
     return out.reshape(a.shape)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ONE octree over G GPUs: spatial exchange
+#
+# Rank r owns the level-L cells of the octree cube that `plan_owners` assigns to it and builds the
+# octree of exactly the points that fall into them; every subtree at level >= L therefore lives on
+# one rank and equals the subtree the single-GPU builder produces from the whole stream (the final
+# topology and the leaf contents do not depend on batch order), and the nodes above level L exist on
+# every rank with that rank's share of their voxels (a voxel cell lies inside one level-L cell, so
+# the shares are disjoint and their union is the single-GPU node). The exchange step per batch:
+#   count     simlod_partition_count: points per destination rank (+ per-cell histogram)
+#   layout    all_gather of the G counts -> G x G matrix -> where my points land in each receiver
+#   push      simlod_partition_scatter: stable scatter whose 16-byte stores go straight into the
+#             receivers' buffers over NVLink peer memory ("p2p"), or into a local staging buffer
+#             followed by all_to_all_single ("nccl", the baseline the fused path is measured against)
+#   barrier   then every rank inserts what it received
+# ---------------------------------------------------------------------------------------------------
+def plan_owners(cell_counts, world_size):
+    """Owner rank of every level-L cell from a (global) per-cell point histogram: longest-processing-time
+    greedy — cells by descending count (ties: lower cell first) to the least loaded rank (ties: lower rank).
+    Deterministic, so every rank derives the same plan from the all-reduced histogram."""
+    counts = np.asarray(cell_counts, dtype=np.int64)
+    owners = np.zeros(len(counts), dtype=np.uint8)
+    load = [0] * world_size
+    order = sorted(range(len(counts)), key=lambda c: (-int(counts[c]), c))
+    for c in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        owners[c] = r
+        load[r] += int(counts[c])
+    return owners
+
+
+def exchange_layout(matrix, rank):
+    """matrix[s][d] = points rank s sends to rank d in this step. Returns (send_offsets, landing_offsets,
+    recv_count): my bucket for d starts at send_offsets[d] of a local staging buffer; in receiver d's buffer my
+    points start at landing_offsets[d] = sum of what lower ranks send to d (receivers see senders in rank
+    order); recv_count = what I receive in total."""
+    m = np.asarray(matrix, dtype=np.int64)
+    send_offsets = np.concatenate(([0], np.cumsum(m[rank])[:-1]))
+    landing_offsets = m[:rank].sum(axis=0)
+    return send_offsets, landing_offsets, int(m[:, rank].sum())
+
+
+def gather_counts(my_counts, device="cpu"):
+    """all_gather of the per-destination counts: the G x G matrix of this step (same on every rank)."""
+    import torch
+    dist = _dist()
+    mine = torch.tensor([int(c) for c in my_counts], dtype=torch.int64, device=device)
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return mine.cpu().numpy()[None, :]
+    out = torch.empty(dist.get_world_size() * len(mine), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, mine)
+    return out.cpu().numpy().reshape(dist.get_world_size(), len(mine))
+
+
+def all_to_all_points(send, recv, matrix, rank):
+    """Baseline exchange: `send` holds my buckets back to back (uint8 tensor, 16 B per point), `recv` receives the
+    senders' buckets in rank order. Returns the number of points received."""
+    dist = _dist()
+    m = np.asarray(matrix, dtype=np.int64)
+    in_split = [int(c) * 16 for c in m[rank]]
+    out_split = [int(c) * 16 for c in m[:, rank]]
+    dist.all_to_all_single(recv[:sum(out_split)], send[:sum(in_split)], output_split_sizes=out_split, input_split_sizes=in_split)
+    return sum(out_split) // 16
+
+
+class SpatialExchange:
+    """Per-rank driver of the exchange on the GPUs (one process per GPU; needs CUDA, NCCL and the C-ABI library).
+
+    mode "p2p":  receive buffers are torch symmetric memory (peer-mapped over NVLink); the scatter kernel of every
+                 rank stores straight into the owners' buffers, NCCL only carries the counts and the barrier.
+    mode "nccl": scatter into a local staging buffer, then all_to_all_single.
+    Receive buffers are double-buffered by step parity, so one barrier per step also protects the buffer the
+    peers overwrite two steps later."""
+
+    def __init__(self, sim, level, owners, capacity_points=1_000_000, mode="p2p", device=None):
+        import torch
+        dist = _dist()
+        self.sim, self.mode = sim, mode
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.plan = sim.partition_plan(level, owners, self.world)
+        self.capacity = int(capacity_points)
+        half = self.world * self.capacity * 16                 # worst case: every sender's whole batch lands here
+        self.half_bytes = half
+        self.step = 0
+        if mode == "p2p":
+            import torch.distributed._symmetric_memory as symm_mem
+            self.recv = symm_mem.empty(2 * half, dtype=torch.uint8, device=self.device)
+            self.handle = symm_mem.rendezvous(self.recv, dist.group.WORLD)
+            self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            assert self.peer_ptrs[self.rank] == self.recv.data_ptr()
+        elif mode == "nccl":
+            self.recv = torch.empty(2 * half, dtype=torch.uint8, device=self.device)
+            self.send = torch.empty(self.capacity * 16, dtype=torch.uint8, device=self.device)
+        else:
+            raise ValueError("mode must be 'p2p' or 'nccl'")
+
+    def cell_histogram(self, device_ptr, count):
+        """Global per-cell histogram of one batch per rank (all-reduced) — the input of plan_owners."""
+        import torch
+        dist = _dist()
+        _, cells = self.sim.partition_count(device_ptr, count, self.plan)
+        t = torch.tensor(cells.astype(np.int64), device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def exchange(self, device_ptr, count):
+        """Send the `count` points at device_ptr to their owners. Returns (device address, number of points) of what
+        this rank received, valid until the step after next."""
+        import torch
+        dist = _dist()
+        if count > self.capacity:
+            raise ValueError("batch of %d points exceeds the exchange capacity %d" % (count, self.capacity))
+        mine, _ = self.sim.partition_count(device_ptr, count, self.plan)
+        matrix = gather_counts(mine, self.device)
+        send_offsets, landing, recv_count = exchange_layout(matrix, self.rank)
+        base = (self.step & 1) * self.half_bytes
+        if self.mode == "p2p":
+            self.sim.partition_scatter(device_ptr, count, self.plan, [p + base for p in self.peer_ptrs], landing)
+            self.sim.synchronize()                       # my stores have left
+            self.handle.barrier()                        # everyone's stores have landed
+            torch.cuda.current_stream().synchronize()
+        else:
+            self.sim.partition_scatter(device_ptr, count, self.plan, [self.send.data_ptr()] * self.world, send_offsets)
+            self.sim.synchronize()
+            got = all_to_all_points(self.send, self.recv[base:base + self.half_bytes], matrix, self.rank)
+            torch.cuda.current_stream().synchronize()
+            assert got == recv_count
+        self.step += 1
+        return self.recv.data_ptr() + base, recv_count

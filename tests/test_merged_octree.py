@@ -1,0 +1,258 @@
+"""ONE octree over several GPUs: the spatial exchange.
+
+CPU (-m "not gpu"): the planning / layout host logic, the defining property of the merged forest checked with
+the CPU oracle as the per-rank builder, and the exchange plumbing at world_size 2 over gloo.
+GPU (-m gpu): the partition kernels against the oracle's restatement (bit-exact, stable order) and the merged
+forest built by our kernels (two rank builders on one GPU) against our single octree and the oracle.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from simlod_b200 import data
+from simlod_b200 import dist as sdist
+
+
+def _plan(points, box, level, world):
+    cells = oracle.partition_cells(points, box[0], box[1], level)
+    return sdist.plan_owners(np.bincount(cells, minlength=8 ** level), world)
+
+
+def test_plan_owners_balances_and_is_deterministic():
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 4, 8):
+        counts = rng.integers(0, 100000, 64)
+        counts[rng.integers(0, 64, 20)] = 0
+        a, b = sdist.plan_owners(counts, world), sdist.plan_owners(counts.copy(), world)
+        assert np.array_equal(a, b) and a.max() < world
+        load = np.bincount(a, weights=counts, minlength=world)
+        assert load.max() - load.min() <= counts.max()          # LPT bound
+    assert list(sdist.plan_owners([5, 0, 9, 0, 3, 3, 0, 1], 2)) == [1, 0, 0, 0, 1, 1, 0, 0]
+
+
+def test_exchange_layout_places_senders_in_rank_order():
+    m = np.array([[4, 1, 0], [2, 0, 7], [3, 3, 3]])
+    for r in range(3):
+        send, landing, got = sdist.exchange_layout(m, r)
+        assert list(send) == list(np.concatenate(([0], np.cumsum(m[r])[:-1])))
+        assert list(landing) == list(m[:r].sum(axis=0))
+        assert got == m[:, r].sum()
+    # the landing ranges of all senders tile every receiver's buffer exactly
+    for d in range(3):
+        spans = sorted((int(sdist.exchange_layout(m, s)[1][d]), int(m[s][d])) for s in range(3))
+        pos = 0
+        for start, n in spans:
+            assert start == pos or n == 0
+            pos += n
+        assert pos == m[:, d].sum()
+
+
+@pytest.mark.parametrize("kind,level,world", [("uniform", 1, 2), ("uniform", 1, 3), ("uniform", 2, 2), ("terrain", 1, 4), ("terrain", 2, 2)])
+def test_merged_forest_equals_single_octree_with_the_oracle_as_builder(kind, level, world):
+    if kind == "uniform":
+        pts, mn, mx = data.uniform_cube(600_000 if level == 1 else 1_000_000, size=64.0, seed=5)
+    else:
+        pts, mn, mx = data.terrain(900_000 if level == 1 else 3_000_000)
+    sizes = [70_000, 1, 129_999, 50_000] + [50_000] * ((len(pts) - 250_000) // 50_000)
+    # the forest is comparable once every rank's share of every shared upper node exceeds the leaf capacity
+    # (oracle.compare_merged): at level 2 on 1 M uniform points that needs an even split of each level-1 node
+    owners = (np.arange(64) % 2).astype(np.uint8) if (kind, level) == ("uniform", 2) else _plan(pts, (mn, mx), level, world)
+    single = oracle.Oracle(mn, mx)
+    ranks = [oracle.Oracle(mn, mx) for _ in range(world)]
+    s = 0
+    for n in sizes:
+        b = pts[s:s + n]
+        s += n
+        single.add_batch(b)
+        for r, part in enumerate(oracle.partition_stable(b, mn, mx, level, owners, world)):
+            ranks[r].add_batch(part)
+    assert s == len(pts)
+    diffs = oracle.compare_merged(single.canon(), [o.canon() for o in ranks], level, owners)
+    assert not diffs, "\n".join(diffs[:10])
+    assert sum(o.stats().numPoints for o in ranks) == len(pts)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+LEVEL, BATCH = 1, 60_000
+
+
+def _stream():
+    return data.terrain(480_000)
+
+
+def _worker(rank, world, port, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pts, mn, mx = _stream()
+        mine = [pts[f:f + c] for f, c in sdist.shard_point_range(len(pts), BATCH, rank, world)]
+        # plan from the all-reduced cell histogram of the local shards
+        hist = torch.from_numpy(np.bincount(oracle.partition_cells(np.concatenate(mine), mn, mx, LEVEL), minlength=8 ** LEVEL).astype(np.int64))
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        owners = sdist.plan_owners(hist.numpy(), world)
+        received = []
+        for b in mine:
+            parts = oracle.partition_stable(b, mn, mx, LEVEL, owners, world)
+            matrix = sdist.gather_counts([len(p) for p in parts])
+            send_offsets, landing, recv_count = sdist.exchange_layout(matrix, rank)
+            staged = np.concatenate(parts)
+            assert all(int(send_offsets[d]) == sum(len(p) for p in parts[:d]) for d in range(world))
+            send = torch.from_numpy(staged.view(np.uint8).copy())
+            recv = torch.empty(world * BATCH * 16, dtype=torch.uint8)
+            got = sdist.all_to_all_points(send, recv, matrix, rank)
+            assert got == recv_count
+            received.append(recv[:got * 16].numpy().view(data.POINT_DTYPE).copy())
+        np.savez(os.path.join(outdir, "rank%d.npz" % rank), owners=owners, hist=hist.numpy(),
+                 **{"step%d" % i: r for i, r in enumerate(received)})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_spatial_exchange_over_gloo_world2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    pts, mn, mx = _stream()
+    out = [np.load(os.path.join(tmp_path, "rank%d.npz" % r)) for r in range(world)]
+    owners = out[0]["owners"]
+    assert np.array_equal(owners, out[1]["owners"])
+    assert np.array_equal(out[0]["hist"], np.bincount(oracle.partition_cells(pts, mn, mx, LEVEL), minlength=8 ** LEVEL))
+    steps = len([k for k in out[0].files if k.startswith("step")])
+    shards = [sdist.shard_point_range(len(pts), BATCH, r, world) for r in range(world)]
+    ranks = [oracle.Oracle(mn, mx) for _ in range(world)]
+    for i in range(steps):
+        # what rank d must have received in step i: the senders' buckets for d, in rank order, each in input order
+        sent = [oracle.partition_stable(pts[f:f + c], mn, mx, LEVEL, owners, world) for f, c in (shards[s][i] for s in range(world))]
+        for d in range(world):
+            want = np.concatenate([sent[s][d] for s in range(world)])
+            got = out[d]["step%d" % i]
+            assert got.tobytes() == want.tobytes()
+            ranks[d].add_batch(got)
+    single = oracle.Oracle(mn, mx)
+    for i in range(steps):
+        for s in range(world):
+            f, c = shards[s][i]
+            single.add_batch(pts[f:f + c])
+    diffs = oracle.compare_merged(single.canon(), [o.canon() for o in ranks], LEVEL, owners)
+    assert not diffs, "\n".join(diffs[:10])
+
+
+# ---- GPU ---------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def sims():
+    from simlod_b200 import SimLOD
+    made = [SimLOD(640, 360, persistent_bytes=3 << 30) for _ in range(3)]
+    yield made
+    for s in made:
+        s.close()
+
+
+def _upload(sim, points):
+    ptr = sim.device_alloc(max(16, len(points) * 16))
+    if len(points):
+        sim.memcpy_htod(ptr, np.ascontiguousarray(points).view(np.uint8))
+    return ptr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,count,level,world", [("terrain", 1_000_000, 2, 2), ("terrain", 777_777, 3, 8), ("uniform", 1_000_000, 1, 3),
+                                                     ("uniform", 1, 2, 4), ("uniform", 255, 1, 2), ("outside", 300_000, 2, 5)])
+def test_partition_kernels_match_the_oracle(sims, kind, count, level, world):
+    sim = sims[0]
+    if kind == "terrain":
+        pts, mn, mx = data.terrain(count)
+    else:
+        pts, mn, mx = data.uniform_cube(count, size=1000.0 if kind == "outside" else 64.0, seed=9)
+    if kind == "outside":            # non power-of-two cube, points beyond the box on both sides: saturation and wrap-around
+        pts = pts.copy()
+        pts["x"][::7] -= 400.0
+        pts["y"][::11] += 900.0
+        pts["z"][::13] = np.float32(1000.0)
+    sim.set_box(mn, mx)
+    size = float(np.max(np.asarray(mx, np.float32) - np.asarray(mn, np.float32)))
+    rcp = sim.device_rcp(size)
+    cells = oracle.partition_cells(pts, mn, mx, level, rcp)
+    owners = sdist.plan_owners(np.bincount(cells, minlength=8 ** level), world)
+    plan = sim.partition_plan(level, owners, world)
+    src = _upload(sim, pts)
+    dst = sim.device_alloc(max(16, count * 16) + 64)
+    try:
+        rank_counts, cell_counts = sim.partition_count(src, count, plan)
+        assert np.array_equal(cell_counts, np.bincount(cells, minlength=8 ** level))
+        want = oracle.partition_stable(pts, mn, mx, level, owners, world, rcp)
+        assert list(rank_counts) == [len(w) for w in want]
+        # all destinations in one buffer, back to back, shifted by one point to catch off-by-one stores
+        offsets = 1 + np.concatenate(([0], np.cumsum(rank_counts)[:-1])).astype(np.int64)
+        sim.memcpy_htod(dst, np.full(count * 16 + 32, 0xAB, dtype=np.uint8))
+        sim.partition_scatter(src, count, plan, [dst] * world, offsets)
+        sim.synchronize()
+        got = sim.memcpy_dtoh(dst, count * 16 + 32)
+        assert bytes(got[:16]) == b"\xab" * 16 and bytes(got[16 + count * 16:]) == b"\xab" * 16
+        assert got[16:16 + count * 16].tobytes() == np.concatenate(want).tobytes()
+        with pytest.raises(Exception):          # pass 2 without a matching pass 1
+            sim.partition_scatter(src, count, plan, [dst] * world, offsets)
+    finally:
+        sim.device_free(src)
+        sim.device_free(dst)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,level", [("terrain", 2), ("uniform", 1)])
+def test_merged_forest_built_on_the_gpu_equals_the_single_octree(sims, kind, level):
+    world = 2
+    single, ranks = sims[0], sims[1:]
+    if kind == "terrain":
+        pts, mn, mx = data.terrain(3_000_000)
+    else:
+        pts, mn, mx = data.uniform_cube(1_500_000, size=64.0, seed=11)
+    batch = 500_000
+    for s in sims:
+        s.set_box(mn, mx)
+        s.reset()
+    size = float(np.max(np.asarray(mx, np.float32) - np.asarray(mn, np.float32)))
+    rcp = single.device_rcp(size)
+    owners = sdist.plan_owners(np.bincount(oracle.partition_cells(pts, mn, mx, level, rcp), minlength=8 ** level), world)
+    plan = single.partition_plan(level, owners, world)
+    src = single.device_alloc(batch * 16)
+    stage = [single.device_alloc(batch * 16) for _ in range(world)]
+    try:
+        for f in range(0, len(pts), batch):
+            b = pts[f:f + batch]
+            single.memcpy_htod(src, b.view(np.uint8))
+            counts, _ = single.partition_count(src, len(b), plan)
+            single.partition_scatter(src, len(b), plan, stage, [0] * world)
+            single.synchronize()
+            single.insert_device(src, len(b))
+            for r in range(world):
+                if counts[r]:
+                    ranks[r].insert_device(stage[r], int(counts[r]))
+    finally:
+        single.device_free(src)
+        for p in stage:
+            single.device_free(p)
+    assert all(s.stats().dbg == 0 for s in sims)
+    assert sum(int(s.stats().numPoints) for s in ranks) == len(pts) == int(single.stats().numPoints)
+    c_single = oracle.canon_from_image(*single.download_octree())
+    c_ranks = [oracle.canon_from_image(*s.download_octree()) for s in ranks]
+    diffs = oracle.compare_merged(c_single, c_ranks, level, owners)
+    assert not diffs, "\n".join(diffs[:10])
+    # and the single octree is the oracle's
+    o = oracle.Oracle(mn, mx, rcp)
+    for f in range(0, len(pts), batch):
+        o.add_batch(pts[f:f + batch])
+    d2 = oracle.compare_canon(c_single, o.canon(), "ours vs oracle")
+    assert not d2, "\n".join(d2)

@@ -1,0 +1,157 @@
+"""Developer tool: ONE octree over G GPUs — run under torchrun, one process per GPU.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      tools/bench_merged.py [batches_per_gpu=8] [level=2] [out.json]
+
+Every rank holds its round-robin shard of a K*G-batch terrain scan in HBM. Per step each rank partitions one
+1 M-point batch by owner and the points travel to their owners ("p2p": the scatter kernel stores straight into the
+owners' receive buffers over NVLink peer memory; "nccl": local scatter + all_to_all_single), then every rank inserts
+what it received. Reported: aggregate Mpoints/s (host clock around synchronised regions, max over ranks), the split
+between exchange and insertion, and a bit-exact check: each rank rebuilds, alone, the octree of the stream it should
+have received (it regenerates all ranks' batches and partitions them locally) and compares canonical forms.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import oracle  # noqa: E402  (checker only: canonical forms of the two device octrees)
+from simlod_b200 import SimLOD, data  # noqa: E402
+from simlod_b200 import dist as sdist  # noqa: E402
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+LEVEL = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "merged.json")
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+B = bench.BATCH
+total_batches = K * world
+mine = sdist.shard_batches(total_batches, rank, world)
+batches, mn, mx = bench.generate_batches(total_batches, mine)
+sim = SimLOD(640, 360, device=local, persistent_bytes=max(6 << 30, K * world * (260 << 20)))
+sim.set_box(mn, mx)
+src = sim.device_alloc(K * B * 16)
+for i, b in enumerate(batches):
+    sim.memcpy_htod(src + i * B * 16, b.view(np.uint8))
+
+# plan: global per-cell histogram of everything -> LPT owners (same on every rank)
+plan0 = sim.partition_plan(LEVEL, np.zeros(8 ** LEVEL, np.uint8), world)
+hist = np.zeros(8 ** LEVEL, np.int64)
+for i in range(K):
+    hist += sim.partition_count(src + i * B * 16, B, plan0)[1].astype(np.int64)
+t = torch.tensor(hist, device=dev)
+dist.all_reduce(t)
+owners = sdist.plan_owners(t.cpu().numpy(), world)
+load = np.bincount(owners, weights=t.cpu().numpy(), minlength=world)
+res = {"world": world, "batches_per_gpu": K, "level": LEVEL, "points_total": K * world * B, "owner_load": [int(v) for v in load]}
+
+
+def sync_all():
+    sim.synchronize()
+    torch.cuda.synchronize()
+    dist.barrier()
+
+
+def run(mode):
+    ex = sdist.SpatialExchange(sim, LEVEL, owners, capacity_points=B, mode=mode, device=dev)
+    best = None
+    for rep in range(3):
+        sim.reset()
+        sync_all()
+        t_ex = t_ins = 0.0
+        kernel_ms = 0.0
+        t0 = time.perf_counter()
+        for i in range(K):
+            a = time.perf_counter()
+            ptr, n = ex.exchange(src + i * B * 16, B)
+            b = time.perf_counter()
+            if n:
+                kms, _ = sim.insert_device(ptr, n)
+                kernel_ms += kms
+            c = time.perf_counter()
+            t_ex += b - a
+            t_ins += c - b
+        sync_all()
+        dt = time.perf_counter() - t0
+        vals = torch.tensor([dt, t_ex, t_ins, kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dt, t_ex, t_ins, kernel_ms = [float(v) for v in vals.cpu()]
+        if best is None or dt < best["seconds"]:
+            best = {"seconds": dt, "mpoints_per_s": K * world * B / dt / 1e6, "exchange_s": t_ex, "insert_s": t_ins,
+                    "construct_kernel_ms": kernel_ms}
+    st = sim.stats()
+    tot = sdist.reduce_stats(st, dev)
+    best["numPoints_all_ranks"] = tot["numPoints"]
+    best["numPoints_this_rank"] = int(st.numPoints)
+    canon = oracle.canon_from_image(*sim.download_octree())
+    return best, canon, st
+
+
+# what this rank should have received, rebuilt locally: all ranks' batches of every step, partitioned here
+def rebuild_locally():
+    plan = sim.partition_plan(LEVEL, owners, world)
+    everyone = [sdist.shard_batches(total_batches, r, world) for r in range(world)]
+    tmp = sim.device_alloc(B * 16)
+    land = sim.device_alloc(world * B * 16)
+    scratch = [sim.device_alloc(B * 16) for _ in range(world)]          # the other ranks' buckets are thrown away
+    sim.reset()
+    for i in range(K):
+        pos = 0
+        for s in range(world):
+            pts = data.terrain(total_batches * B, everyone[s][i] * B, B)[0]
+            sim.memcpy_htod(tmp, pts.view(np.uint8))
+            counts, _ = sim.partition_count(tmp, B, plan)
+            ptrs = [land if d == rank else scratch[d] for d in range(world)]
+            offs = [pos if d == rank else 0 for d in range(world)]
+            sim.partition_scatter(tmp, B, plan, ptrs, offs)
+            sim.synchronize()
+            pos += int(counts[rank])
+        if pos:
+            sim.insert_device(land, pos)
+    st = sim.stats()
+    canon = oracle.canon_from_image(*sim.download_octree())
+    for p in [tmp, land] + scratch:
+        sim.device_free(p)
+    return canon, st
+
+
+want_canon, want_stats = rebuild_locally()
+for mode in ("nccl", "p2p"):
+    try:
+        r, canon, st = run(mode)
+        diffs = oracle.compare_canon(canon, want_canon, mode) + oracle.compare_stats(st, want_stats)
+        ok = torch.tensor([0 if diffs else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        r["octree_bit_exact_vs_local_rebuild_all_ranks"] = bool(int(ok.item()))
+        if diffs:
+            print("rank", rank, mode, "DIFFS", diffs[:5], flush=True)
+        res[mode] = r
+    except Exception as e:                      # tool only: report which transport is unavailable on this box
+        res[mode] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if rank == 0:
+        print(mode, json.dumps(res[mode]), flush=True)
+
+# baseline beside it: the batch-sharded forest (no exchange), same data
+sim.reset()
+sync_all()
+t0 = time.perf_counter()
+kms, _ = sim.insert_device(src, K * B)
+sync_all()
+dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+res["batch_sharded_forest"] = {"seconds": float(dt.item()), "mpoints_per_s": K * world * B / float(dt.item()) / 1e6}
+if rank == 0:
+    print("sharded", json.dumps(res["batch_sharded_forest"]), flush=True)
+    json.dump(res, open(out, "w"), indent=1)
+sim.close()
+dist.destroy_process_group()
