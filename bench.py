@@ -216,12 +216,12 @@ def bench_stream_file(batches, mn, mx, device):
             best = None
             for rep in range(3):
                 t0 = time.perf_counter()
-                got, kms, tms = sim.insert_simlod_file(path, loader_threads=min(32, os.cpu_count() or 8))
+                got, kms, tms = sim.insert_simlod_file(path, loader_threads=min(16, os.cpu_count() or 8))
                 dt = time.perf_counter() - t0
                 assert got == n and sim.stats().numPoints == n
                 if best is None or dt < best[0]:
                     best = (dt, kms, tms)
-            out["e2e"] = {"value": round(n / best[0] / 1e6, 1), "unit": "Mpoints/s", "how": "wall clock incl. reset, %d loader threads, file in tmpfs" % min(32, os.cpu_count() or 8),
+            out["e2e"] = {"value": round(n / best[0] / 1e6, 1), "unit": "Mpoints/s", "how": "wall clock incl. reset, %d loader threads, file in tmpfs" % min(16, os.cpu_count() or 8),
                           "device_ms": round(best[2], 3), "kernel_ms": round(best[1], 3)}
         finally:
             sim.close()

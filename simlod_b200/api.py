@@ -333,7 +333,7 @@ class SimLOD:
         self._check(self._lib.simlod_insert_device(self._ctx, int(device_ptr), int(count), C.byref(kms), C.byref(tms)))
         return kms.value, tms.value
 
-    def insert_simlod_file(self, path, loader_threads=4):
+    def insert_simlod_file(self, path, loader_threads=16):
         """reload() of the reference for one .simlod file: reset, stream the file through pinned slots with
         `loader_threads` reader threads, insert. Returns (num_points, summed kernel ms, total device ms)."""
         n, kms, tms = C.c_uint64(), C.c_float(), C.c_float()

@@ -13,9 +13,16 @@
 #include <cuda.h>
 #include <dlfcn.h>
 #include <fcntl.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <unistd.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <cstdarg>
 #include <cstdio>
@@ -97,6 +104,81 @@ struct Program {
 
 }  // namespace
 
+// Copy with non-temporal stores: the destination lines go to memory without being read or left in the cache.
+// The loaders must not fill the page-locked pool with ordinary stores (pread straight into it): each piece would
+// stay dirty in the cache of whichever core read it, and the copy engine's reads of such lines are served by
+// cross-core snoops — measured on the 2-socket host of the B200 box at ~19 GB/s against ~52 GB/s for lines that
+// are in DRAM. Each loader therefore preads into a 256 KB cache-resident staging buffer and streams it out.
+static inline void copyStreaming(char* dst, const char* src, uint64_t bytes) {      // dst, src 16-byte aligned, bytes % 16 == 0
+#if defined(__x86_64__)
+    uint64_t i = 0;
+    for (; i + 64 <= bytes; i += 64) {
+        __m128i a = _mm_load_si128((const __m128i*)(src + i)), b = _mm_load_si128((const __m128i*)(src + i + 16));
+        __m128i c = _mm_load_si128((const __m128i*)(src + i + 32)), d = _mm_load_si128((const __m128i*)(src + i + 48));
+        _mm_stream_si128((__m128i*)(dst + i), a); _mm_stream_si128((__m128i*)(dst + i + 16), b);
+        _mm_stream_si128((__m128i*)(dst + i + 32), c); _mm_stream_si128((__m128i*)(dst + i + 48), d);
+    }
+    for (; i < bytes; i += 16) _mm_stream_si128((__m128i*)(dst + i), _mm_load_si128((const __m128i*)(src + i)));
+    _mm_sfence();
+#else
+    memcpy(dst, src, bytes);
+#endif
+}
+
+// Long-lived loader threads of the file streamer (the reference keeps its loaders alive too, main.cpp:811-958).
+// Creating and retiring a thread costs 40-250 us in a process that has a CUDA context (every stack mmap/munmap
+// passes the driver's MMU notifiers), which at 32 threads was more than the whole read of a 256 MB file.
+struct LoaderPool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cvStart, cvDone;
+    std::function<void(int)> job;
+    std::vector<char*> bounce;        // one cache-resident staging buffer per worker (BOUNCE_BYTES)
+    static constexpr size_t BOUNCE_BYTES = 256 << 10;
+    uint64_t generation = 0;
+    int wanted = 0, running = 0;
+    bool quit = false;
+
+    void worker(int idx) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void(int)> fn;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cvStart.wait(lk, [&] { return quit || generation != seen; });
+                if (quit) return;
+                seen = generation;
+                if (idx >= wanted) continue;
+                fn = job;
+            }
+            fn(idx);
+            std::lock_guard<std::mutex> lk(m);
+            if (--running == 0) cvDone.notify_all();
+        }
+    }
+    // start n workers on fn; returns at once. fn must stay valid until wait() returns.
+    void run(int n, std::function<void(int)> fn) {
+        while ((int)threads.size() < n) {
+            int idx = (int)threads.size();
+            bounce.push_back((char*)aligned_alloc(64, BOUNCE_BYTES));
+            threads.emplace_back([this, idx] { worker(idx); });
+        }
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(fn); wanted = n; running = n; generation++;
+        cvStart.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cvDone.wait(lk, [&] { return running == 0; });
+    }
+    ~LoaderPool() {
+        { std::lock_guard<std::mutex> lk(m); quit = true; }
+        cvStart.notify_all();
+        for (auto& t : threads) t.join();
+        for (char* b : bounce) free(b);
+    }
+};
+
 struct SimlodContext {
     CUdevice device = 0;
     CUcontext primary = nullptr;
@@ -121,6 +203,7 @@ struct SimlodContext {
     CUfunction fnLas = nullptr;
     CUdeviceptr lasStaging = 0;        // raw LAS records of the batch being decoded
     void* pinnedPool = nullptr;        // POOL_SLOTS x 16 MB page-locked staging slots of the file streamer
+    LoaderPool* loaderPool = nullptr;
     CUevent evPool[32] = {};           // H2D copy out of pool slot i has been enqueued and completed
     CUfunction fnRcp = nullptr, fnFill = nullptr;
     uint32_t uploaded = 0;             // batches published to the device
@@ -359,6 +442,7 @@ void simlod_destroy(SimlodContext* ctx) {
         if (ctx->partScratch) D(cuMemFree)(ctx->partScratch);
         if (ctx->lasModule) D(cuModuleUnload)(ctx->lasModule);
         if (ctx->lasStaging) D(cuMemFree)(ctx->lasStaging);
+        delete ctx->loaderPool;          // joins the loader threads
         if (ctx->pinnedPool) D(cuMemFreeHost)(ctx->pinnedPool);
         for (int i = 0; i < 32; i++) if (ctx->evPool[i]) D(cuEventDestroy)(ctx->evPool[i]);
         if (ctx->evStart) D(cuEventDestroy)(ctx->evStart);
@@ -586,40 +670,51 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
     // of work is a 1 MB piece of a batch, handed out in file order, so that all threads read the batch the uploader
     // needs next (the reference reads one whole batch per thread, main.cpp:811-958: every batch then arrives late).
     constexpr uint64_t PIECE_POINTS = 65536, PIECES = (SLOT_POINTS + PIECE_POINTS - 1) / PIECE_POINTS;
+    const bool trace = getenv("SIMLOD_STREAM_TRACE") != nullptr;          // developer aid: host timeline to stderr
+    const auto tBegin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tBegin).count(); };
+    double tSpawned = 0, tFirst = 0, tAllLoaded = 0, tLastUpload = 0;
     std::vector<std::atomic<int>> loaded(numBatches);          // pieces of batch k that have arrived
     for (auto& l : loaded) l.store(0);
     std::atomic<int64_t> copiesDone{0};           // batches whose host->device copy has completed
     std::atomic<uint64_t> nextPiece{0};
     std::atomic<bool> abort{false};
     const int nThreads = std::max(1, std::min(loader_threads, 64));
-    std::vector<std::thread> loaders;
     const int fd = open(path, O_RDONLY);
     if (fd < 0) return fail(SIMLOD_ERR_INVALID, "cannot open %s", path);
-    for (int t = 0; t < nThreads; t++) {
-        loaders.emplace_back([&]() {
-            for (;;) {
-                const uint64_t item = nextPiece.fetch_add(1);
-                const uint64_t k = item / PIECES, piece = item % PIECES;
-                if (k >= numBatches || abort.load()) break;
-                while (copiesDone.load() + POOL_SLOTS <= (int64_t)k && !abort.load()) std::this_thread::yield();
-                const uint64_t inBatch = std::min<uint64_t>(SLOT_POINTS, numPoints - k * SLOT_POINTS);
-                const uint64_t p0 = piece * PIECE_POINTS;
-                if (p0 < inBatch) {
-                    uint64_t bytes = std::min<uint64_t>(PIECE_POINTS, inBatch - p0) * 16;
-                    char* dst = (char*)ctx->pinnedPool + (k % POOL_SLOTS) * slotBytes + p0 * 16;
-                    off_t at = (off_t)(24 + (k * SLOT_POINTS + p0) * 16);
-                    while (bytes) {
-                        ssize_t r = pread(fd, dst, bytes, at);
+    if (!ctx->loaderPool) ctx->loaderPool = new LoaderPool();
+    LoaderPool* pool = ctx->loaderPool;
+    pool->run(nThreads, [&, pool](int worker) {
+        for (;;) {
+            const uint64_t item = nextPiece.fetch_add(1);
+            const uint64_t k = item / PIECES, piece = item % PIECES;
+            if (k >= numBatches || abort.load()) break;
+            while (copiesDone.load() + POOL_SLOTS <= (int64_t)k && !abort.load()) std::this_thread::yield();
+            const uint64_t inBatch = std::min<uint64_t>(SLOT_POINTS, numPoints - k * SLOT_POINTS);
+            const uint64_t p0 = piece * PIECE_POINTS;
+            if (p0 < inBatch) {
+                uint64_t bytes = std::min<uint64_t>(PIECE_POINTS, inBatch - p0) * 16;
+                char* dst = (char*)ctx->pinnedPool + (k % POOL_SLOTS) * slotBytes + p0 * 16;
+                off_t at = (off_t)(24 + (k * SLOT_POINTS + p0) * 16);
+                char* stage = pool->bounce[worker];
+                while (bytes) {
+                    uint64_t want = std::min<uint64_t>(bytes, LoaderPool::BOUNCE_BYTES), have = 0;
+                    while (have < want) {
+                        ssize_t r = pread(fd, stage + have, want - have, at + (off_t)have);
                         if (r <= 0) { abort.store(true); break; }
-                        dst += r; at += r; bytes -= (uint64_t)r;
+                        have += (uint64_t)r;
                     }
+                    if (have < want) break;
+                    copyStreaming(dst, stage, want);
+                    dst += want; at += (off_t)want; bytes -= want;
                 }
-                loaded[k].fetch_add(1);
             }
-        });
-    }
+            loaded[k].fetch_add(1);
+        }
+    });
     const int allPieces = (int)PIECES;
-    auto joinAll = [&]() { abort.store(true); for (auto& th : loaders) th.join(); close(fd); };
+    tSpawned = since();
+    auto joinAll = [&]() { abort.store(true); ctx->loaderPool->wait(); close(fd); };
 
     float kernelTotal = 0.0f;
     int pairInUse[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -646,6 +741,8 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
     for (uint64_t k = 0; k < numBatches; k++) {
         while (loaded[k].load() < allPieces && !abort.load()) std::this_thread::yield();
         if (abort.load()) { joinAll(); return fail(SIMLOD_ERR_INVALID, "read error in %s", path); }
+        if (k == 0) tFirst = since();
+        if (k + 1 == numBatches) tAllLoaded = since();
         if (ctx->uploaded - ctx->processed >= RING_SLOTS - 1) { rc = readStats(ctx); if (rc) { joinAll(); return rc; } }   // back-pressure (main.cpp:1012)
         uint64_t first = k * SLOT_POINTS;
         uint32_t n = (uint32_t)std::min<uint64_t>(SLOT_POINTS, numPoints - first);
@@ -663,8 +760,10 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
             while (copiesDone.load() < copiesEnqueued && D(cuEventQuery)(ctx->evPool[copiesDone.load() % POOL_SLOTS]) == CUDA_SUCCESS) copiesDone.fetch_add(1);
         }
     }
-    for (auto& th : loaders) th.join();
+    tLastUpload = since();
+    ctx->loaderPool->wait();
     close(fd);
+    const double tJoined = since();
     // drain: launches until every batch has been consumed
     const uint32_t target = firstUploaded + (uint32_t)numBatches;
     rc = readStats(ctx); if (rc) return rc;
@@ -678,6 +777,8 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
     for (int k = 0; k < 8; k++) if (pairInUse[k]) { float ms = 0.0f; D(cuEventElapsedTime)(&ms, ctx->evBurst[k][0], ctx->evBurst[k][1]); kernelTotal += ms; }
     if (kernel_ms) *kernel_ms = kernelTotal;
     if (total_ms) CU(D(cuEventElapsedTime)(total_ms, ctx->evTotalStart, ctx->evTotalEnd));
+    if (trace) fprintf(stderr, "[simlod stream] %llu batches, %d threads: started %.2f ms, first batch %.2f, all loaded %.2f, last upload enqueued %.2f, loaders idle %.2f, done %.2f\n",
+                       (unsigned long long)numBatches, nThreads, tSpawned, tFirst, tAllLoaded, tLastUpload, tJoined, since());
     return SIMLOD_OK;
 }
 
