@@ -162,12 +162,18 @@ typedef struct SimlodPartitionPlan {
 // (optional, [8^level]) receives the per-cell histogram used to plan owners. Synchronous.
 int simlod_partition_count(SimlodContext* ctx, uint64_t device_points, uint32_t count, const SimlodPartitionPlan* plan,
                            uint64_t* rank_counts, uint64_t* cell_counts);
-// pass 2 (after pass 1 with the same points / count / plan): stable scatter. The k-th point of the batch that
-// belongs to rank d is stored at ((SimlodPoint*)dest_ptrs[d])[dest_offsets[d] + k]; dest_ptrs may be local device
-// memory or peer memory mapped over NVLink (the store stream IS the exchange). Asynchronous on the launch
-// stream: simlod_synchronize() before another rank may read.
+// pass 2 (after pass 1 on the same points / count; up to 64 counted batches may be outstanding): stable scatter.
+// The k-th point of the batch that belongs to rank d is stored at ((SimlodPoint*)dest_ptrs[d])[dest_offsets[d] + k];
+// dest_ptrs may be local device memory or peer memory mapped over NVLink (the store stream IS the exchange).
+// signal_ptrs (optional, [num_ranks]): this sender's 32-bit flag word in every destination; once all stores of
+// the launch are visible system-wide the kernel releases signal_value into each of them. Asynchronous on the
+// launch stream.
 int simlod_partition_scatter(SimlodContext* ctx, uint64_t device_points, uint32_t count, const SimlodPartitionPlan* plan,
-                             const uint64_t* dest_ptrs, const uint64_t* dest_offsets);
+                             const uint64_t* dest_ptrs, const uint64_t* dest_offsets, const uint64_t* signal_ptrs, uint32_t signal_value);
+// receiving side: returns when every sender's flag in local_flags[0..num_ranks) has reached `value` (wrap-around
+// compare), i.e. all buckets of that step have landed here; everything enqueued on this context before the call
+// has completed too. SIMLOD_ERR_CUDA naming the silent rank after timeout_ms (0 = 10 s).
+int simlod_partition_wait(SimlodContext* ctx, uint64_t local_flags, uint32_t num_ranks, uint32_t value, uint32_t timeout_ms);
 
 #ifdef __cplusplus
 }

@@ -115,7 +115,7 @@ EXPORTS = [
     "simlod_read_framebuffer", "simlod_read_surface", "simlod_get_buffers", "simlod_memcpy_dtoh",
     "simlod_memcpy_htod", "simlod_host_alloc", "simlod_host_free", "simlod_device_alloc", "simlod_device_free",
     "simlod_get_launch_info", "simlod_device_rcp", "simlod_synchronize", "simlod_flush_l2",
-    "simlod_partition_count", "simlod_partition_scatter",
+    "simlod_partition_count", "simlod_partition_scatter", "simlod_partition_wait",
 ]
 
 _lib = None
@@ -162,7 +162,8 @@ def load_library():
         "simlod_flush_l2": [vp],
         "simlod_synchronize": [vp],
         "simlod_partition_count": [vp, u64, u32, C.POINTER(PartitionPlan), C.POINTER(u64), C.POINTER(u64)],
-        "simlod_partition_scatter": [vp, u64, u32, C.POINTER(PartitionPlan), C.POINTER(u64), C.POINTER(u64)],
+        "simlod_partition_scatter": [vp, u64, u32, C.POINTER(PartitionPlan), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), u32],
+        "simlod_partition_wait": [vp, u64, u32, u32, u32],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -450,7 +451,11 @@ class SimLOD:
         self._check(self._lib.simlod_partition_count(self._ctx, int(device_ptr), int(count), C.byref(plan), ranks, cells))
         return np.array(ranks[:], dtype=np.uint64), np.array(cells[:], dtype=np.uint64)
 
-    def partition_scatter(self, device_ptr, count, plan, dest_ptrs, dest_offsets):
+    def partition_scatter(self, device_ptr, count, plan, dest_ptrs, dest_offsets, signal_ptrs=None, signal_value=0):
         ptrs = (C.c_uint64 * plan.num_ranks)(*[int(p) for p in dest_ptrs])
         offs = (C.c_uint64 * plan.num_ranks)(*[int(o) for o in dest_offsets])
-        self._check(self._lib.simlod_partition_scatter(self._ctx, int(device_ptr), int(count), C.byref(plan), ptrs, offs))
+        sig = (C.c_uint64 * plan.num_ranks)(*[int(p) for p in signal_ptrs]) if signal_ptrs is not None else None
+        self._check(self._lib.simlod_partition_scatter(self._ctx, int(device_ptr), int(count), C.byref(plan), ptrs, offs, sig, int(signal_value)))
+
+    def partition_wait(self, local_flags_ptr, num_ranks, value, timeout_ms=0):
+        self._check(self._lib.simlod_partition_wait(self._ctx, int(local_flags_ptr), int(num_ranks), int(value), int(timeout_ms)))

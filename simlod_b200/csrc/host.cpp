@@ -197,9 +197,10 @@ struct SimlodContext {
     Program programs[3];
     CUmodule utilModule = nullptr, lasModule = nullptr, partitionModule = nullptr;
     CUfunction fnPartCount = nullptr, fnPartScan = nullptr, fnPartScatter = nullptr;
-    CUdeviceptr partScratch = 0;       // blockHist | blockBase | totals | cellCounts of the spatial exchange
-    uint32_t partCount = 0xffffffffu;  // arguments of the last simlod_partition_count (pass 2 must match)
-    uint64_t partPoints = 0;
+    CUfunction fnPartWait = nullptr;
+    CUdeviceptr partScratch = 0;       // spatial exchange: PART_SLOTS x (blockHist | blockBase | totals | cellCounts), then blocksDone, timedOut
+    struct PartSlot { uint64_t points = 0; uint32_t count = 0; bool valid = false; } partSlots[64];   // counted batches awaiting their scatter
+    uint32_t partNextSlot = 0;
     CUfunction fnLas = nullptr;
     CUdeviceptr lasStaging = 0;        // raw LAS records of the batch being decoded
     void* pinnedPool = nullptr;        // POOL_SLOTS x 16 MB page-locked staging slots of the file streamer
@@ -369,6 +370,7 @@ int simlod_create(const SimlodConfig* config, SimlodContext** out) {
     CU(D(cuModuleGetFunction)(&ctx->fnPartCount, ctx->partitionModule, "simlod_partition_count"));
     CU(D(cuModuleGetFunction)(&ctx->fnPartScan, ctx->partitionModule, "simlod_partition_scan"));
     CU(D(cuModuleGetFunction)(&ctx->fnPartScatter, ctx->partitionModule, "simlod_partition_scatter"));
+    CU(D(cuModuleGetFunction)(&ctx->fnPartWait, ctx->partitionModule, "simlod_partition_wait"));
 
     // buffers (main.cpp:552-586)
     SimlodBuffers& b = ctx->buf;
@@ -909,13 +911,16 @@ int simlod_flush_l2(SimlodContext* ctx) {
 
 // ---- spatial exchange; kernels in partition.cu ----------------------------------------
 namespace {
-constexpr uint32_t PART_MAX_RANKS = 8, PART_MAX_CELLS = 512, PART_BLOCK = 256;
+constexpr uint32_t PART_MAX_RANKS = 8, PART_MAX_CELLS = 512, PART_BLOCK = 256, PART_SLOTS = 64;
 struct PartitionParams {             // mirrors partition.cu
     float minx, miny, minz, size;
     uint32_t level, numRanks, count, perBlock;
     uint8_t owner[PART_MAX_CELLS];
 };
-struct ScatterTargets { uint64_t ptr[PART_MAX_RANKS]; uint64_t offset[PART_MAX_RANKS]; };
+struct ScatterTargets { uint64_t ptr[PART_MAX_RANKS]; uint64_t offset[PART_MAX_RANKS]; uint64_t signal[PART_MAX_RANKS]; uint32_t signalValue, pad; };
+
+// per counted batch: blockHist[blocks][8] | blockBase[blocks][8] | totals[8] | cellCounts[512]
+uint64_t partSlotBytes(uint32_t blocks) { return (uint64_t)blocks * PART_MAX_RANKS * 4 * 2 + PART_MAX_RANKS * 4 + PART_MAX_CELLS * 4; }
 
 int partitionSetup(SimlodContext* ctx, uint32_t count, const SimlodPartitionPlan* plan, PartitionParams* p, uint32_t* blocks) {
     if (!plan) return fail(SIMLOD_ERR_INVALID, "null plan");
@@ -934,7 +939,11 @@ int partitionSetup(SimlodContext* ctx, uint32_t count, const SimlodPartitionPlan
     p->perBlock = std::max(PART_BLOCK, (per + PART_BLOCK - 1) / PART_BLOCK * PART_BLOCK);
     memset(p->owner, 0, sizeof(p->owner));
     memcpy(p->owner, plan->owner, numCells);
-    if (!ctx->partScratch) CU(D(cuMemAlloc)(&ctx->partScratch, (size_t)*blocks * PART_MAX_RANKS * 4 * 2 + PART_MAX_RANKS * 4 + PART_MAX_CELLS * 4));
+    if (!ctx->partScratch) {
+        const size_t bytes = (size_t)(partSlotBytes(*blocks) * PART_SLOTS + 16);
+        CU(D(cuMemAlloc)(&ctx->partScratch, bytes));
+        CU(D(cuMemsetD8)(ctx->partScratch, 0, bytes));
+    }
     return SIMLOD_OK;
 }
 }  // namespace
@@ -946,8 +955,13 @@ int simlod_partition_count(SimlodContext* ctx, uint64_t device_points, uint32_t 
     if (!device_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
     PartitionParams p; uint32_t blocks = 0;
     rc = partitionSetup(ctx, count, plan, &p, &blocks); if (rc) return rc;
+    // a batch may be counted well ahead of its scatter (planning a window of steps): its block bases stay in a slot
+    uint32_t slot = PART_SLOTS;
+    for (uint32_t i = 0; i < PART_SLOTS; i++)
+        if (ctx->partSlots[i].valid && ctx->partSlots[i].points == device_points && ctx->partSlots[i].count == count) slot = i;
+    if (slot == PART_SLOTS) { slot = ctx->partNextSlot; ctx->partNextSlot = (ctx->partNextSlot + 1) % PART_SLOTS; }
     CUdeviceptr pts = (CUdeviceptr)device_points;
-    CUdeviceptr blockHist = ctx->partScratch, blockBase = blockHist + (size_t)blocks * PART_MAX_RANKS * 4,
+    CUdeviceptr blockHist = ctx->partScratch + partSlotBytes(blocks) * slot, blockBase = blockHist + (size_t)blocks * PART_MAX_RANKS * 4,
                 totals = blockBase + (size_t)blocks * PART_MAX_RANKS * 4, cells = totals + PART_MAX_RANKS * 4;
     CU(D(cuMemsetD8Async)(cells, 0, PART_MAX_CELLS * 4, ctx->streamMain));
     { void* args[] = {&p, &pts, &blockHist, &cells};
@@ -960,16 +974,18 @@ int simlod_partition_count(SimlodContext* ctx, uint64_t device_points, uint32_t 
     CU(D(cuStreamSynchronize)(ctx->streamMain));
     for (uint32_t d = 0; d < plan->num_ranks; d++) rank_counts[d] = host[d];
     if (cell_counts) for (uint32_t c = 0; c < (1u << (3 * plan->level)); c++) cell_counts[c] = host[PART_MAX_RANKS + c];
-    ctx->partCount = count; ctx->partPoints = device_points;
+    ctx->partSlots[slot].points = device_points; ctx->partSlots[slot].count = count; ctx->partSlots[slot].valid = true;
     return SIMLOD_OK;
 }
 
 int simlod_partition_scatter(SimlodContext* ctx, uint64_t device_points, uint32_t count, const SimlodPartitionPlan* plan,
-                             const uint64_t* dest_ptrs, const uint64_t* dest_offsets) {
+                             const uint64_t* dest_ptrs, const uint64_t* dest_offsets, const uint64_t* signal_ptrs, uint32_t signal_value) {
     int rc = setCurrent(ctx); if (rc) return rc;
     if (!dest_ptrs || !dest_offsets) return fail(SIMLOD_ERR_INVALID, "null argument");
-    if (ctx->partCount != count || ctx->partPoints != device_points)
-        return fail(SIMLOD_ERR_INVALID, "simlod_partition_scatter must follow simlod_partition_count on the same batch");
+    uint32_t slot = PART_SLOTS;
+    for (uint32_t i = 0; i < PART_SLOTS; i++)
+        if (ctx->partSlots[i].valid && ctx->partSlots[i].points == device_points && ctx->partSlots[i].count == count) slot = i;
+    if (slot == PART_SLOTS) return fail(SIMLOD_ERR_INVALID, "simlod_partition_scatter must follow simlod_partition_count on the same batch");
     PartitionParams p; uint32_t blocks = 0;
     rc = partitionSetup(ctx, count, plan, &p, &blocks); if (rc) return rc;
     ScatterTargets t;
@@ -977,13 +993,39 @@ int simlod_partition_scatter(SimlodContext* ctx, uint64_t device_points, uint32_
     for (uint32_t d = 0; d < plan->num_ranks; d++) {
         if (!dest_ptrs[d]) return fail(SIMLOD_ERR_INVALID, "null destination for rank %u", d);
         t.ptr[d] = dest_ptrs[d]; t.offset[d] = dest_offsets[d];
+        if (signal_ptrs) {
+            if (!signal_ptrs[d]) return fail(SIMLOD_ERR_INVALID, "null signal word for rank %u", d);
+            t.signal[d] = signal_ptrs[d];
+        }
     }
+    t.signalValue = signal_value;
     CUdeviceptr pts = (CUdeviceptr)device_points;
-    CUdeviceptr blockBase = ctx->partScratch + (size_t)blocks * PART_MAX_RANKS * 4;
-    void* args[] = {&p, &t, &pts, &blockBase};
+    CUdeviceptr blockBase = ctx->partScratch + partSlotBytes(blocks) * slot + (size_t)blocks * PART_MAX_RANKS * 4;
+    CUdeviceptr blocksDone = ctx->partScratch + partSlotBytes(blocks) * PART_SLOTS;
+    void* args[] = {&p, &t, &pts, &blockBase, &blocksDone};
     CU(D(cuLaunchKernel)(ctx->fnPartScatter, blocks, 1, 1, PART_BLOCK, 1, 1, 0, ctx->streamMain, args, nullptr));
     ctx->launches++;
-    ctx->partCount = 0xffffffffu;
+    ctx->partSlots[slot].valid = false;
+    return SIMLOD_OK;
+}
+
+int simlod_partition_wait(SimlodContext* ctx, uint64_t local_flags, uint32_t num_ranks, uint32_t value, uint32_t timeout_ms) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!local_flags || num_ranks < 1 || num_ranks > PART_MAX_RANKS) return fail(SIMLOD_ERR_INVALID, "bad flags / rank count");
+    if (!ctx->partScratch) return fail(SIMLOD_ERR_INVALID, "simlod_partition_wait before any simlod_partition_count");
+    CUdeviceptr flags = (CUdeviceptr)local_flags;
+    CUdeviceptr timedOut = ctx->partScratch + partSlotBytes((uint32_t)ctx->numSMs * 4) * PART_SLOTS + 4;
+    uint64_t cycles = (uint64_t)(timeout_ms ? timeout_ms : 10000) * 2000000ull;          // SM clock ~2 GHz
+    void* args[] = {&flags, &num_ranks, &value, &cycles, &timedOut};
+    CU(D(cuLaunchKernel)(ctx->fnPartWait, 1, 1, 1, 32, 1, 1, 0, ctx->streamMain, args, nullptr));
+    ctx->launches++;
+    uint32_t host = 0;
+    CU(D(cuMemcpyDtoHAsync)(&host, timedOut, 4, ctx->streamMain));
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
+    if (host) {
+        CU(D(cuMemsetD8)(timedOut, 0, 4));
+        return fail(SIMLOD_ERR_CUDA, "spatial exchange: rank %u did not signal step %u within %u ms", host - 1, value, timeout_ms ? timeout_ms : 10000);
+    }
     return SIMLOD_OK;
 }
 

@@ -14,7 +14,9 @@
 //   simlod_partition_count    per-block histogram over destination ranks (+ global per-cell histogram)
 //   simlod_partition_scan     exclusive scan of the block histograms per destination, totals
 //   simlod_partition_scatter  stable scatter: dst[d][offset[d] + rank of the point among the batch's
-//                             points for d] = point      (16-byte stores, local or peer)
+//                             points for d] = point      (16-byte stores, local or peer); the last block to
+//                             finish then releases a flag in every destination ("my bucket has landed")
+//   simlod_partition_wait     acquire side: spins until every sender's flag has reached the step's value
 #include <stdint.h>
 #include "fpmath.cuh"
 
@@ -35,6 +37,9 @@ struct PartitionParams {
 struct ScatterTargets {
     uint64_t ptr[MAX_RANKS];                // destination buffers (device addresses, local or peer)
     uint64_t offset[MAX_RANKS];             // first point slot of THIS sender in each destination
+    uint64_t signal[MAX_RANKS];             // this sender's flag word in each destination (0 = no signalling)
+    uint32_t signalValue;
+    uint32_t pad;
 };
 
 __device__ __forceinline__ uint32_t cellOf(const PartitionParams& p, float rcpSize, uint4 pt) {
@@ -104,7 +109,7 @@ simlod_partition_scan(const uint32_t* __restrict__ blockHist, uint32_t numBlocks
 
 extern "C" __global__ void __launch_bounds__(BLOCK)
 simlod_partition_scatter(const PartitionParams p, const ScatterTargets t, const uint4* __restrict__ points,
-                         const uint32_t* __restrict__ blockBase) {
+                         const uint32_t* __restrict__ blockBase, uint32_t* __restrict__ blocksDone) {
     __shared__ uint32_t sh_warpBuf[2][WARPS][MAX_RANKS];   // points of warp w for destination d in the current 256-point group
                                                             // (two copies by iteration parity: zeroing never races the previous readers)
     __shared__ uint32_t sh_running[MAX_RANKS];          // points of this block already placed per destination
@@ -140,5 +145,35 @@ simlod_partition_scatter(const PartitionParams p, const ScatterTargets t, const 
             sh_running[threadIdx.x] += add;
         }
         // the next iteration's first __syncthreads orders this update before its readers
+    }
+    // ---- "my buckets have landed": every thread orders its (possibly remote) stores at system scope, the last block
+    // to arrive releases this sender's flag in every destination (the threadfence-reduction pattern, system scope)
+    if (t.signal[0] != 0) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t arrived = atomicAdd(blocksDone, 1u);
+            if (arrived == gridDim.x - 1u) {
+                __threadfence_system();
+                for (uint32_t d = 0; d < p.numRanks; d++)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(t.signal[d]), "r"(t.signalValue) : "memory");
+                *blocksDone = 0;
+            }
+        }
+    }
+}
+
+// acquire side, one thread per sender: flags[s] >= value  <=>  sender s's stores of this step are visible here.
+// Gives up after `timeoutCycles` SM clocks (a peer died) and reports it instead of hanging the stream.
+extern "C" __global__ void simlod_partition_wait(const uint32_t* flags, uint32_t numRanks, uint32_t value, uint64_t timeoutCycles,
+                                                 uint32_t* __restrict__ timedOut) {
+    if (threadIdx.x >= numRanks) return;
+    const long long start = clock64();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+        if ((int32_t)(v - value) >= 0) return;
+        if ((uint64_t)(clock64() - start) > timeoutCycles) { atomicExch(timedOut, 1u + threadIdx.x); return; }
+        __nanosleep(200);
     }
 }

@@ -151,16 +151,21 @@ def all_to_all_points(send, recv, matrix, rank):
 class SpatialExchange:
     """Per-rank driver of the exchange on the GPUs (one process per GPU; needs CUDA, NCCL and the C-ABI library).
 
-    mode "p2p":  receive buffers are torch symmetric memory (peer-mapped over NVLink); the scatter kernel of every
-                 rank stores straight into the owners' buffers, NCCL only carries the counts and the barrier.
-    mode "nccl": scatter into a local staging buffer, then all_to_all_single.
-    Receive buffers are double-buffered by step parity, so one barrier per step also protects the buffer the
-    peers overwrite two steps later."""
+    mode "p2p":  receive buffers are torch symmetric memory (peer-mapped over NVLink). ONE kernel per step
+                 partitions the batch, stores every point straight into its owner's buffer and, when its last
+                 store is visible system-wide, releases this sender's flag in every receiver; the receiver's
+                 wait kernel acquires the G flags. NCCL carries only the counts (8*G bytes per step, or one
+                 all_gather for a whole window of steps after `prepare`).
+    mode "nccl": scatter into a local staging buffer, then all_to_all_single (the baseline).
+    Receive buffers are double-buffered by step parity: a sender reaches step k+2 only after it has seen every
+    receiver's flag of step k+1, which a receiver releases after it has consumed step k."""
 
-    def __init__(self, sim, level, owners, capacity_points=1_000_000, mode="p2p", device=None):
+    FLAG_BYTES = 4096
+
+    def __init__(self, sim, level, owners, capacity_points=1_000_000, mode="p2p", device=None, timeout_ms=10000):
         import torch
         dist = _dist()
-        self.sim, self.mode = sim, mode
+        self.sim, self.mode, self.timeout_ms = sim, mode, timeout_ms
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.plan = sim.partition_plan(level, owners, self.world)
@@ -168,12 +173,18 @@ class SpatialExchange:
         half = self.world * self.capacity * 16                 # worst case: every sender's whole batch lands here
         self.half_bytes = half
         self.step = 0
+        self.prepared = {}                                     # (device_ptr, count) -> G x G matrix of that step
         if mode == "p2p":
             import torch.distributed._symmetric_memory as symm_mem
-            self.recv = symm_mem.empty(2 * half, dtype=torch.uint8, device=self.device)
+            self.recv = symm_mem.empty(2 * half + self.FLAG_BYTES, dtype=torch.uint8, device=self.device)
             self.handle = symm_mem.rendezvous(self.recv, dist.group.WORLD)
             self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
             assert self.peer_ptrs[self.rank] == self.recv.data_ptr()
+            self.recv[2 * half:].zero_()                       # flag words: [sender] u32, monotonically increasing step numbers
+            torch.cuda.synchronize()
+            dist.barrier()
+            self.flag_ptrs = [p + 2 * half + 4 * self.rank for p in self.peer_ptrs]     # my word in every receiver
+            self.local_flags = self.recv.data_ptr() + 2 * half
         elif mode == "nccl":
             self.recv = torch.empty(2 * half, dtype=torch.uint8, device=self.device)
             self.send = torch.empty(self.capacity * 16, dtype=torch.uint8, device=self.device)
@@ -189,27 +200,40 @@ class SpatialExchange:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.cpu().numpy()
 
+    def prepare(self, batches):
+        """Count a window of upcoming batches [(device_ptr, count)] (at most 64, the same number on every rank) and
+        gather all their counts with ONE all_gather, so that the steps themselves need no collective."""
+        import torch
+        dist = _dist()
+        mine = np.stack([self.sim.partition_count(p, c, self.plan)[0].astype(np.int64) for p, c in batches])      # [K][G]
+        t = torch.from_numpy(mine).to(self.device)
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(out, t)
+        allc = out.cpu().numpy()                               # [sender][K][G]
+        for k, (p, c) in enumerate(batches):
+            self.prepared[(int(p), int(c))] = allc[:, k, :]
+
     def exchange(self, device_ptr, count):
         """Send the `count` points at device_ptr to their owners. Returns (device address, number of points) of what
         this rank received, valid until the step after next."""
         import torch
-        dist = _dist()
         if count > self.capacity:
             raise ValueError("batch of %d points exceeds the exchange capacity %d" % (count, self.capacity))
-        mine, _ = self.sim.partition_count(device_ptr, count, self.plan)
-        matrix = gather_counts(mine, self.device)
+        matrix = self.prepared.pop((int(device_ptr), int(count)), None)
+        if matrix is None:
+            mine, _ = self.sim.partition_count(device_ptr, count, self.plan)
+            matrix = gather_counts(mine, self.device)
         send_offsets, landing, recv_count = exchange_layout(matrix, self.rank)
         base = (self.step & 1) * self.half_bytes
+        self.step += 1
         if self.mode == "p2p":
-            self.sim.partition_scatter(device_ptr, count, self.plan, [p + base for p in self.peer_ptrs], landing)
-            self.sim.synchronize()                       # my stores have left
-            self.handle.barrier()                        # everyone's stores have landed
-            torch.cuda.current_stream().synchronize()
+            self.sim.partition_scatter(device_ptr, count, self.plan, [p + base for p in self.peer_ptrs], landing,
+                                       signal_ptrs=self.flag_ptrs, signal_value=self.step)
+            self.sim.partition_wait(self.local_flags, self.world, self.step, self.timeout_ms)
         else:
             self.sim.partition_scatter(device_ptr, count, self.plan, [self.send.data_ptr()] * self.world, send_offsets)
             self.sim.synchronize()
             got = all_to_all_points(self.send, self.recv[base:base + self.half_bytes], matrix, self.rank)
             torch.cuda.current_stream().synchronize()
             assert got == recv_count
-        self.step += 1
         return self.recv.data_ptr() + base, recv_count

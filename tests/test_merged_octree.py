@@ -198,8 +198,15 @@ def test_partition_kernels_match_the_oracle(sims, kind, count, level, world):
         # all destinations in one buffer, back to back, shifted by one point to catch off-by-one stores
         offsets = 1 + np.concatenate(([0], np.cumsum(rank_counts)[:-1])).astype(np.int64)
         sim.memcpy_htod(dst, np.full(count * 16 + 32, 0xAB, dtype=np.uint8))
-        sim.partition_scatter(src, count, plan, [dst] * world, offsets)
-        sim.synchronize()
+        # the kernel releases a flag per destination once its stores are visible; the wait acquires them
+        flags = sim.device_alloc(64)
+        sim.memcpy_htod(flags, np.zeros(16, dtype=np.uint32))
+        sim.partition_scatter(src, count, plan, [dst] * world, offsets, signal_ptrs=[flags + 4 * d for d in range(world)], signal_value=7)
+        sim.partition_wait(flags, world, 7)
+        assert list(sim.memcpy_dtoh(flags, 32).view(np.uint32)[:world]) == [7] * world
+        with pytest.raises(Exception, match="did not signal"):
+            sim.partition_wait(flags, world, 8, timeout_ms=20)
+        sim.device_free(flags)
         got = sim.memcpy_dtoh(dst, count * 16 + 32)
         assert bytes(got[:16]) == b"\xab" * 16 and bytes(got[16 + count * 16:]) == b"\xab" * 16
         assert got[16:16 + count * 16].tobytes() == np.concatenate(want).tobytes()

@@ -71,6 +71,9 @@ def run(mode):
         t_ex = t_ins = 0.0
         kernel_ms = 0.0
         t0 = time.perf_counter()
+        for w0 in range(0, K, 32):                   # plan a window of steps: their counts travel in one all_gather
+            ex.prepare([(src + i * B * 16, B) for i in range(w0, min(K, w0 + 32))])
+        t_prep = time.perf_counter() - t0
         for i in range(K):
             a = time.perf_counter()
             ptr, n = ex.exchange(src + i * B * 16, B)
@@ -83,11 +86,11 @@ def run(mode):
             t_ins += c - b
         sync_all()
         dt = time.perf_counter() - t0
-        vals = torch.tensor([dt, t_ex, t_ins, kernel_ms], dtype=torch.float64, device=dev)
+        vals = torch.tensor([dt, t_ex, t_ins, kernel_ms, t_prep], dtype=torch.float64, device=dev)
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dt, t_ex, t_ins, kernel_ms = [float(v) for v in vals.cpu()]
+        dt, t_ex, t_ins, kernel_ms, t_prep = [float(v) for v in vals.cpu()]
         if best is None or dt < best["seconds"]:
-            best = {"seconds": dt, "mpoints_per_s": K * world * B / dt / 1e6, "exchange_s": t_ex, "insert_s": t_ins,
+            best = {"seconds": dt, "mpoints_per_s": K * world * B / dt / 1e6, "plan_window_s": t_prep, "exchange_s": t_ex, "insert_s": t_ins,
                     "construct_kernel_ms": kernel_ms}
     st = sim.stats()
     tot = sdist.reduce_stats(st, dev)
