@@ -175,6 +175,20 @@ int simlod_partition_scatter(SimlodContext* ctx, uint64_t device_points, uint32_
 // has completed too. SIMLOD_ERR_CUDA naming the silent rank after timeout_ms (0 = 10 s).
 int simlod_partition_wait(SimlodContext* ctx, uint64_t local_flags, uint32_t num_ranks, uint32_t value, uint32_t timeout_ms);
 
+// ---- depth compositing of the ranks' packed framebuffers over peer memory. The u64 word
+// is depth << 32 | colour (render.cu:61-104 of the reference), so an element-wise unsigned minimum over the ranks
+// is the depth test one GPU's atomicMin performs on the union of the samples.
+// copy this context's packed framebuffer (width x height u64) to dst_device, e.g. a peer-visible buffer; async
+int simlod_export_framebuffer(SimlodContext* ctx, uint64_t dst_device);
+// release `value` into this rank's flag word in every peer, behind everything enqueued so far; async
+int simlod_peer_signal(SimlodContext* ctx, const uint64_t* signal_ptrs, uint32_t num_ranks, uint32_t value);
+// two-shot all-reduce(min) in one kernel: this rank reduces slice `rank` of all fb_ptrs[0..num_ranks) (peer loads)
+// and stores the result into slice `rank` of all of them (peer stores), then releases signal_value into
+// signal_ptrs (optional). Callers order it after every peer's simlod_peer_signal with simlod_partition_wait and
+// wait for every peer's completion flag the same way. Asynchronous.
+int simlod_composite_framebuffers(SimlodContext* ctx, const uint64_t* fb_ptrs, uint32_t num_ranks, uint32_t rank,
+                                  const uint64_t* signal_ptrs, uint32_t signal_value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,7 @@ EXPORTS = [
     "simlod_memcpy_htod", "simlod_host_alloc", "simlod_host_free", "simlod_device_alloc", "simlod_device_free",
     "simlod_get_launch_info", "simlod_device_rcp", "simlod_synchronize", "simlod_flush_l2",
     "simlod_partition_count", "simlod_partition_scatter", "simlod_partition_wait",
+    "simlod_export_framebuffer", "simlod_peer_signal", "simlod_composite_framebuffers",
 ]
 
 _lib = None
@@ -164,6 +165,9 @@ def load_library():
         "simlod_partition_count": [vp, u64, u32, C.POINTER(PartitionPlan), C.POINTER(u64), C.POINTER(u64)],
         "simlod_partition_scatter": [vp, u64, u32, C.POINTER(PartitionPlan), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), u32],
         "simlod_partition_wait": [vp, u64, u32, u32, u32],
+        "simlod_export_framebuffer": [vp, u64],
+        "simlod_peer_signal": [vp, C.POINTER(u64), u32, u32],
+        "simlod_composite_framebuffers": [vp, C.POINTER(u64), u32, u32, C.POINTER(u64), u32],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -456,6 +460,19 @@ class SimLOD:
         offs = (C.c_uint64 * plan.num_ranks)(*[int(o) for o in dest_offsets])
         sig = (C.c_uint64 * plan.num_ranks)(*[int(p) for p in signal_ptrs]) if signal_ptrs is not None else None
         self._check(self._lib.simlod_partition_scatter(self._ctx, int(device_ptr), int(count), C.byref(plan), ptrs, offs, sig, int(signal_value)))
+
+    def export_framebuffer(self, dst_device_ptr):
+        self._check(self._lib.simlod_export_framebuffer(self._ctx, int(dst_device_ptr)))
+
+    def peer_signal(self, signal_ptrs, value):
+        sig = (C.c_uint64 * len(signal_ptrs))(*[int(p) for p in signal_ptrs])
+        self._check(self._lib.simlod_peer_signal(self._ctx, sig, len(signal_ptrs), int(value)))
+
+    def composite_framebuffers(self, fb_ptrs, rank, signal_ptrs=None, signal_value=0):
+        n = len(fb_ptrs)
+        fbs = (C.c_uint64 * n)(*[int(p) for p in fb_ptrs])
+        sig = (C.c_uint64 * n)(*[int(p) for p in signal_ptrs]) if signal_ptrs is not None else None
+        self._check(self._lib.simlod_composite_framebuffers(self._ctx, fbs, n, int(rank), sig, int(signal_value)))
 
     def partition_wait(self, local_flags_ptr, num_ranks, value, timeout_ms=0):
         self._check(self._lib.simlod_partition_wait(self._ctx, int(local_flags_ptr), int(num_ranks), int(value), int(timeout_ms)))

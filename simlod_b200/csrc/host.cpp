@@ -197,7 +197,7 @@ struct SimlodContext {
     Program programs[3];
     CUmodule utilModule = nullptr, lasModule = nullptr, partitionModule = nullptr;
     CUfunction fnPartCount = nullptr, fnPartScan = nullptr, fnPartScatter = nullptr;
-    CUfunction fnPartWait = nullptr;
+    CUfunction fnPartWait = nullptr, fnComposite = nullptr, fnPeerSignal = nullptr;
     CUdeviceptr partScratch = 0;       // spatial exchange: PART_SLOTS x (blockHist | blockBase | totals | cellCounts), then blocksDone, timedOut
     struct PartSlot { uint64_t points = 0; uint32_t count = 0; bool valid = false; } partSlots[64];   // counted batches awaiting their scatter
     uint32_t partNextSlot = 0;
@@ -331,17 +331,9 @@ extern "C" {
 
 const char* simlod_last_error(void) { return g_error.c_str(); }
 
-int simlod_create(const SimlodConfig* config, SimlodContext** out) {
-    if (!config || !out) return fail(SIMLOD_ERR_INVALID, "null argument");
-    if (config->width == 0 || config->height == 0) return fail(SIMLOD_ERR_INVALID, "render target must be non-empty");
-    { int rc0 = loadDriver(); if (rc0) return rc0; }
-    CU(D(cuInit)(0));
-    SimlodContext* ctx = new SimlodContext();
-    ctx->cfg = *config;
-    // the primary context, so the library composes with other runtime-API users in the process
-    CUresult r = D(cuDeviceGet)(&ctx->device, config->device);
-    if (r != CUDA_SUCCESS) { delete ctx; return fail(SIMLOD_ERR_CUDA, "D(cuDeviceGet)(%d) failed: no such CUDA device", config->device); }
-    CU(D(cuDevicePrimaryCtxRetain)(&ctx->primary, ctx->device));
+// everything simlod_create sets up after the primary context is retained; on failure the caller destroys the
+// partially built context (simlod_destroy releases whatever exists)
+static int createResources(SimlodContext* ctx, const SimlodConfig* config) {
     CU(D(cuCtxSetCurrent)(ctx->primary));
     CU(D(cuDeviceGetAttribute)(&ctx->numSMs, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, ctx->device));
     int coop = 0;
@@ -371,6 +363,8 @@ int simlod_create(const SimlodConfig* config, SimlodContext** out) {
     CU(D(cuModuleGetFunction)(&ctx->fnPartScan, ctx->partitionModule, "simlod_partition_scan"));
     CU(D(cuModuleGetFunction)(&ctx->fnPartScatter, ctx->partitionModule, "simlod_partition_scatter"));
     CU(D(cuModuleGetFunction)(&ctx->fnPartWait, ctx->partitionModule, "simlod_partition_wait"));
+    CU(D(cuModuleGetFunction)(&ctx->fnComposite, ctx->partitionModule, "simlod_composite_min"));
+    CU(D(cuModuleGetFunction)(&ctx->fnPeerSignal, ctx->partitionModule, "simlod_peer_signal"));
 
     // buffers (main.cpp:552-586)
     SimlodBuffers& b = ctx->buf;
@@ -424,6 +418,23 @@ int simlod_create(const SimlodConfig* config, SimlodContext** out) {
     int rc = computeGrids(ctx);
     if (rc != SIMLOD_OK) return rc;
     CU(D(cuCtxSynchronize)());
+    return SIMLOD_OK;
+}
+
+int simlod_create(const SimlodConfig* config, SimlodContext** out) {
+    if (!config || !out) return fail(SIMLOD_ERR_INVALID, "null argument");
+    if (config->width == 0 || config->height == 0) return fail(SIMLOD_ERR_INVALID, "render target must be non-empty");
+    { int rc0 = loadDriver(); if (rc0) return rc0; }
+    CU(D(cuInit)(0));
+    SimlodContext* ctx = new SimlodContext();
+    ctx->cfg = *config;
+    // the primary context, so the library composes with other runtime-API users in the process
+    CUresult r = D(cuDeviceGet)(&ctx->device, config->device);
+    if (r != CUDA_SUCCESS) { delete ctx; return fail(SIMLOD_ERR_CUDA, "D(cuDeviceGet)(%d) failed: no such CUDA device", config->device); }
+    r = D(cuDevicePrimaryCtxRetain)(&ctx->primary, ctx->device);
+    if (r != CUDA_SUCCESS) { delete ctx; return fail(SIMLOD_ERR_CUDA, "cuDevicePrimaryCtxRetain failed on device %d", config->device); }
+    int rc = createResources(ctx, config);
+    if (rc != SIMLOD_OK) { simlod_destroy(ctx); return rc; }       // last_error keeps the reason
     *out = ctx;
     return SIMLOD_OK;
 }
@@ -921,6 +932,14 @@ struct ScatterTargets { uint64_t ptr[PART_MAX_RANKS]; uint64_t offset[PART_MAX_R
 
 // per counted batch: blockHist[blocks][8] | blockBase[blocks][8] | totals[8] | cellCounts[512]
 uint64_t partSlotBytes(uint32_t blocks) { return (uint64_t)blocks * PART_MAX_RANKS * 4 * 2 + PART_MAX_RANKS * 4 + PART_MAX_CELLS * 4; }
+// scratch tail after the slots: blocksDone (scatter) | timedOut | blocksDone (composite) | pad
+int partScratchEnsure(SimlodContext* ctx) {
+    if (ctx->partScratch) return SIMLOD_OK;
+    const size_t bytes = (size_t)(partSlotBytes((uint32_t)ctx->numSMs * 4) * PART_SLOTS + 16);
+    CU(D(cuMemAlloc)(&ctx->partScratch, bytes));
+    CU(D(cuMemsetD8)(ctx->partScratch, 0, bytes));
+    return SIMLOD_OK;
+}
 
 int partitionSetup(SimlodContext* ctx, uint32_t count, const SimlodPartitionPlan* plan, PartitionParams* p, uint32_t* blocks) {
     if (!plan) return fail(SIMLOD_ERR_INVALID, "null plan");
@@ -939,12 +958,7 @@ int partitionSetup(SimlodContext* ctx, uint32_t count, const SimlodPartitionPlan
     p->perBlock = std::max(PART_BLOCK, (per + PART_BLOCK - 1) / PART_BLOCK * PART_BLOCK);
     memset(p->owner, 0, sizeof(p->owner));
     memcpy(p->owner, plan->owner, numCells);
-    if (!ctx->partScratch) {
-        const size_t bytes = (size_t)(partSlotBytes(*blocks) * PART_SLOTS + 16);
-        CU(D(cuMemAlloc)(&ctx->partScratch, bytes));
-        CU(D(cuMemsetD8)(ctx->partScratch, 0, bytes));
-    }
-    return SIMLOD_OK;
+    return partScratchEnsure(ctx);
 }
 }  // namespace
 
@@ -1012,7 +1026,7 @@ int simlod_partition_scatter(SimlodContext* ctx, uint64_t device_points, uint32_
 int simlod_partition_wait(SimlodContext* ctx, uint64_t local_flags, uint32_t num_ranks, uint32_t value, uint32_t timeout_ms) {
     int rc = setCurrent(ctx); if (rc) return rc;
     if (!local_flags || num_ranks < 1 || num_ranks > PART_MAX_RANKS) return fail(SIMLOD_ERR_INVALID, "bad flags / rank count");
-    if (!ctx->partScratch) return fail(SIMLOD_ERR_INVALID, "simlod_partition_wait before any simlod_partition_count");
+    { int rcs = partScratchEnsure(ctx); if (rcs) return rcs; }
     CUdeviceptr flags = (CUdeviceptr)local_flags;
     CUdeviceptr timedOut = ctx->partScratch + partSlotBytes((uint32_t)ctx->numSMs * 4) * PART_SLOTS + 4;
     uint64_t cycles = (uint64_t)(timeout_ms ? timeout_ms : 10000) * 2000000ull;          // SM clock ~2 GHz
@@ -1026,6 +1040,53 @@ int simlod_partition_wait(SimlodContext* ctx, uint64_t local_flags, uint32_t num
         CU(D(cuMemsetD8)(timedOut, 0, 4));
         return fail(SIMLOD_ERR_CUDA, "spatial exchange: rank %u did not signal step %u within %u ms", host - 1, value, timeout_ms ? timeout_ms : 10000);
     }
+    return SIMLOD_OK;
+}
+
+// ---- depth compositing of the ranks' framebuffers over peer memory ------------------------
+namespace {
+struct CompositeArgs { uint64_t fb[PART_MAX_RANKS]; uint64_t signal[PART_MAX_RANKS]; uint64_t numWords; uint32_t numRanks, rank, signalValue, pad; };
+struct SignalArgs { uint64_t signal[PART_MAX_RANKS]; uint32_t numRanks, value; };
+}  // namespace
+
+int simlod_export_framebuffer(SimlodContext* ctx, uint64_t dst_device) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!dst_device) return fail(SIMLOD_ERR_INVALID, "null destination");
+    CU(D(cuMemcpyDtoDAsync)((CUdeviceptr)dst_device, ctx->buf.renderbuffer + FB_OFFSET, (size_t)ctx->cfg.width * ctx->cfg.height * 8, ctx->streamMain));
+    return SIMLOD_OK;
+}
+
+int simlod_peer_signal(SimlodContext* ctx, const uint64_t* signal_ptrs, uint32_t num_ranks, uint32_t value) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!signal_ptrs || num_ranks < 1 || num_ranks > PART_MAX_RANKS) return fail(SIMLOD_ERR_INVALID, "bad signal words / rank count");
+    SignalArgs a;
+    memset(&a, 0, sizeof(a));
+    for (uint32_t d = 0; d < num_ranks; d++) { if (!signal_ptrs[d]) return fail(SIMLOD_ERR_INVALID, "null signal word for rank %u", d); a.signal[d] = signal_ptrs[d]; }
+    a.numRanks = num_ranks; a.value = value;
+    void* args[] = {&a};
+    CU(D(cuLaunchKernel)(ctx->fnPeerSignal, 1, 1, 1, 32, 1, 1, 0, ctx->streamMain, args, nullptr));
+    ctx->launches++;
+    return SIMLOD_OK;
+}
+
+int simlod_composite_framebuffers(SimlodContext* ctx, const uint64_t* fb_ptrs, uint32_t num_ranks, uint32_t rank,
+                                  const uint64_t* signal_ptrs, uint32_t signal_value) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!fb_ptrs || num_ranks < 1 || num_ranks > PART_MAX_RANKS || rank >= num_ranks) return fail(SIMLOD_ERR_INVALID, "bad framebuffer list / rank");
+    rc = partScratchEnsure(ctx); if (rc) return rc;
+    CompositeArgs a;
+    memset(&a, 0, sizeof(a));
+    for (uint32_t d = 0; d < num_ranks; d++) {
+        if (!fb_ptrs[d]) return fail(SIMLOD_ERR_INVALID, "null framebuffer for rank %u", d);
+        a.fb[d] = fb_ptrs[d];
+        if (signal_ptrs) { if (!signal_ptrs[d]) return fail(SIMLOD_ERR_INVALID, "null signal word for rank %u", d); a.signal[d] = signal_ptrs[d]; }
+    }
+    a.numWords = (uint64_t)ctx->cfg.width * ctx->cfg.height;
+    a.numRanks = num_ranks; a.rank = rank; a.signalValue = signal_value;
+    CUdeviceptr blocksDone = ctx->partScratch + partSlotBytes((uint32_t)ctx->numSMs * 4) * PART_SLOTS + 8;
+    void* args[] = {&a, &blocksDone};
+    CU(D(cuLaunchKernel)(ctx->fnComposite, (unsigned)ctx->numSMs * 4, 1, 1, PART_BLOCK, 1, 1, 0, ctx->streamMain, args, nullptr));
+    ctx->launches++;
     return SIMLOD_OK;
 }
 

@@ -177,3 +177,55 @@ extern "C" __global__ void simlod_partition_wait(const uint32_t* flags, uint32_t
         __nanosleep(200);
     }
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Depth compositing of the ranks' packed framebuffers: the u64 word is depth<<32 | colour, so an
+// element-wise unsigned minimum over the ranks is exactly the depth test one GPU's atomicMin performs on the union
+// of the samples (render.cu drawPoint = render.cu:61-104 of the reference). Two-shot all-reduce over peer memory in
+// ONE kernel: rank r reduces slice r of every rank's buffer (peer loads) and stores the result into slice r of every
+// rank's buffer (peer stores); slices are disjoint, so no rank reads what another writes. Ends like the scatter:
+// the last block releases this rank's flag in every peer.
+struct CompositeArgs {
+    uint64_t fb[MAX_RANKS];                 // every rank's framebuffer copy (device addresses, local or peer)
+    uint64_t signal[MAX_RANKS];
+    uint64_t numWords;
+    uint32_t numRanks, rank, signalValue, pad;
+};
+
+extern "C" __global__ void __launch_bounds__(BLOCK)
+simlod_composite_min(const CompositeArgs a, uint32_t* __restrict__ blocksDone) {
+    const uint64_t lo = a.numWords * a.rank / a.numRanks, hi = a.numWords * (a.rank + 1) / a.numRanks;
+    for (uint64_t i = lo + (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * BLOCK) {
+        unsigned long long m = 0xffffffffffffffffull;
+        for (uint32_t s = 0; s < a.numRanks; s++) {
+            unsigned long long v;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(reinterpret_cast<const unsigned long long*>(a.fb[s]) + i) : "memory");
+            m = v < m ? v : m;
+        }
+        for (uint32_t d = 0; d < a.numRanks; d++)
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(reinterpret_cast<unsigned long long*>(a.fb[d]) + i), "l"(m) : "memory");
+    }
+    if (a.signal[0] != 0) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t arrived = atomicAdd(blocksDone, 1u);
+            if (arrived == gridDim.x - 1u) {
+                __threadfence_system();
+                for (uint32_t d = 0; d < a.numRanks; d++)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.signal[d]), "r"(a.signalValue) : "memory");
+                *blocksDone = 0;
+            }
+        }
+    }
+}
+
+// "what this stream has written so far is ready": releases this rank's flag in every peer (enqueued behind the work
+// it announces, e.g. the copy of the framebuffer into the peer-visible buffer)
+struct SignalArgs { uint64_t signal[MAX_RANKS]; uint32_t numRanks, value; };
+extern "C" __global__ void simlod_peer_signal(const SignalArgs a) {
+    if (threadIdx.x < a.numRanks) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.signal[threadIdx.x]), "r"(a.value) : "memory");
+    }
+}

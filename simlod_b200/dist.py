@@ -237,3 +237,46 @@ class SpatialExchange:
             torch.cuda.current_stream().synchronize()
             assert got == recv_count
         return self.recv.data_ptr() + base, recv_count
+
+
+class FramebufferCompositor:
+    """Depth compositing of the ranks' packed framebuffers on the GPUs (one process per GPU): every rank renders its
+    octree, copies the packed u64 framebuffer into a peer-visible buffer (torch symmetric memory), and ONE kernel
+    per rank reduces its slice of all buffers with peer loads and writes the minimum back into all of them with
+    peer stores (simlod_composite_framebuffers). Flags: 2k+1 = "frame k is in my buffer", 2k+2 = "my slice of frame
+    k is composited everywhere". The host-side fallback for CPU tests is composite_framebuffers() above."""
+
+    FLAG_BYTES = 4096
+
+    def __init__(self, sim, width, height, device=None, timeout_ms=10000):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        dist = _dist()
+        self.sim, self.timeout_ms = sim, timeout_ms
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.fb_bytes = int(width) * int(height) * 8
+        self.buf = symm_mem.empty(self.fb_bytes + self.FLAG_BYTES, dtype=torch.uint8, device=self.device)
+        self.handle = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.buf[self.fb_bytes:].zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.flag_ptrs = [p + self.fb_bytes + 4 * self.rank for p in self.peer_ptrs]       # my word in every peer
+        self.local_flags = self.buf.data_ptr() + self.fb_bytes
+        self.frame = 0
+
+    def composite(self):
+        """Composite the framebuffer the last simlod_render left in this context with every peer's. Returns the
+        device address of the composited packed framebuffer (identical on every rank)."""
+        k = self.frame
+        self.frame += 1
+        self.sim.export_framebuffer(self.peer_ptrs[self.rank])
+        self.sim.peer_signal(self.flag_ptrs, 2 * k + 1)
+        self.sim.partition_wait(self.local_flags, self.world, 2 * k + 1, self.timeout_ms)      # every peer's frame is in place
+        self.sim.composite_framebuffers(self.peer_ptrs, self.rank, signal_ptrs=self.flag_ptrs, signal_value=2 * k + 2)
+        self.sim.partition_wait(self.local_flags, self.world, 2 * k + 2, self.timeout_ms)      # every slice has landed here
+        return self.peer_ptrs[self.rank]
+
+    def read(self, width, height):
+        return self.sim.memcpy_dtoh(self.peer_ptrs[self.rank], self.fb_bytes).view(np.uint64).reshape(height, width)

@@ -263,3 +263,89 @@ def test_merged_forest_built_on_the_gpu_equals_the_single_octree(sims, kind, lev
         o.add_batch(pts[f:f + batch])
     d2 = oracle.compare_canon(c_single, o.canon(), "ours vs oracle")
     assert not d2, "\n".join(d2)
+
+
+@pytest.mark.gpu
+def test_composite_kernel_is_the_elementwise_u64_minimum(sims):
+    """Two "ranks" on one GPU: both run their half of the two-shot all-reduce over the two buffers; afterwards both
+    buffers hold the element-wise minimum, flags released, and a stale wait times out naming the rank."""
+    sim = sims[0]
+    w, h = 640, 360                              # the contexts of this module render at 640 x 360
+    rng = np.random.default_rng(3)
+    fbs = [rng.integers(0, 2 ** 63, size=w * h, dtype=np.uint64) for _ in range(2)]
+    fbs[0][::5] = np.uint64(0x7f800000) << np.uint64(32)            # clear value on one side
+    fbs[1][::7] = np.uint64(0xffffffffffffffff)
+    bufs = [sim.device_alloc(w * h * 8) for _ in range(2)]
+    flags = sim.device_alloc(64)
+    try:
+        sim.memcpy_htod(flags, np.zeros(16, dtype=np.uint32))
+        for b, f in zip(bufs, fbs):
+            sim.memcpy_htod(b, f)
+        for r in range(2):                        # rank r signals word r of the (shared) flag array
+            sim.composite_framebuffers(bufs, r, signal_ptrs=[flags + 4 * r] * 2, signal_value=2)
+        sim.partition_wait(flags, 2, 2)
+        want = np.minimum(fbs[0], fbs[1])
+        for b in bufs:
+            assert np.array_equal(sim.memcpy_dtoh(b, w * h * 8).view(np.uint64), want)
+        sim.peer_signal([flags + 8, flags + 12], 9)
+        sim.synchronize()
+        assert list(sim.memcpy_dtoh(flags, 16).view(np.uint32)) == [2, 2, 9, 9]
+    finally:
+        for p in bufs + [flags]:
+            sim.device_free(p)
+
+
+@pytest.mark.gpu
+def test_composited_renders_of_the_merged_forest_match_the_single_octree_in_depth(sims):
+    """Each rank rasterises its own octree; the u64 minimum of the packed framebuffers must carry, in every pixel,
+    the depth the single octree's render has (the colour of a voxel may be any of its candidates)."""
+    from simlod_b200 import camera
+    world, level = 2, 1
+    single, ranks = sims[0], sims[1:]
+    pts, mn, mx = data.uniform_cube(1_500_000, size=64.0, seed=11)
+    for s in sims:
+        s.set_box(mn, mx)
+        s.set_settings(useHighQualityShading=0)          # the atomicMin path: the packed word is depth | colour
+        s.reset()
+    size = float(np.max(np.asarray(mx, np.float32) - np.asarray(mn, np.float32)))
+    owners = sdist.plan_owners(np.bincount(oracle.partition_cells(pts, mn, mx, level, single.device_rcp(size)), minlength=8), world)
+    plan = single.partition_plan(level, owners, world)
+    batch = 500_000
+    src = single.device_alloc(batch * 16)
+    stage = [single.device_alloc(batch * 16) for _ in range(world)]
+    try:
+        for f in range(0, len(pts), batch):
+            b = pts[f:f + batch]
+            single.memcpy_htod(src, b.view(np.uint8))
+            counts, _ = single.partition_count(src, len(b), plan)
+            single.partition_scatter(src, len(b), plan, stage, [0] * world)
+            single.synchronize()
+            single.insert_device(src, len(b))
+            for r in range(world):
+                ranks[r].insert_device(stage[r], int(counts[r]))
+        w, h = 640, 360
+        bufs = [single.device_alloc(w * h * 8) for _ in range(world)]
+        for yaw in (0.0, 2.0):
+            view, proj = camera.autofocus(mx, w, h, yaw_offset=yaw)
+            for s in sims:
+                s.set_camera(view, proj)
+                s.render()
+            want = single.framebuffer().copy()
+            for r in range(world):
+                ranks[r].export_framebuffer(bufs[r])
+                ranks[r].synchronize()
+            for r in range(world):
+                ranks[r].composite_framebuffers(bufs, r)
+                ranks[r].synchronize()
+            got = single.memcpy_dtoh(bufs[0], w * h * 8).view(np.uint64).reshape(want.shape)
+            assert np.array_equal(got, single.memcpy_dtoh(bufs[1], w * h * 8).view(np.uint64).reshape(want.shape))
+            host = sdist.composite_framebuffers(np.minimum(ranks[0].framebuffer(), ranks[1].framebuffer()))
+            assert np.array_equal(got, host)
+            assert np.array_equal(got >> np.uint64(32), want >> np.uint64(32))
+            assert (got != want).mean() < 0.5           # colours: mostly identical, voxel colours may differ
+        for p in bufs:
+            single.device_free(p)
+    finally:
+        single.device_free(src)
+        for p in stage:
+            single.device_free(p)

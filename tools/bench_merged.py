@@ -144,6 +144,38 @@ for mode in ("nccl", "p2p"):
     if rank == 0:
         print(mode, json.dumps(res[mode]), flush=True)
 
+# render the merged octree: every rank rasterises its part, the packed framebuffers are depth-composited over peer
+# memory (one kernel per rank) and, beside it, with NCCL all_reduce(MIN) through the host path of dist.py
+try:
+    from simlod_b200 import camera
+    W, H = 640, 360
+    comp = sdist.FramebufferCompositor(sim, W, H, device=dev)
+    sim.set_settings(useHighQualityShading=0)
+    frames = []
+    for name, cam in (("morro_bird", camera.orbit_camera(width=W, height=H, **camera.MORRO_BIRD)), ("autofocus", camera.autofocus(mx, W, H))):
+        sim.set_camera(*cam)
+        sim.render()
+        sync_all()
+        t0 = time.perf_counter()
+        render_ms = sim.render()
+        t1 = time.perf_counter()
+        comp.composite()
+        t2 = time.perf_counter()
+        got = comp.read(W, H)
+        want = sdist.composite_framebuffers(sim.framebuffer(), dev)
+        ok = torch.tensor([1 if np.array_equal(got, want) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        tt = torch.tensor([t1 - t0, t2 - t1], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        covered = int((got >> np.uint64(32) != np.uint64(0x7f800000)).sum())
+        frames.append({"camera": name, "render_kernel_ms": render_ms, "render_call_ms": float(tt[0]) * 1e3, "composite_ms": float(tt[1]) * 1e3,
+                       "equals_nccl_allreduce_min_all_ranks": bool(int(ok.item())), "covered_pixels": covered})
+    res["render_composite"] = {"width": W, "height": H, "frames": frames}
+except Exception as e:
+    res["render_composite"] = {"error": "%s: %s" % (type(e).__name__, e)}
+if rank == 0:
+    print("render", json.dumps(res["render_composite"]), flush=True)
+
 # baseline beside it: the batch-sharded forest (no exchange), same data
 sim.reset()
 sync_all()
