@@ -151,42 +151,48 @@ def all_to_all_points(send, recv, matrix, rank):
 class SpatialExchange:
     """Per-rank driver of the exchange on the GPUs (one process per GPU; needs CUDA, NCCL and the C-ABI library).
 
-    mode "p2p":  receive buffers are torch symmetric memory (peer-mapped over NVLink). ONE kernel per step
-                 partitions the batch, stores every point straight into its owner's buffer and, when its last
-                 store is visible system-wide, releases this sender's flag in every receiver; the receiver's
-                 wait kernel acquires the G flags. NCCL carries only the counts (8*G bytes per step, or one
-                 all_gather for a whole window of steps after `prepare`).
+    mode "p2p":  receive buffers are torch symmetric memory (peer-mapped over NVLink). ONE kernel per batch
+                 partitions it, stores every point straight into its owner's buffer and, when its last store is
+                 visible system-wide, releases this sender's flag in every receiver; the receiver's wait kernel
+                 acquires the G flags. NCCL carries only the counts: 8*G bytes per batch, or one all_gather for a
+                 whole window of batches after `prepare`.
     mode "nccl": scatter into a local staging buffer, then all_to_all_single (the baseline).
-    Receive buffers are double-buffered by step parity: a sender reaches step k+2 only after it has seen every
-    receiver's flag of step k+1, which a receiver releases after it has consumed step k."""
+
+    The unit of exchange is a GROUP of up to `depth` batches (`exchange_group`): their scatters are launched back to
+    back without a host round trip, land contiguously in the receiver (senders in rank order within a batch,
+    batches in order) and are acquired with one wait; the receiver then inserts the whole group with one
+    simlod_insert_device call, i.e. at the streaming rate of the builder instead of one blocking launch per batch.
+    There are two group regions, used alternately: a sender starts group g+2 only after it has seen every
+    receiver's flags of group g+1, which a receiver releases after it has consumed group g."""
 
     FLAG_BYTES = 4096
 
-    def __init__(self, sim, level, owners, capacity_points=1_000_000, mode="p2p", device=None, timeout_ms=10000):
+    def __init__(self, sim, level, owners, capacity_points=1_000_000, depth=1, mode="p2p", device=None, timeout_ms=10000):
         import torch
         dist = _dist()
         self.sim, self.mode, self.timeout_ms = sim, mode, timeout_ms
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.plan = sim.partition_plan(level, owners, self.world)
-        self.capacity = int(capacity_points)
-        half = self.world * self.capacity * 16                 # worst case: every sender's whole batch lands here
-        self.half_bytes = half
-        self.step = 0
-        self.prepared = {}                                     # (device_ptr, count) -> G x G matrix of that step
+        self.capacity, self.depth = int(capacity_points), int(depth)
+        region = self.depth * self.world * self.capacity * 16  # worst case: every sender's whole group lands here
+        self.region_bytes = region
+        self.step = 0                                          # batches sent so far = value of my flag in every receiver
+        self.group = 0
+        self.prepared = {}                                     # (device_ptr, count) -> G x G matrix of that batch
         if mode == "p2p":
             import torch.distributed._symmetric_memory as symm_mem
-            self.recv = symm_mem.empty(2 * half + self.FLAG_BYTES, dtype=torch.uint8, device=self.device)
+            self.recv = symm_mem.empty(2 * region + self.FLAG_BYTES, dtype=torch.uint8, device=self.device)
             self.handle = symm_mem.rendezvous(self.recv, dist.group.WORLD)
             self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
             assert self.peer_ptrs[self.rank] == self.recv.data_ptr()
-            self.recv[2 * half:].zero_()                       # flag words: [sender] u32, monotonically increasing step numbers
+            self.recv[2 * region:].zero_()                     # flag words: [sender] u32, monotonically increasing batch numbers
             torch.cuda.synchronize()
             dist.barrier()
-            self.flag_ptrs = [p + 2 * half + 4 * self.rank for p in self.peer_ptrs]     # my word in every receiver
-            self.local_flags = self.recv.data_ptr() + 2 * half
+            self.flag_ptrs = [p + 2 * region + 4 * self.rank for p in self.peer_ptrs]      # my word in every receiver
+            self.local_flags = self.recv.data_ptr() + 2 * region
         elif mode == "nccl":
-            self.recv = torch.empty(2 * half, dtype=torch.uint8, device=self.device)
+            self.recv = torch.empty(2 * region, dtype=torch.uint8, device=self.device)
             self.send = torch.empty(self.capacity * 16, dtype=torch.uint8, device=self.device)
         else:
             raise ValueError("mode must be 'p2p' or 'nccl'")
@@ -202,7 +208,7 @@ class SpatialExchange:
 
     def prepare(self, batches):
         """Count a window of upcoming batches [(device_ptr, count)] (at most 64, the same number on every rank) and
-        gather all their counts with ONE all_gather, so that the steps themselves need no collective."""
+        gather all their counts with ONE all_gather, so that the exchange itself needs no collective."""
         import torch
         dist = _dist()
         mine = np.stack([self.sim.partition_count(p, c, self.plan)[0].astype(np.int64) for p, c in batches])      # [K][G]
@@ -213,30 +219,42 @@ class SpatialExchange:
         for k, (p, c) in enumerate(batches):
             self.prepared[(int(p), int(c))] = allc[:, k, :]
 
-    def exchange(self, device_ptr, count):
-        """Send the `count` points at device_ptr to their owners. Returns (device address, number of points) of what
-        this rank received, valid until the step after next."""
+    def exchange_group(self, batches):
+        """Send the batches [(device_ptr, count)] (at most `depth`) to their owners. Returns (device address, number
+        of points) of what this rank received — contiguous, batches in order, senders in rank order within a batch —
+        valid until the group after next."""
         import torch
-        if count > self.capacity:
-            raise ValueError("batch of %d points exceeds the exchange capacity %d" % (count, self.capacity))
-        matrix = self.prepared.pop((int(device_ptr), int(count)), None)
-        if matrix is None:
-            mine, _ = self.sim.partition_count(device_ptr, count, self.plan)
-            matrix = gather_counts(mine, self.device)
-        send_offsets, landing, recv_count = exchange_layout(matrix, self.rank)
-        base = (self.step & 1) * self.half_bytes
-        self.step += 1
+        if len(batches) > self.depth:
+            raise ValueError("group of %d batches exceeds the exchange depth %d" % (len(batches), self.depth))
+        if any(c > self.capacity for _, c in batches):
+            raise ValueError("a batch exceeds the exchange capacity of %d points" % self.capacity)
+        if any((int(p), int(c)) not in self.prepared for p, c in batches):
+            self.prepare(batches)
+        base = (self.group & 1) * self.region_bytes
+        self.group += 1
+        arrived = np.zeros(self.world, dtype=np.int64)         # points every receiver already holds of this group
+        for ptr, count in batches:
+            matrix = self.prepared.pop((int(ptr), int(count)))
+            send_offsets, landing, _ = exchange_layout(matrix, self.rank)
+            self.step += 1
+            if self.mode == "p2p":
+                self.sim.partition_scatter(ptr, count, self.plan, [p + base for p in self.peer_ptrs], arrived + landing,
+                                           signal_ptrs=self.flag_ptrs, signal_value=self.step)
+            else:
+                self.sim.partition_scatter(ptr, count, self.plan, [self.send.data_ptr()] * self.world, send_offsets)
+                self.sim.synchronize()
+                at = base + int(arrived[self.rank]) * 16
+                all_to_all_points(self.send, self.recv[at:base + self.region_bytes], matrix, self.rank)
+                torch.cuda.current_stream().synchronize()
+            arrived += np.asarray(matrix, dtype=np.int64).sum(axis=0)
         if self.mode == "p2p":
-            self.sim.partition_scatter(device_ptr, count, self.plan, [p + base for p in self.peer_ptrs], landing,
-                                       signal_ptrs=self.flag_ptrs, signal_value=self.step)
+            # flags are batch numbers and every sender's scatters run in stream order: the last value covers the group
             self.sim.partition_wait(self.local_flags, self.world, self.step, self.timeout_ms)
-        else:
-            self.sim.partition_scatter(device_ptr, count, self.plan, [self.send.data_ptr()] * self.world, send_offsets)
-            self.sim.synchronize()
-            got = all_to_all_points(self.send, self.recv[base:base + self.half_bytes], matrix, self.rank)
-            torch.cuda.current_stream().synchronize()
-            assert got == recv_count
-        return self.recv.data_ptr() + base, recv_count
+        return self.recv.data_ptr() + base, int(arrived[self.rank])
+
+    def exchange(self, device_ptr, count):
+        """One batch (a group of one)."""
+        return self.exchange_group([(device_ptr, count)])
 
 
 class FramebufferCompositor:

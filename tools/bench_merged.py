@@ -29,6 +29,7 @@ from simlod_b200 import dist as sdist  # noqa: E402
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 LEVEL = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "merged.json")
+DEPTH = int(sys.argv[4]) if len(sys.argv) > 4 else 8          # batches per exchange group
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -53,7 +54,7 @@ t = torch.tensor(hist, device=dev)
 dist.all_reduce(t)
 owners = sdist.plan_owners(t.cpu().numpy(), world)
 load = np.bincount(owners, weights=t.cpu().numpy(), minlength=world)
-res = {"world": world, "batches_per_gpu": K, "level": LEVEL, "points_total": K * world * B, "owner_load": [int(v) for v in load]}
+res = {"world": world, "batches_per_gpu": K, "level": LEVEL, "group_depth": DEPTH, "points_total": K * world * B, "owner_load": [int(v) for v in load]}
 
 
 def sync_all():
@@ -63,7 +64,7 @@ def sync_all():
 
 
 def run(mode):
-    ex = sdist.SpatialExchange(sim, LEVEL, owners, capacity_points=B, mode=mode, device=dev)
+    ex = sdist.SpatialExchange(sim, LEVEL, owners, capacity_points=B, depth=DEPTH, mode=mode, device=dev)
     best = None
     for rep in range(3):
         sim.reset()
@@ -74,9 +75,9 @@ def run(mode):
         for w0 in range(0, K, 32):                   # plan a window of steps: their counts travel in one all_gather
             ex.prepare([(src + i * B * 16, B) for i in range(w0, min(K, w0 + 32))])
         t_prep = time.perf_counter() - t0
-        for i in range(K):
+        for g0 in range(0, K, DEPTH):
             a = time.perf_counter()
-            ptr, n = ex.exchange(src + i * B * 16, B)
+            ptr, n = ex.exchange_group([(src + i * B * 16, B) for i in range(g0, min(K, g0 + DEPTH))])
             b = time.perf_counter()
             if n:
                 kms, _ = sim.insert_device(ptr, n)
@@ -105,11 +106,11 @@ def rebuild_locally():
     plan = sim.partition_plan(LEVEL, owners, world)
     everyone = [sdist.shard_batches(total_batches, r, world) for r in range(world)]
     tmp = sim.device_alloc(B * 16)
-    land = sim.device_alloc(world * B * 16)
+    land = sim.device_alloc(DEPTH * world * B * 16)
     scratch = [sim.device_alloc(B * 16) for _ in range(world)]          # the other ranks' buckets are thrown away
     sim.reset()
+    pos = 0
     for i in range(K):
-        pos = 0
         for s in range(world):
             pts = data.terrain(total_batches * B, everyone[s][i] * B, B)[0]
             sim.memcpy_htod(tmp, pts.view(np.uint8))
@@ -119,8 +120,10 @@ def rebuild_locally():
             sim.partition_scatter(tmp, B, plan, ptrs, offs)
             sim.synchronize()
             pos += int(counts[rank])
-        if pos:
-            sim.insert_device(land, pos)
+        if (i + 1) % DEPTH == 0 or i + 1 == K:      # the exchange delivers a group of DEPTH batches as one contiguous stream
+            if pos:
+                sim.insert_device(land, pos)
+            pos = 0
     st = sim.stats()
     canon = oracle.canon_from_image(*sim.download_octree())
     for p in [tmp, land] + scratch:
