@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-batches", type=int, default=8)
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "blocks", "roundrobin"],
+                    help="N > 1: every rank inserts its own K-batch scan of the N=1 extent and density (tiles: a survey of N tiles, "
+                         "per-GPU work identical to N=1), or a share of ONE N*K-batch scan: batches [g*K, (g+1)*K) (blocks) / b %% N == g (roundrobin)")
     return ap.parse_args()
 
 
@@ -102,14 +105,14 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def generate_batches(total_batches, mine, threads=None):
+def generate_batches(total_batches, mine, threads=None, seed=7):
     """This rank's batches of the terrain scan of total_batches * 1 M points (counter-based generator)."""
     from concurrent.futures import ThreadPoolExecutor
     from simlod_b200 import data
     n_total = total_batches * BATCH
     threads = threads or min(16, os.cpu_count() or 4)
     with ThreadPoolExecutor(threads) as ex:
-        out = list(ex.map(lambda b: data.terrain(n_total, b * BATCH, BATCH)[0], mine))
+        out = list(ex.map(lambda b: data.terrain(n_total, b * BATCH, BATCH, seed)[0], mine))
     return out, (0.0, 0.0, 0.0), data.TERRAIN_EXTENT
 
 
@@ -247,8 +250,12 @@ def run_reference(args, rank, world):
     import oracle
     W, K = args.warmup, args.steps
     total = world * K
-    mine = list(range(0, total, world))
-    batches, mn, mx = generate_batches(total, mine[:max(K, W)])
+    from simlod_b200 import dist as sdist
+    if args.shard == "tiles":
+        batches, mn, mx = generate_batches(K, list(range(K)), seed=7)            # rank 0's tile
+    else:
+        mine = sdist.shard_batches_blocks(total, 0, world) if args.shard == "blocks" else sdist.shard_batches(total, 0, world)
+        batches, mn, mx = generate_batches(total, mine[:max(K, W)])
     o = oracle.Oracle(mn, mx)
     for b in batches[:W]:
         o.add_batch(b)
@@ -300,9 +307,12 @@ def main():
 
     W, K = max(args.warmup, 0), args.steps
     total_batches = world * K
-    mine = sdist.shard_batches(total_batches, rank, world)
     t_gen = time.time()
-    batches, mn, mx = generate_batches(total_batches, mine)
+    if args.shard == "tiles":           # rank g: its own K-batch scan (tile g of the survey), same extent and density as N = 1
+        batches, mn, mx = generate_batches(K, list(range(K)), seed=7 + rank)
+    else:
+        mine = sdist.shard_batches_blocks(total_batches, rank, world) if args.shard == "blocks" else sdist.shard_batches(total_batches, rank, world)
+        batches, mn, mx = generate_batches(total_batches, mine)
     t_gen = time.time() - t_gen
     npts = K * BATCH
 
@@ -430,7 +440,7 @@ def main():
             "dtype": "u32+f32", "data": "synthetic",
             "config": {"workload": "terrain_synth_%dM (Morro Bay 36M stand-in: 4800x4300x300 m fBm terrain in 50 m flight strips), "
                                    "%d x 1M-point batches per GPU streamed from a reset octree" % (K, K),
-                       "batch_points": BATCH, "points_per_gpu": npts, "parallelism": "batch-sharded x%d" % world,
+                       "batch_points": BATCH, "points_per_gpu": npts, "parallelism": "batch-sharded x%d (%s)" % (world, {"tiles": "one %d-batch scan tile per GPU" % K, "blocks": "contiguous blocks of one scan", "roundrobin": "round-robin over one scan"}[args.shard]),
                        "l2": "inputs %d MB > L2 (126 MB); L2 flushed before each timed region" % (npts * 16 // 1000000),
                        "kernel_only_mpoints_per_s": round(all_pts / t_kernel / 1e3, 2),
                        "octree": {k: totals[k] for k in ("numNodes", "numInner", "numLeaves", "numPoints", "numVoxels", "allocatedBytes_persistent")},

@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <sched.h>
 #if defined(__x86_64__)
 #include <emmintrin.h>
 #endif
@@ -26,6 +27,7 @@
 #include <thread>
 #include <cstdarg>
 #include <cstdio>
+#include <cctype>
 #include <cstring>
 #include <fstream>
 #include <string>
@@ -57,7 +59,7 @@ int fail(int code, const char* fmt, ...) {
 // and its exports inspected on a machine without a GPU driver; every entry point that touches
 // the device fails with SIMLOD_ERR_CUDA there. There is no other code path.
 // ------------------------------------------------------------------------------------------
-#define DRV_LIST(X) X(cuArray3DCreate) X(cuArrayDestroy) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuDeviceGet) X(cuDeviceGetAttribute) X(cuDevicePrimaryCtxRelease) X(cuDevicePrimaryCtxRetain) X(cuEventCreate) X(cuEventDestroy) X(cuEventElapsedTime) X(cuEventQuery) X(cuEventRecord) X(cuEventSynchronize) X(cuGetErrorString) X(cuInit) X(cuLaunchCooperativeKernel) X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree) X(cuMemFreeHost) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemcpy2D) X(cuMemcpyDtoDAsync) X(cuMemcpyDtoH) X(cuMemcpyDtoHAsync) X(cuMemcpyHtoD) X(cuMemcpyHtoDAsync) X(cuMemsetD32Async) X(cuMemsetD8) X(cuMemsetD8Async) X(cuModuleGetFunction) X(cuModuleLoadData) X(cuModuleUnload) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuSurfObjectCreate) X(cuSurfObjectDestroy)
+#define DRV_LIST(X) X(cuArray3DCreate) X(cuArrayDestroy) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuDeviceGet) X(cuDeviceGetAttribute) X(cuDeviceGetPCIBusId) X(cuDevicePrimaryCtxRelease) X(cuDevicePrimaryCtxRetain) X(cuEventCreate) X(cuEventDestroy) X(cuEventElapsedTime) X(cuEventQuery) X(cuEventRecord) X(cuEventSynchronize) X(cuGetErrorString) X(cuInit) X(cuLaunchCooperativeKernel) X(cuLaunchKernel) X(cuMemAlloc) X(cuMemFree) X(cuMemFreeHost) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemcpy2D) X(cuMemcpyDtoDAsync) X(cuMemcpyDtoH) X(cuMemcpyDtoHAsync) X(cuMemcpyHtoD) X(cuMemcpyHtoDAsync) X(cuMemsetD32Async) X(cuMemsetD8) X(cuMemsetD8Async) X(cuModuleGetFunction) X(cuModuleLoadData) X(cuModuleUnload) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuSurfObjectCreate) X(cuSurfObjectDestroy)
 #define DRV_STR2(x) #x
 #define DRV_STR(x) DRV_STR2(x)
 struct DriverApi {
@@ -223,6 +225,40 @@ int devAlloc(uint64_t* out, uint64_t bytes) {
     return SIMLOD_OK;
 }
 #define ALLOC(field, bytes) do { int _rc = devAlloc(&(field), (bytes)); if (_rc) return _rc; } while (0)
+
+// Page-locked host memory should live on the NUMA node the GPU hangs off: the copy engine then reads local DRAM
+// instead of crossing the socket interconnect (which all ranks of a multi-GPU job would share). The driver
+// allocates on the node of the calling thread, so the thread is parked on that node's CPUs for the call.
+struct NumaLocal {
+    cpu_set_t old;
+    bool active = false;
+    explicit NumaLocal(SimlodContext* ctx) {
+        char bus[32] = {0};
+        if (D(cuDeviceGetPCIBusId)(bus, (int)sizeof(bus), ctx->device) != CUDA_SUCCESS) return;
+        for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+        char path[128];
+        snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+        int node = -1;
+        if (FILE* f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+        if (node < 0) return;
+        snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+        char list[4096] = {0};
+        if (FILE* f = fopen(path, "r")) { if (!fgets(list, sizeof(list), f)) list[0] = 0; fclose(f); }
+        cpu_set_t want;
+        CPU_ZERO(&want);
+        for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+            int a = 0, b = 0;
+            int n = sscanf(tok, "%d-%d", &a, &b);
+            if (n == 1) b = a;
+            if (n >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET(c, &want);
+        }
+        if (sched_getaffinity(0, sizeof(old), &old) != 0) return;
+        CPU_AND(&want, &want, &old);
+        if (CPU_COUNT(&want) == 0) return;
+        active = sched_setaffinity(0, sizeof(want), &want) == 0;
+    }
+    ~NumaLocal() { if (active) sched_setaffinity(0, sizeof(old), &old); }
+};
 
 const char* kernelName(int program) {
     switch (program) {
@@ -676,6 +712,7 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
     for (int i = 0; i < 3; i++) { ctx->uniforms.boxMin[i] = 0.0f; ctx->uniforms.boxMax[i] = hdr[3 + i] - hdr[i]; }   // main.cpp:312-313
     rc = simlod_reset(ctx); if (rc) return rc;                            // reload() -> reset
     if (!ctx->pinnedPool) {
+        NumaLocal onGpuNode(ctx);
         CU(D(cuMemHostAlloc)(&ctx->pinnedPool, (size_t)POOL_SLOTS * slotBytes, CU_MEMHOSTALLOC_PORTABLE));
         for (int i = 0; i < POOL_SLOTS; i++) CU(D(cuEventCreate)(&ctx->evPool[i], CU_EVENT_DISABLE_TIMING));
     }
@@ -860,6 +897,7 @@ int simlod_memcpy_htod(SimlodContext* ctx, uint64_t dst_device, const void* src,
 
 int simlod_host_alloc(SimlodContext* ctx, uint64_t bytes, void** out) {
     int rc = setCurrent(ctx); if (rc) return rc;
+    NumaLocal onGpuNode(ctx);
     CU(D(cuMemHostAlloc)(out, (size_t)bytes, CU_MEMHOSTALLOC_PORTABLE));
     return SIMLOD_OK;
 }

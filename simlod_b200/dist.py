@@ -25,6 +25,17 @@ def shard_batches(num_batches, rank, world_size):
     return list(range(rank, num_batches, world_size))
 
 
+def shard_batches_blocks(num_batches, rank, world_size):
+    """Contiguous assignment: rank g inserts batches [g*K, (g+1)*K) (K = ceil(num_batches / G)), in order. For a
+    scan that arrives in spatial order (flight strips) every rank then builds the octree of a compact region of the
+    global cube — per-GPU work and tree shape stay what they are on one GPU — instead of a G-times sparser sample
+    of the whole extent (round-robin), and the ranks' octrees overlap little when they are rendered and composited."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank %d outside world of %d" % (rank, world_size))
+    per = -(-num_batches // world_size)
+    return list(range(min(rank * per, num_batches), min((rank + 1) * per, num_batches)))
+
+
 def shard_point_range(num_points, batch_size, rank, world_size):
     """[(first, count)] point ranges of this rank's batches for a stream of num_points points."""
     num_batches = -(-num_points // batch_size)

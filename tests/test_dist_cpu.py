@@ -20,6 +20,11 @@ def test_round_robin_sharding_partitions_the_stream():
             assert flat == list(range(nb))
             assert all(o == sorted(o) for o in owned)
             assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+    for nb in (0, 1, 7, 36, 250):
+        for g in (1, 2, 4, 8):
+            owned = [sdist.shard_batches_blocks(nb, r, g) for r in range(g)]
+            assert [b for o in owned for b in o] == list(range(nb))          # contiguous, in order, disjoint, complete
+            assert max(len(o) for o in owned) <= -(-nb // g)
     ranges = sdist.shard_point_range(2_500_001, 1_000_000, 0, 2)
     assert ranges == [(0, 1_000_000), (2_000_000, 500_001)]
 
