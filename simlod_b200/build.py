@@ -44,7 +44,7 @@ def build_native(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
     os.makedirs(CUBIN_DIR, exist_ok=True)
     headers = [os.path.join(ROOT, "include", "simlod_abi.h"), os.path.join(ROOT, "include", "simlod_b200.h"),
-               os.path.join(CSRC, "fpmath.cuh")]
+               os.path.join(CSRC, "fpmath.cuh"), os.path.join(CSRC, "loader_pool.h")]
     images = []
     for name in PROGRAMS:
         src = os.path.join(CSRC, name + ".cu")

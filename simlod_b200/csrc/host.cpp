@@ -106,80 +106,7 @@ struct Program {
 
 }  // namespace
 
-// Copy with non-temporal stores: the destination lines go to memory without being read or left in the cache.
-// The loaders must not fill the page-locked pool with ordinary stores (pread straight into it): each piece would
-// stay dirty in the cache of whichever core read it, and the copy engine's reads of such lines are served by
-// cross-core snoops — measured on the 2-socket host of the B200 box at ~19 GB/s against ~52 GB/s for lines that
-// are in DRAM. Each loader therefore preads into a 256 KB cache-resident staging buffer and streams it out.
-static inline void copyStreaming(char* dst, const char* src, uint64_t bytes) {      // dst, src 16-byte aligned, bytes % 16 == 0
-#if defined(__x86_64__)
-    uint64_t i = 0;
-    for (; i + 64 <= bytes; i += 64) {
-        __m128i a = _mm_load_si128((const __m128i*)(src + i)), b = _mm_load_si128((const __m128i*)(src + i + 16));
-        __m128i c = _mm_load_si128((const __m128i*)(src + i + 32)), d = _mm_load_si128((const __m128i*)(src + i + 48));
-        _mm_stream_si128((__m128i*)(dst + i), a); _mm_stream_si128((__m128i*)(dst + i + 16), b);
-        _mm_stream_si128((__m128i*)(dst + i + 32), c); _mm_stream_si128((__m128i*)(dst + i + 48), d);
-    }
-    for (; i < bytes; i += 16) _mm_stream_si128((__m128i*)(dst + i), _mm_load_si128((const __m128i*)(src + i)));
-    _mm_sfence();
-#else
-    memcpy(dst, src, bytes);
-#endif
-}
-
-// Long-lived loader threads of the file streamer (the reference keeps its loaders alive too, main.cpp:811-958).
-// Creating and retiring a thread costs 40-250 us in a process that has a CUDA context (every stack mmap/munmap
-// passes the driver's MMU notifiers), which at 32 threads was more than the whole read of a 256 MB file.
-struct LoaderPool {
-    std::vector<std::thread> threads;
-    std::mutex m;
-    std::condition_variable cvStart, cvDone;
-    std::function<void(int)> job;
-    std::vector<char*> bounce;        // one cache-resident staging buffer per worker (BOUNCE_BYTES)
-    static constexpr size_t BOUNCE_BYTES = 256 << 10;
-    uint64_t generation = 0;
-    int wanted = 0, running = 0;
-    bool quit = false;
-
-    void worker(int idx) {
-        uint64_t seen = 0;
-        for (;;) {
-            std::function<void(int)> fn;
-            {
-                std::unique_lock<std::mutex> lk(m);
-                cvStart.wait(lk, [&] { return quit || generation != seen; });
-                if (quit) return;
-                seen = generation;
-                if (idx >= wanted) continue;
-                fn = job;
-            }
-            fn(idx);
-            std::lock_guard<std::mutex> lk(m);
-            if (--running == 0) cvDone.notify_all();
-        }
-    }
-    // start n workers on fn; returns at once. fn must stay valid until wait() returns.
-    void run(int n, std::function<void(int)> fn) {
-        while ((int)threads.size() < n) {
-            int idx = (int)threads.size();
-            bounce.push_back((char*)aligned_alloc(64, BOUNCE_BYTES));
-            threads.emplace_back([this, idx] { worker(idx); });
-        }
-        std::lock_guard<std::mutex> lk(m);
-        job = std::move(fn); wanted = n; running = n; generation++;
-        cvStart.notify_all();
-    }
-    void wait() {
-        std::unique_lock<std::mutex> lk(m);
-        cvDone.wait(lk, [&] { return running == 0; });
-    }
-    ~LoaderPool() {
-        { std::lock_guard<std::mutex> lk(m); quit = true; }
-        cvStart.notify_all();
-        for (auto& t : threads) t.join();
-        for (char* b : bounce) free(b);
-    }
-};
+#include "loader_pool.h"
 
 struct SimlodContext {
     CUdevice device = 0;
