@@ -40,11 +40,36 @@ def _newer(target, sources):
     return all(os.path.getmtime(s) <= t for s in sources)
 
 
+def _digest(paths, extra=""):
+    """Content hash of the inputs of a build step: freshness must not depend on mtimes or on the intermediate
+    build/ directory, neither of which survives the trip to the GPU box (the built artefacts and the stamp do)."""
+    import hashlib
+    h = hashlib.sha256(extra.encode())
+    for p in sorted(paths):
+        h.update(os.path.relpath(p, ROOT).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stamp_matches(stamp, digest, artefacts):
+    try:
+        return all(os.path.exists(a) for a in artefacts) and open(stamp).read().strip() == digest
+    except OSError:
+        return False
+
+
 def build_native(force=False, verbose=False):
-    os.makedirs(BUILD, exist_ok=True)
-    os.makedirs(CUBIN_DIR, exist_ok=True)
     headers = [os.path.join(ROOT, "include", "simlod_abi.h"), os.path.join(ROOT, "include", "simlod_b200.h"),
                os.path.join(CSRC, "fpmath.cuh"), os.path.join(CSRC, "loader_pool.h")]
+    sources = [os.path.join(CSRC, name + ".cu") for name in PROGRAMS] + [os.path.join(CSRC, "host.cpp")]
+    digest = _digest(sources + headers, " ".join(ARCH) + " -O3 -lineinfo")
+    stamp = os.path.join(CUBIN_DIR, "BUILD_STAMP")
+    artefacts = [LIB] + [os.path.join(CUBIN_DIR, "simlod_%s.cubin" % name) for name in PROGRAMS]
+    if not force and _stamp_matches(stamp, digest, artefacts):
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    os.makedirs(CUBIN_DIR, exist_ok=True)
     images = []
     for name in PROGRAMS:
         src = os.path.join(CSRC, name + ".cu")
@@ -70,6 +95,8 @@ def build_native(force=False, verbose=False):
             objs.append(o)
         _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I" + os.path.join(CUDA, "include"), host] + objs +
              ["-o", LIB, "-ldl"])
+    with open(stamp, "w") as f:
+        f.write(digest + "\n")
     return LIB
 
 
@@ -79,8 +106,12 @@ def build_oracle(force=False):
     odir = os.path.join(ROOT, "oracle")
     lib = os.path.join(odir, "liboracle.so")
     srcs = [os.path.join(odir, f) for f in ("oracle.cpp",)]
-    if force or not _newer(lib, srcs + [os.path.join(ROOT, "include", "simlod_abi.h")]):
+    odigest = _digest(srcs + [os.path.join(ROOT, "include", "simlod_abi.h")], "-O2 -ffp-contract=off")
+    ostamp = lib + ".stamp"
+    if force or not _stamp_matches(ostamp, odigest, [lib]):
         _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-ffp-contract=off", "-I" + os.path.join(ROOT, "include")] + srcs + ["-o", lib])
+        with open(ostamp, "w") as f:
+            f.write(odigest + "\n")
     ref_root = os.environ.get("SIMLOD_REFERENCE", "/root/reference")
     refdir = os.path.join(odir, "_ref")
     if os.path.isdir(os.path.join(ref_root, "modules", "progressive_octree")):
