@@ -218,7 +218,11 @@ __device__ __forceinline__ T* carve(uint32_t* buffer, uint64_t off) { return rei
 // block has finished its pass it adds each node's count to numVoxels ONCE and patches the entries
 // it wrote with the returned base.
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t VOXTAB_SIZE = 64;
+#ifndef SIMLOD_VOXTAB_SIZE
+#define SIMLOD_VOXTAB_SIZE 64          // tuning knob (tools/exp_variants.py): power of two, <= 256
+#endif
+constexpr uint32_t VOXTAB_SIZE = SIMLOD_VOXTAB_SIZE;
+static_assert((VOXTAB_SIZE & (VOXTAB_SIZE - 1)) == 0 && VOXTAB_SIZE <= 256, "table size must be a power of two that one block can sweep");
 constexpr uint32_t VOXTAB_EMPTY = 0xffffffffu;
 __shared__ uint32_t sh_tabKey[VOXTAB_SIZE];
 __shared__ uint32_t sh_tabCount[VOXTAB_SIZE];
@@ -454,7 +458,11 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
 #else
 #define SIMLOD_TMA 0
 #endif
-constexpr uint32_t TILE_POINTS = 512;
+#ifndef SIMLOD_TILE_POINTS
+#define SIMLOD_TILE_POINTS 512         // tuning knob (tools/exp_variants.py): a multiple of 256
+#endif
+constexpr uint32_t TILE_POINTS = SIMLOD_TILE_POINTS;
+static_assert(TILE_POINTS % 256 == 0 && TILE_POINTS >= 256, "a tile is walked in 256-point steps");
 #if SIMLOD_TMA
 __shared__ __align__(128) uint4 sh_tile[2][TILE_POINTS];
 __shared__ __align__(8) uint64_t sh_tileBar[2];
