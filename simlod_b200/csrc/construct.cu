@@ -466,6 +466,12 @@ static_assert(TILE_POINTS % 256 == 0 && TILE_POINTS >= 256, "a tile is walked in
 #if SIMLOD_TMA
 __shared__ __align__(128) uint4 sh_tile[2][TILE_POINTS];
 __shared__ __align__(8) uint64_t sh_tileBar[2];
+#if defined(SIMLOD_DYNAMIC_TILES)
+constexpr uint32_t MY_TILES_CAP = 64;
+__shared__ uint32_t sh_tileIdx[2];
+__shared__ uint32_t sh_myTiles[MY_TILES_CAP];
+__shared__ uint32_t sh_numMyTiles;
+#endif
 
 __device__ __forceinline__ void tileBarInit() {
     if (threadIdx.x == 0) {
@@ -511,6 +517,46 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
     const uint32_t blockEnd = FRESH ? min(numBatch, blockFirst + perBlock) : numBatch;
     const uint32_t step = FRESH ? blockDim.x : stride;
 #if SIMLOD_TMA
+#if defined(SIMLOD_DYNAMIC_TILES)
+    // EXPERIMENTAL variant (tools/exp_variants.py, not the shipped configuration): tiles are handed out from a global
+    // cursor instead of fixed runs, so a block that draws cheap tiles takes more of them. The block remembers its
+    // tiles for the rank -> slot pass below.
+    if (FRESH) {
+        const uint32_t totalTiles = (numBatch + TILE_POINTS - 1) / TILE_POINTS;
+        uint32_t* cursor = &c.bc->_pad[(SAMPLE && !COUNT) ? 1 : 0];
+        tileBarInit();
+        if (threadIdx.x == 0) {
+            sh_numMyTiles = 0;
+            const uint32_t t0 = atomicAdd(cursor, 1u);
+            sh_tileIdx[0] = t0;
+            if (t0 < totalTiles) tileLoad(0, batch + t0 * TILE_POINTS, min(TILE_POINTS, numBatch - t0 * TILE_POINTS));
+        }
+        for (uint32_t n = 0;; n++) {
+            __syncthreads();                               // sh_tileIdx[n & 1] published; stage (n+1)&1 drained
+            const uint32_t cur = sh_tileIdx[n & 1];
+            if (cur >= totalTiles) break;                  // block-uniform
+            if (threadIdx.x == 0) {
+                const uint32_t nxt = atomicAdd(cursor, 1u);
+                sh_tileIdx[(n + 1) & 1] = nxt;
+                if (nxt < totalTiles) tileLoad((n + 1) & 1, batch + nxt * TILE_POINTS, min(TILE_POINTS, numBatch - nxt * TILE_POINTS));
+                if (sh_numMyTiles < MY_TILES_CAP) sh_myTiles[sh_numMyTiles] = cur; else atomicOr(&c.ctl->errorFlags, ERR_DIR_OVERFLOW);
+                sh_numMyTiles++;
+            }
+            tileWait(n & 1, (n >> 1) & 1);
+            const uint32_t tileFirst = cur * TILE_POINTS, tileEnd = min(numBatch, tileFirst + TILE_POINTS);
+#pragma unroll 1
+            for (uint32_t k = 0; k < TILE_POINTS / 256; k++) {
+                const uint32_t idx = k * 256 + threadIdx.x;
+                const uint32_t i = tileFirst + idx;
+                const bool valid = i < tileEnd;
+                uint4 pt = valid ? sh_tile[n & 1][idx] : make_uint4(0, 0, 0, 0);
+                uint32_t lp = 0, slot = 0;
+                walk<SAMPLE, COUNT>(c, valid, pt, 0, 0, lp, slot);
+                if (valid && COUNT) { c.leafOf[i] = lp; c.slotOf[i] = slot; }
+            }
+        }
+    } else
+#else
     if (FRESH) {
         const uint32_t runLen = blockFirst < blockEnd ? blockEnd - blockFirst : 0u;
         const uint32_t numTiles = (runLen + TILE_POINTS - 1) / TILE_POINTS;
@@ -534,6 +580,7 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
             __syncthreads();
         }
     } else
+#endif
 #endif
     for (uint32_t base = blockFirst + (threadIdx.x - laneId()); base < blockEnd; base += step) {
         uint32_t i = base + laneId();
@@ -576,6 +623,18 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
             if (leaf != VOXTAB_EMPTY && cnt > 0) sh_leafBase[threadIdx.x] = countGlobal(c, leaf, c.nodes[leaf].level, cnt);
         }
         __syncthreads();
+#if SIMLOD_TMA && defined(SIMLOD_DYNAMIC_TILES)
+        if (FRESH) {
+            const uint32_t mine = min(sh_numMyTiles, MY_TILES_CAP);
+            for (uint32_t m = 0; m < mine; m++) {
+                const uint32_t tileFirst = sh_myTiles[m] * TILE_POINTS, tileEnd = min(numBatch, tileFirst + TILE_POINTS);
+                for (uint32_t i = tileFirst + threadIdx.x; i < tileEnd; i += blockDim.x) {
+                    uint32_t sl = c.slotOf[i];
+                    if (sl & PROVISIONAL) c.slotOf[i] = sh_leafBase[tabFind(sh_leafKey, c.leafOf[i] & 0xffffffu)] + (sl & ~PROVISIONAL);
+                }
+            }
+        } else
+#endif
         for (uint32_t base = blockFirst + (threadIdx.x - laneId()); base < blockEnd; base += step) {
             uint32_t i = base + laneId();
             if (i < blockEnd) {
@@ -901,6 +960,9 @@ __device__ void insertAll(const Ctx& c, const Point* batch, uint32_t numBatch, u
 
 __device__ __forceinline__ void clearBatchCounters(BatchCounters* b) {
     b->numSpillTotal = 0; b->numSpilled = 0; b->numBacklog = 0; b->numDirtyLeaves = 0; b->numDirtyVox = 0; b->dirCursor = 0;
+#if defined(SIMLOD_DYNAMIC_TILES)
+    b->_pad[0] = 0; b->_pad[1] = 0;            // tile cursors of the experimental dynamic hand-out
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -25,6 +25,8 @@ KNOBS = {
     "tab128": ["-DSIMLOD_VOXTAB_SIZE=128"],
     "tab32": ["-DSIMLOD_VOXTAB_SIZE=32"],
     "no_tma": ["-DSIMLOD_NO_TMA"],
+    "dyn": ["-DSIMLOD_DYNAMIC_TILES"],                                   # tiles from a global cursor (written blind at the
+    "dyn256": ["-DSIMLOD_DYNAMIC_TILES", "-DSIMLOD_TILE_POINTS=256"],   # end of round 1: never run, parity unknown)
 }
 EXP = os.path.join(ROOT, "tools", "exp")
 os.makedirs(EXP, exist_ok=True)
