@@ -30,8 +30,16 @@ KNOBS = {
 }
 EXP = os.path.join(ROOT, "tools", "exp")
 os.makedirs(EXP, exist_ok=True)
+import hashlib  # noqa: E402
+_h = hashlib.sha256()
+for _f in ("simlod_b200/csrc/construct.cu", "simlod_b200/csrc/fpmath.cuh", "include/simlod_abi.h"):
+    _h.update(open(os.path.join(ROOT, _f), "rb").read())
+SRC_TAG = _h.hexdigest()[:8]                  # variants are rebuilt when the kernel source changes
 for name, flags in KNOBS.items():
-    out = os.path.join(EXP, "knob_%s.cubin" % name)
+    out = os.path.join(EXP, "knob_%s_%s.cubin" % (name, SRC_TAG))
+    for stale in glob.glob(os.path.join(EXP, "knob_%s_*.cubin" % name)):
+        if stale != out:
+            os.remove(stale)
     if not os.path.exists(out):
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-cubin"] + flags + \
               ["-o", out, os.path.join(ROOT, "simlod_b200", "csrc", "construct.cu")]
