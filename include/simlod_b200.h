@@ -144,6 +144,11 @@ int simlod_get_launch_info(SimlodContext* ctx, uint64_t* launches, uint32_t* con
 // MUFU.RCP(x) as the device computes it (the one float a CPU restatement cannot derive when the
 // octree cube size is not a power of two; see oracle/)
 int simlod_device_rcp(SimlodContext* ctx, float x, float* out);
+// Synthetic point streams of the benchmark configurations generated on the device (bench / test
+// infrastructure; restates simlod_b200/data.py, see csrc/gen.cu): points [first, first + count) of an
+// n_total-point stream into device_points. `size` is the cube edge of SIMLOD_GEN_UNIFORM (ignored otherwise).
+enum { SIMLOD_GEN_UNIFORM = 0, SIMLOD_GEN_TERRAIN = 1, SIMLOD_GEN_SHELL = 2 };
+int simlod_generate(SimlodContext* ctx, int kind, uint64_t n_total, uint64_t first, uint64_t count, uint64_t seed, float size, uint64_t device_points);
 // wait for everything this context has enqueued (uploads, decodes, launches)
 int simlod_synchronize(SimlodContext* ctx);
 // flush the L2 cache by overwriting a scratch buffer larger than it (bench hygiene)

@@ -116,7 +116,7 @@ EXPORTS = [
     "simlod_memcpy_htod", "simlod_host_alloc", "simlod_host_free", "simlod_device_alloc", "simlod_device_free",
     "simlod_get_launch_info", "simlod_device_rcp", "simlod_synchronize", "simlod_flush_l2",
     "simlod_partition_count", "simlod_partition_scatter", "simlod_partition_wait",
-    "simlod_export_framebuffer", "simlod_peer_signal", "simlod_composite_framebuffers",
+    "simlod_export_framebuffer", "simlod_peer_signal", "simlod_composite_framebuffers", "simlod_generate",
 ]
 
 _lib = None
@@ -161,6 +161,7 @@ def load_library():
         "simlod_get_launch_info": [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)],
         "simlod_device_rcp": [vp, C.c_float, C.POINTER(C.c_float)],
         "simlod_flush_l2": [vp],
+        "simlod_generate": [vp, C.c_int, u64, u64, u64, u64, C.c_float, u64],
         "simlod_synchronize": [vp],
         "simlod_partition_count": [vp, u64, u32, C.POINTER(PartitionPlan), C.POINTER(u64), C.POINTER(u64)],
         "simlod_partition_scatter": [vp, u64, u32, C.POINTER(PartitionPlan), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), u32],
@@ -431,6 +432,12 @@ class SimLOD:
         out = C.c_float()
         self._check(self._lib.simlod_device_rcp(self._ctx, float(x), C.byref(out)))
         return np.float32(out.value)
+
+    GEN_UNIFORM, GEN_TERRAIN, GEN_SHELL = 0, 1, 2
+
+    def generate(self, kind, device_ptr, n_total, first, count, seed, size=0.0):
+        """Points [first, first+count) of a synthetic n_total-point stream (data.py generators restated on the device)."""
+        self._check(self._lib.simlod_generate(self._ctx, int(kind), int(n_total), int(first), int(count), int(seed), float(size), int(device_ptr)))
 
     def synchronize(self):
         self._check(self._lib.simlod_synchronize(self._ctx))

@@ -21,7 +21,9 @@ NVCC = os.path.join(CUDA, "bin", "nvcc")
 BIN2C = os.path.join(CUDA, "bin", "bin2c")
 LIB = os.path.join(ROOT, "simlod_b200", "libsimlod_b200.so")
 CUBIN_DIR = os.path.join(ROOT, "simlod_b200", "cubin")
-PROGRAMS = ["construct", "render", "reset", "util", "las", "partition"]
+PROGRAMS = ["construct", "render", "reset", "util", "las", "partition", "gen"]
+# gen.cu restates numpy generators in IEEE double arithmetic: no mul+add contraction
+EXTRA_FLAGS = {"gen": ["--fmad=false"]}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -63,7 +65,7 @@ def build_native(force=False, verbose=False):
     headers = [os.path.join(ROOT, "include", "simlod_abi.h"), os.path.join(ROOT, "include", "simlod_b200.h"),
                os.path.join(CSRC, "fpmath.cuh"), os.path.join(CSRC, "loader_pool.h")]
     sources = [os.path.join(CSRC, name + ".cu") for name in PROGRAMS] + [os.path.join(CSRC, "host.cpp")]
-    digest = _digest(sources + headers, " ".join(ARCH) + " -O3 -lineinfo")
+    digest = _digest(sources + headers, " ".join(ARCH) + " -O3 -lineinfo " + repr(sorted(EXTRA_FLAGS.items())))
     stamp = os.path.join(CUBIN_DIR, "BUILD_STAMP")
     artefacts = [LIB] + [os.path.join(CUBIN_DIR, "simlod_%s.cubin" % name) for name in PROGRAMS]
     if not force and _stamp_matches(stamp, digest, artefacts):
@@ -75,7 +77,7 @@ def build_native(force=False, verbose=False):
         src = os.path.join(CSRC, name + ".cu")
         cubin = os.path.join(BUILD, name + ".cubin")
         if force or not _newer(cubin, [src] + headers):
-            out = _run([NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xptxas", "-v", "-cubin", "-o", cubin, src])
+            out = _run([NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xptxas", "-v"] + EXTRA_FLAGS.get(name, []) + ["-cubin", "-o", cubin, src])
             if verbose:
                 print(out)
         shutil.copyfile(cubin, os.path.join(CUBIN_DIR, "simlod_%s.cubin" % name))

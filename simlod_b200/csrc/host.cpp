@@ -40,6 +40,7 @@ extern const unsigned char simlod_cubin_reset[];
 extern const unsigned char simlod_cubin_util[];
 extern const unsigned char simlod_cubin_partition[];
 extern const unsigned char simlod_cubin_las[];
+extern const unsigned char simlod_cubin_gen[];
 }
 
 namespace {
@@ -124,7 +125,8 @@ struct SimlodContext {
     CUsurfObject surface = 0;
     SimlodStats* hStats = nullptr;     // pinned
     Program programs[3];
-    CUmodule utilModule = nullptr, lasModule = nullptr, partitionModule = nullptr;
+    CUmodule utilModule = nullptr, lasModule = nullptr, partitionModule = nullptr, genModule = nullptr;
+    CUfunction fnGenUniform = nullptr, fnGenTerrain = nullptr, fnGenShell = nullptr;
     CUfunction fnPartCount = nullptr, fnPartScan = nullptr, fnPartScatter = nullptr;
     CUfunction fnPartWait = nullptr, fnComposite = nullptr, fnPeerSignal = nullptr;
     CUdeviceptr partScratch = 0;       // spatial exchange: PART_SLOTS x (blockHist | blockBase | totals | cellCounts), then blocksDone, timedOut
@@ -321,6 +323,10 @@ static int createResources(SimlodContext* ctx, const SimlodConfig* config) {
     CU(D(cuModuleGetFunction)(&ctx->fnFill, ctx->utilModule, "simlod_util_fill"));
     CU(D(cuModuleLoadData)(&ctx->lasModule, simlod_cubin_las));
     CU(D(cuModuleGetFunction)(&ctx->fnLas, ctx->lasModule, "simlod_las_decode"));
+    CU(D(cuModuleLoadData)(&ctx->genModule, simlod_cubin_gen));
+    CU(D(cuModuleGetFunction)(&ctx->fnGenUniform, ctx->genModule, "simlod_gen_uniform"));
+    CU(D(cuModuleGetFunction)(&ctx->fnGenTerrain, ctx->genModule, "simlod_gen_terrain"));
+    CU(D(cuModuleGetFunction)(&ctx->fnGenShell, ctx->genModule, "simlod_gen_shell"));
     CU(D(cuModuleLoadData)(&ctx->partitionModule, simlod_cubin_partition));
     CU(D(cuModuleGetFunction)(&ctx->fnPartCount, ctx->partitionModule, "simlod_partition_count"));
     CU(D(cuModuleGetFunction)(&ctx->fnPartScan, ctx->partitionModule, "simlod_partition_scan"));
@@ -417,6 +423,7 @@ void simlod_destroy(SimlodContext* ctx) {
         if (ctx->partitionModule) D(cuModuleUnload)(ctx->partitionModule);
         if (ctx->partScratch) D(cuMemFree)(ctx->partScratch);
         if (ctx->lasModule) D(cuModuleUnload)(ctx->lasModule);
+        if (ctx->genModule) D(cuModuleUnload)(ctx->genModule);
         if (ctx->lasStaging) D(cuMemFree)(ctx->lasStaging);
         delete ctx->loaderPool;          // joins the loader threads
         if (ctx->pinnedPool) D(cuMemFreeHost)(ctx->pinnedPool);
@@ -863,6 +870,27 @@ int simlod_device_rcp(SimlodContext* ctx, float x, float* out) {
     ctx->launches++;
     CU(D(cuStreamSynchronize)(ctx->streamMain));
     CU(D(cuMemcpyDtoH)(out, dst, 4));
+    return SIMLOD_OK;
+}
+
+int simlod_generate(SimlodContext* ctx, int kind, uint64_t n_total, uint64_t first, uint64_t count, uint64_t seed, float size, uint64_t device_points) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    if (!device_points && count) return fail(SIMLOD_ERR_INVALID, "null destination");
+    if (first + count > n_total && kind != SIMLOD_GEN_UNIFORM) return fail(SIMLOD_ERR_INVALID, "range [%llu, %llu) outside the %llu-point stream", (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)n_total);
+    if (count == 0) return SIMLOD_OK;
+    CUdeviceptr dst = (CUdeviceptr)device_points;
+    unsigned blocks = (unsigned)std::min<uint64_t>((count + 255) / 256, (uint64_t)ctx->numSMs * 16);
+    if (kind == SIMLOD_GEN_UNIFORM) {
+        void* args[] = {&dst, &first, &count, &seed, &size};
+        CU(D(cuLaunchKernel)(ctx->fnGenUniform, blocks, 1, 1, 256, 1, 1, 0, ctx->streamMain, args, nullptr));
+    } else if (kind == SIMLOD_GEN_TERRAIN || kind == SIMLOD_GEN_SHELL) {
+        void* args[] = {&dst, &n_total, &first, &count, &seed};
+        CU(D(cuLaunchKernel)(kind == SIMLOD_GEN_TERRAIN ? ctx->fnGenTerrain : ctx->fnGenShell, blocks, 1, 1, 256, 1, 1, 0, ctx->streamMain, args, nullptr));
+    } else {
+        return fail(SIMLOD_ERR_INVALID, "unknown generator %d", kind);
+    }
+    ctx->launches++;
+    CU(D(cuStreamSynchronize)(ctx->streamMain));
     return SIMLOD_OK;
 }
 
