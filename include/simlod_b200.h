@@ -27,6 +27,7 @@ enum {
     SIMLOD_ERR_RING_FULL     = -3,   // all 50 ring slots hold unprocessed batches (back-pressure, main.cpp:820,1012)
     SIMLOD_ERR_MODULE        = -4,   // cubin could not be loaded or lacks the required kernel
     SIMLOD_ERR_CAPACITY      = -5,   // persistent heap almost full: the device stopped consuming batches (Stats::memCapacityReached)
+    SIMLOD_ERR_OVERFLOW      = -6,   // kernel_construct exceeded one of its per-batch capacities (Stats::dbg, sticky until the next reset)
 };
 
 enum {  // the three CUDA programs of main_progressive_octree.cpp:603-626
@@ -64,6 +65,9 @@ int simlod_get_uniforms(SimlodContext* ctx, SimlodUniforms* out);
 
 // resetCUDA (main.cpp:333-361). Also clears nodes[] first (the reference relies on a zeroed allocation).
 int simlod_reset(SimlodContext* ctx);
+// same with an explicit launch shape of the reset kernel; (1, 1) is the reference's own (main.cpp:348-354),
+// simlod_reset uses one 256-thread block per SM (the kernel is grid-stride)
+int simlod_reset_with_grid(SimlodContext* ctx, uint32_t blocks, uint32_t threads);
 
 // spawnUploader's inner step (main.cpp:1033-1056): copy one batch (<= 1 000 000 points) into ring
 // slot (uploaded % 50) on the upload stream, then publish batchSizes[slot] and numBatchesUploaded.

@@ -116,7 +116,7 @@ EXPORTS = [
     "simlod_memcpy_htod", "simlod_host_alloc", "simlod_host_free", "simlod_device_alloc", "simlod_device_free",
     "simlod_get_launch_info", "simlod_device_rcp", "simlod_synchronize", "simlod_flush_l2",
     "simlod_partition_count", "simlod_partition_scatter", "simlod_partition_wait",
-    "simlod_export_framebuffer", "simlod_peer_signal", "simlod_composite_framebuffers", "simlod_generate",
+    "simlod_export_framebuffer", "simlod_peer_signal", "simlod_composite_framebuffers", "simlod_generate", "simlod_reset_with_grid",
 ]
 
 _lib = None
@@ -139,6 +139,7 @@ def load_library():
         "simlod_set_uniforms": [vp, C.POINTER(Uniforms)],
         "simlod_get_uniforms": [vp, C.POINTER(Uniforms)],
         "simlod_reset": [vp],
+        "simlod_reset_with_grid": [vp, u32, u32],
         "simlod_upload_batch": [vp, vp, u32],
         "simlod_upload_batch_device": [vp, u64, u32],
         "simlod_upload_batch_las": [vp, vp, u32, C.POINTER(LasLayout)],
@@ -290,8 +291,12 @@ class SimLOD:
     def use_module(self, program, cubin_path):
         self._check(self._lib.simlod_use_module(self._ctx, program, cubin_path.encode() if cubin_path else None))
 
-    def reset(self):
-        self._check(self._lib.simlod_reset(self._ctx))
+    def reset(self, grid=None):
+        """resetCUDA. grid=(blocks, threads) picks the reset kernel's launch shape; (1, 1) is the reference's."""
+        if grid is None:
+            self._check(self._lib.simlod_reset(self._ctx))
+        else:
+            self._check(self._lib.simlod_reset_with_grid(self._ctx, int(grid[0]), int(grid[1])))
 
     def upload_batch(self, points):
         pts = _as_points(points)

@@ -11,15 +11,19 @@
 //   ------------------------------------------------    ------------------------------------------
 //   3 full passes over the batch (count, voxel-         1 streaming pass (count + voxel-sample fused),
 //   sample, insert), each re-descending the tree        leaf id + slot cached per point (8 B), 1 insert pass
-//   via 64-byte children[] pointer arrays               descent through a 4 B/node first-child table
-//   contiguous-per-thread ranges (uncoalesced)          grid-stride 128-bit coalesced loads
-//   atomicAdd(numPoints) per point at insert            slot = warp-aggregated counter add (no atomics at insert)
-//   chunk lists walked i/1000 hops per point/voxel      per-batch chunk directory: O(1) address per element
+//   via 64-byte children[] pointer arrays               descent through a 4 B/node first-child table,
+//                                                       skipped when the point falls into the thread's last leaf
+//   voxel sampling top-down, one bitmap probe per       bottom-up from the deepest inner node, stops at the first
+//   level of the path (voxels.cu:426-470)               set bit: occupancy bits are nested across levels
+//   contiguous-per-thread ranges (uncoalesced)          TMA-staged contiguous block runs, 128-bit shared loads
+//   atomicAdd(numPoints) per point at insert            slot = block-aggregated counter add (no atomics at insert)
+//   chunk lists walked i/1000 hops per point/voxel      chunk rows / per-batch chunk directory: O(1) address
 //   one thread walks/extends each node's list           tail pointers kept per node; only dirty nodes visited
-//   1 global atomic per created voxel (backlog)         one atomic per warp per level (ballot-aggregated)
-//   >= 24 grid-wide barriers per batch                  3 (+2 per split round)
+//   1 global atomic per created voxel (backlog)         block-local ranks, one add per node per block
+//   >= 24 grid-wide barriers per batch                  1 (+2 per split round): allocation and insertion of
+//                                                       batch b-1 run inside the counting phase of batch b
 //
-// The scratch ("momentary") buffer is carved with our own layout (Scratch below); it fits in
+// The scratch ("momentary") buffer is carved with our own layout (namespace scratch); it fits in
 // the 300 000 000 bytes the unmodified host allocates (main_progressive_octree.cpp:554),
 // unlike the reference's carve-out which needs 408 800 192 (voxels.cu:834-856).
 #include <cooperative_groups.h>
@@ -38,65 +42,70 @@ typedef SimlodHeapHeader Heap;
 struct CudaPrint;   // opaque: the reference's debug channel is a dead parameter (CudaPrint.cuh:51)
 
 // ------------------------------------------------------------------------------------------
-// scratch layout inside the momentary buffer (all offsets 256-byte aligned)
+// scratch layout inside the momentary buffer (all offsets 256-byte aligned). Everything that the
+// insertion of batch b-1 reads while batch b is being counted exists twice (index = batch parity).
 // ------------------------------------------------------------------------------------------
 namespace scratch {
-constexpr uint64_t NODE_CAP       = 263168;            // >= floor(40 000 000 / 152) nodes the host allocates
+constexpr uint64_t NODE_CAP       = 263157;            // floor(40 000 000 / 152): the nodes the host allocates (main.cpp:552-555)
+constexpr uint64_t NODE_TAB       = 263168;            // side-table length (NODE_CAP rounded up)
 constexpr uint64_t MAX_BATCH      = SIMLOD_MAX_BATCH_SIZE;
-constexpr uint64_t SPILL_CAP      = 3ull << 20;        // spilled points per batch (reference re-inserts <= 3 000 001)
+constexpr uint64_t SPILL_CAP      = 3ull << 20;        // spilled points per batch (the reference re-inserts <= 3 000 001, voxels.cu:628)
 constexpr uint64_t ITEM_CAP       = MAX_BATCH + SPILL_CAP;
-constexpr uint64_t VOXEL_CAP      = 8ull << 20;        // voxels created per batch (reference backlog: 10 M)
-constexpr uint64_t DIR_CAP        = 1ull << 20;        // chunk directory entries per batch
-constexpr uint64_t QUEUE_CAP      = 4ull << 20;        // free-chunk stack (reference: 1 M)
+constexpr uint64_t VOXEL_CAP      = 4ull << 20;        // voxels created per batch, per parity
+constexpr uint64_t VOXEL_SHARED   = 512ull << 10;      // tail of the voxel backlog shared by all blocks (overflow of a block's own segment)
+constexpr uint64_t DIR_CAP        = 512ull << 10;      // chunk directory entries per batch, per parity
+constexpr uint64_t QUEUE_CAP      = 2ull << 20;        // free-chunk stack (reference: 1 M)
 constexpr uint64_t SPILLNODE_CAP  = 100000;            // voxels.cu:847
-
 constexpr uint64_t ROW_CAP        = 65536;             // leaves that hold points at the same time (x 64 chunk slots)
 constexpr uint64_t ROW_SLOTS      = 64;                // chunk pointers per leaf row (a leaf holds <= 50 chunks)
-constexpr uint64_t VOXEL_SHARED   = 1ull << 20;        // tail of the voxel backlog shared by all blocks (overflow of a block's own segment)
 constexpr uint64_t BLOCK_CAP      = 4096;              // per-block cursor slots (grid sizes up to 4096 blocks)
 
 constexpr uint64_t align256(uint64_t x) { return (x + 255) & ~255ull; }
 constexpr uint64_t OFF_CTL        = 0;
 constexpr uint64_t OFF_FIRSTCHILD = 4096;
-constexpr uint64_t OFF_GRIDPTR    = align256(OFF_FIRSTCHILD + NODE_CAP * 4);
-constexpr uint64_t OFF_LEAFROW    = align256(OFF_GRIDPTR + NODE_CAP * 8);
-constexpr uint64_t OFF_VTAIL      = align256(OFF_LEAFROW + NODE_CAP * 4);
-constexpr uint64_t OFF_VDIR       = align256(OFF_VTAIL + NODE_CAP * 8);
-constexpr uint64_t OFF_DIRTYLEAF  = align256(OFF_VDIR + NODE_CAP * 8);
-constexpr uint64_t OFF_DIRTYVOX   = align256(OFF_DIRTYLEAF + NODE_CAP * 4);
-constexpr uint64_t OFF_SPILLINFO  = align256(OFF_DIRTYVOX + NODE_CAP * 4);
-constexpr uint64_t OFF_BLOCKCUR   = align256(OFF_SPILLINFO + SPILLNODE_CAP * 32);
-constexpr uint64_t OFF_ROWFREE    = align256(OFF_BLOCKCUR + BLOCK_CAP * 4);
+constexpr uint64_t OFF_PARENT     = align256(OFF_FIRSTCHILD + NODE_TAB * 4);
+constexpr uint64_t OFF_GRIDPTR    = align256(OFF_PARENT + NODE_TAB * 4);
+constexpr uint64_t OFF_LEAFROW    = align256(OFF_GRIDPTR + NODE_TAB * 8);
+constexpr uint64_t OFF_SPLITSTATE = align256(OFF_LEAFROW + NODE_TAB * 4);
+constexpr uint64_t OFF_VTAIL      = align256(OFF_SPLITSTATE + NODE_TAB * 4);
+constexpr uint64_t OFF_VDIR       = align256(OFF_VTAIL + NODE_TAB * 8);
+constexpr uint64_t OFF_DIRTYLEAF  = align256(OFF_VDIR + NODE_TAB * 8);                 // [2]
+constexpr uint64_t OFF_DIRTYVOX   = align256(OFF_DIRTYLEAF + 2 * NODE_TAB * 4);        // [2]
+constexpr uint64_t OFF_SPILLINFO  = align256(OFF_DIRTYVOX + 2 * NODE_TAB * 4);
+constexpr uint64_t OFF_BLOCKCUR   = align256(OFF_SPILLINFO + SPILLNODE_CAP * 32);      // [2]
+constexpr uint64_t OFF_ROWFREE    = align256(OFF_BLOCKCUR + 2 * BLOCK_CAP * 4);
 constexpr uint64_t OFF_ROWS       = align256(OFF_ROWFREE + ROW_CAP * 4);
-constexpr uint64_t OFF_CHUNKDIR   = align256(OFF_ROWS + ROW_CAP * ROW_SLOTS * 8);
-constexpr uint64_t OFF_QUEUE      = align256(OFF_CHUNKDIR + DIR_CAP * 8);
-constexpr uint64_t OFF_LEAFOF     = align256(OFF_QUEUE + QUEUE_CAP * 8);
-constexpr uint64_t OFF_SLOTOF     = align256(OFF_LEAFOF + ITEM_CAP * 4);
-constexpr uint64_t OFF_SPILLED    = align256(OFF_SLOTOF + ITEM_CAP * 4);
-constexpr uint64_t OFF_VKEY       = align256(OFF_SPILLED + SPILL_CAP * 16);
-constexpr uint64_t OFF_VCOLOR     = align256(OFF_VKEY + VOXEL_CAP * 8);
-constexpr uint64_t TOTAL          = align256(OFF_VCOLOR + VOXEL_CAP * 4);
+constexpr uint64_t OFF_CHUNKDIR   = align256(OFF_ROWS + ROW_CAP * ROW_SLOTS * 8);      // [2]
+constexpr uint64_t OFF_QUEUE      = align256(OFF_CHUNKDIR + 2 * DIR_CAP * 8);
+constexpr uint64_t OFF_LEAFOF     = align256(OFF_QUEUE + QUEUE_CAP * 8);               // [2]
+constexpr uint64_t OFF_SLOTOF     = align256(OFF_LEAFOF + 2 * ITEM_CAP * 4);           // [2]
+constexpr uint64_t OFF_SPILLED    = align256(OFF_SLOTOF + 2 * ITEM_CAP * 4);
+constexpr uint64_t OFF_VKEY       = align256(OFF_SPILLED + SPILL_CAP * 16);            // [2]
+constexpr uint64_t OFF_VCOLOR     = align256(OFF_VKEY + 2 * VOXEL_CAP * 8);            // [2]
+constexpr uint64_t TOTAL          = align256(OFF_VCOLOR + 2 * VOXEL_CAP * 4);
 static_assert(TOTAL <= 300000000ull, "scratch must fit the host's 300 MB momentary buffer (main.cpp:554)");
 }  // namespace scratch
 
-enum : uint32_t {   // Ctl::errorFlags, mirrored into Stats::dbg
-    ERR_SPILL_OVERFLOW  = 1u << 0,   // more than SPILL_CAP spilled points in one batch (reference-undefined regime)
-    ERR_VOXEL_OVERFLOW  = 1u << 1,   // more than VOXEL_CAP voxels created in one batch
+enum : uint32_t {   // Ctl::errorFlags, mirrored into Stats::dbg. Sticky: cleared only by a reset (batchletIndex == 0).
+    ERR_SPILL_OVERFLOW  = 1u << 0,   // more than SPILL_CAP spilled points in one batch: a split was postponed (reference-undefined regime)
+    ERR_VOXEL_OVERFLOW  = 1u << 1,   // more than VOXEL_CAP voxels created in one batch: voxels were dropped
     ERR_DIR_OVERFLOW    = 1u << 2,
-    ERR_NODE_OVERFLOW   = 1u << 3,   // nodes[] capacity exceeded
+    ERR_NODE_OVERFLOW   = 1u << 3,   // nodes[] capacity exceeded: a split was refused
     ERR_QUEUE_OVERFLOW  = 1u << 4,
     ERR_SPILLNODE_OVERFLOW = 1u << 5,
-    ERR_ROW_OVERFLOW    = 1u << 6,   // more than ROW_CAP non-empty leaves, or a leaf with more than 64 chunks
+    ERR_ROW_OVERFLOW    = 1u << 6,   // more than ROW_CAP non-empty leaves, or a leaf with more than 64 chunks: points were dropped
+    ERR_FAR_POINT       = 1u << 7,   // a point further than 16 cube edges outside the box (its 2^28 and 2^20 quantisations disagree)
 };
 
-struct BatchCounters {              // one set per batch parity: batch b uses set b & 1, the other one is cleared meanwhile
+struct BatchCounters {              // one set per batch, index = batch % 3; the idle set is cleared during the phase before its use
     uint32_t numSpillTotal;        // spilling nodes found so far in this batch (monotonic)
     uint32_t numSpilled;           // spilled points in this batch
     uint32_t numBacklog;           // voxels of this batch that went to the shared overflow part of the backlog
     uint32_t numDirtyLeaves;
     uint32_t numDirtyVox;
     uint32_t dirCursor;
-    uint32_t _pad[2];
+    uint32_t voxelsCreated;        // voxels of this batch (bound for the capacity guard)
+    uint32_t _pad;
 };
 
 struct Ctl {
@@ -110,11 +119,15 @@ struct Ctl {
     uint64_t voxelsByPass[2];      // @64 voxels created in first-visit passes / in re-walk passes since the last reset
     uint64_t spilledTotal;         // @80 spilled (re-inserted) points since the last reset: the `s` of the roofline's 32*s bytes
     uint64_t voxelsTotal;          // @88 voxels created since the last reset (incl. leaf-root voxels)
-    BatchCounters batch[2];        // @96
-    uint64_t phaseNanos[8];        // @160 time per phase since reset, by the grid's first thread (%globaltimer):
-                                   //      0 count+sample, 1 split round, 2 re-walk, 3 deferred sampling, 4 allocate, 5 insert, 6 stats, 7 launch prologue
+    uint64_t phaseNanos[8];        // @96 time per phase since reset, by the grid's first thread (%globaltimer):
+                                   //     0 fused phase (alloc b-1 | count+sample b | insert b-1), 1 split round, 2 re-walk, 3 deferred sampling,
+                                   //     4 final allocate, 5 final insert + stats, 6 split rounds run, 7 launch prologue
+    BatchCounters batch[3];        // @160
+    uint32_t allocDone;            // @256 blocks that have finished their share of the in-phase allocations of this launch (monotonic)
+    uint32_t _pad[3];
 };
 static_assert(offsetof(Ctl, spilledTotal) == 80, "bench.py reads Ctl::spilledTotal at byte 80");
+static_assert(offsetof(Ctl, phaseNanos) == 96 && offsetof(Ctl, batch) == 160 && offsetof(Ctl, allocDone) == 256, "tools read Ctl by offset");
 
 // what the lane that sees a leaf cross 50 000 records about it (everything the split round needs)
 struct SpillInfo {
@@ -130,33 +143,48 @@ static_assert(sizeof(SpillInfo) == 32, "SpillInfo");
 
 struct DirEntry { uint32_t base; uint32_t k0; };   // chunkDir[base + (slot/1000 - k0)] holds element `slot`
 
+// Everything is addressed from the kernel's own parameters (constant bank) plus compile-time
+// offsets, so the context is a handful of registers and never lives in local memory.
 struct Ctx {
+    uint8_t*   buf;           // momentary buffer
     Node*      nodes;
     Stats*     stats;
-    Heap*      heap;
     uint8_t*   heapBytes;
-    Ctl*       ctl;
-    uint32_t*  firstChild;    // node -> index of child 0 (children are 8 consecutive nodes); 0 = leaf
-    uint64_t*  gridPtr;       // node -> OccupancyGrid* (0 = none)
-    BatchCounters* bc;        // counters of the batch in flight
-    uint32_t*  leafRow;       // leaf -> row of its chunk pointers (+1; 0 = leaf holds no chunk)
-    uint64_t*  rows;          // [ROW_CAP][64] chunk pointers of leaves, in list order
-    uint32_t*  rowFree;       // stack of recycled rows
-    uint64_t*  voxelTail;     // node -> last Chunk* of voxel list  (valid iff node.voxelChunks != 0)
-    DirEntry*  voxelDir;
-    uint32_t*  dirtyLeaves;
-    uint32_t*  dirtyVox;
-    SpillInfo* spill;
-    uint32_t*  blockCursor;   // per block: entries of its own backlog segment filled in this batch
-    uint32_t   segCap;        // entries per block segment
-    uint64_t*  chunkDir;
-    uint64_t*  chunkQueue;
-    uint32_t*  leafOf;        // item -> leaf node | level << 24
-    uint32_t*  slotOf;        // item -> index inside the leaf
-    Point*     spilled;
-    uint64_t*  vkey;          // cell | node << 21 | slot << 41
-    uint32_t*  vcolor;
     float minx, miny, minz, size, rcpSize;
+    uint32_t   segCap;        // backlog entries per block segment
+
+    template <typename T> __device__ __forceinline__ T* at(uint64_t off) const { return reinterpret_cast<T*>(buf + off); }
+    __device__ __forceinline__ Heap*      heap()        const { return reinterpret_cast<Heap*>(heapBytes); }
+    __device__ __forceinline__ Ctl*       ctl()         const { return at<Ctl>(scratch::OFF_CTL); }
+    __device__ __forceinline__ uint32_t*  firstChild()  const { return at<uint32_t>(scratch::OFF_FIRSTCHILD); }   // node -> index of child 0 (8 consecutive nodes); 0 = leaf
+    __device__ __forceinline__ uint32_t*  parentOf()    const { return at<uint32_t>(scratch::OFF_PARENT); }
+    __device__ __forceinline__ uint64_t*  gridPtr()     const { return at<uint64_t>(scratch::OFF_GRIDPTR); }      // node -> OccupancyGrid* (0 = none)
+    __device__ __forceinline__ uint32_t*  leafRow()     const { return at<uint32_t>(scratch::OFF_LEAFROW); }      // leaf -> row of its chunk pointers (+1; 0 = none)
+    __device__ __forceinline__ uint32_t*  splitState()  const { return at<uint32_t>(scratch::OFF_SPLITSTATE); }   // leaf -> 1 once its split has been requested
+    __device__ __forceinline__ uint64_t*  voxelTail()   const { return at<uint64_t>(scratch::OFF_VTAIL); }        // node -> last Chunk* of its voxel list
+    __device__ __forceinline__ DirEntry*  voxelDir()    const { return at<DirEntry>(scratch::OFF_VDIR); }
+    __device__ __forceinline__ uint32_t*  dirtyLeaves(uint32_t p) const { return at<uint32_t>(scratch::OFF_DIRTYLEAF) + p * scratch::NODE_TAB; }
+    __device__ __forceinline__ uint32_t*  dirtyVox(uint32_t p)    const { return at<uint32_t>(scratch::OFF_DIRTYVOX) + p * scratch::NODE_TAB; }
+    __device__ __forceinline__ SpillInfo* spill()       const { return at<SpillInfo>(scratch::OFF_SPILLINFO); }
+    __device__ __forceinline__ uint32_t*  blockCursor(uint32_t p) const { return at<uint32_t>(scratch::OFF_BLOCKCUR) + p * scratch::BLOCK_CAP; }
+    __device__ __forceinline__ uint32_t*  rowFree()     const { return at<uint32_t>(scratch::OFF_ROWFREE); }
+    __device__ __forceinline__ uint64_t*  rows()        const { return at<uint64_t>(scratch::OFF_ROWS); }         // [ROW_CAP][64] chunk pointers of leaves, in list order
+    __device__ __forceinline__ uint64_t*  chunkDir(uint32_t p) const { return at<uint64_t>(scratch::OFF_CHUNKDIR) + p * scratch::DIR_CAP; }
+    __device__ __forceinline__ uint64_t*  chunkQueue()  const { return at<uint64_t>(scratch::OFF_QUEUE); }
+    __device__ __forceinline__ uint32_t*  leafOf(uint32_t p) const { return at<uint32_t>(scratch::OFF_LEAFOF) + p * scratch::ITEM_CAP; }   // item -> leaf node | level << 24
+    __device__ __forceinline__ uint32_t*  slotOf(uint32_t p) const { return at<uint32_t>(scratch::OFF_SLOTOF) + p * scratch::ITEM_CAP; }   // item -> index inside the leaf
+    __device__ __forceinline__ Point*     spilled()     const { return at<Point>(scratch::OFF_SPILLED); }
+    __device__ __forceinline__ uint64_t*  vkey(uint32_t p)   const { return at<uint64_t>(scratch::OFF_VKEY) + p * scratch::VOXEL_CAP; }     // cell | node << 21 | slot << 41
+    __device__ __forceinline__ uint32_t*  vcolor(uint32_t p) const { return at<uint32_t>(scratch::OFF_VCOLOR) + p * scratch::VOXEL_CAP; }
+};
+
+// the batch a pass works on
+struct Batch {
+    const Point* points;     // ring slot
+    uint32_t size;
+    uint32_t index;          // global batch index (Stats::batchletIndex of this batch)
+    uint32_t parity;         // index & 1: which copy of the per-batch arrays
+    BatchCounters* bc;       // &ctl->batch[index % 3]
 };
 
 // ------------------------------------------------------------------------------------------
@@ -164,6 +192,8 @@ struct Ctx {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ldv(const uint32_t* p) { return *(volatile const uint32_t*)p; }
 __device__ __forceinline__ uint64_t ldv(const uint64_t* p) { return *(volatile const uint64_t*)p; }
+__device__ __forceinline__ uint32_t ldcg(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldAcquire(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t lanemaskLt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 __device__ __forceinline__ uint64_t globaltimer() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -194,6 +224,13 @@ __device__ __forceinline__ Coords quantize(const Ctx& c, uint4 pt) {
     q.pZ = fpx::f2u(fpx::mul_ftz(fpx::mul(dz, 268435456.0f), c.rcpSize));
     return q;
 }
+// The occupancy cell of level l is bits [21-l, 28-l) of pX, the child taken at level l is bit 19-l of X. For every
+// point whose two quantisations agree (X == pX >> 8 on the 20 bits the descent uses: true unless the point lies
+// more than 16 cube edges outside the box, where the float -> u32 conversions saturate differently) the cells
+// are nested: same node and same level-l cell  =>  same cell in every ancestor's grid.
+__device__ __forceinline__ bool nested(const Coords& q) {
+    return ((((q.pX >> 8) ^ q.X) | ((q.pY >> 8) ^ q.Y) | ((q.pZ >> 8) ^ q.Z)) & 0xfffffu) == 0;
+}
 // voxels.cu:171-179
 __device__ __forceinline__ uint32_t childIndexAt(const Coords& q, uint32_t level) {
     uint32_t sh = SIMLOD_MAX_DEPTH - 1 - level;
@@ -206,17 +243,37 @@ __device__ __forceinline__ uint32_t cellAt(const Coords& q, uint32_t level) {
     return cx | (cy << 7) | (cz << 14);
 }
 
-template <typename T>
-__device__ __forceinline__ T* carve(uint32_t* buffer, uint64_t off) { return reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(buffer) + off); }
+// ------------------------------------------------------------------------------------------
+// The in-phase allocation handshake. Allocation and insertion of batch b-1 run inside the counting
+// phase of batch b: every block first allocates its share of b-1's dirty nodes and signals, then
+// counts its run of batch b WITHOUT touching anything the allocation reads or writes (leaf counters,
+// numPoints, numVoxels[Stored], rows), and only when all blocks have signalled does it flush its
+// block-local tables into those fields and insert its share of b-1. All blocks of a cooperative
+// launch are co-resident and nobody waits before signalling, so the wait cannot deadlock.
+// ------------------------------------------------------------------------------------------
+__shared__ uint32_t sh_allocTarget;      // value Ctl::allocDone must reach before this block may touch allocation state (0 = no wait)
+__shared__ uint32_t sh_allocSeen;        // set once this block has seen it
+
+__device__ __forceinline__ void waitAllocThread(const Ctx& c) {      // any single thread (slow paths inside the counting loop)
+    const uint32_t target = sh_allocTarget;
+    if (target == 0 || *(volatile uint32_t*)&sh_allocSeen) return;
+    while ((int32_t)(ldAcquire(&c.ctl()->allocDone) - target) < 0) __nanosleep(64);
+    *(volatile uint32_t*)&sh_allocSeen = 1;
+}
+__device__ __forceinline__ void waitAllocBlock(const Ctx& c) {       // whole block, block-uniform
+    if (sh_allocTarget != 0) {
+        if (threadIdx.x == 0) waitAllocThread(c);
+        __syncthreads();
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // block-local voxel bookkeeping. A created voxel needs (a) a slot in its node's voxel list =
 // numVoxels++ and (b) a backlog entry. For a coherent scan these are two very hot global
-// addresses (the upper nodes' counters, the backlog cursor); same-address atomics serialise in L2
-// and were 2/3 of the counting pass. Instead every block owns a segment of the backlog and a
-// 64-entry node -> count table in shared memory; winners take a block-local rank, and when the
-// block has finished its pass it adds each node's count to numVoxels ONCE and patches the entries
-// it wrote with the returned base.
+// addresses (the upper nodes' counters, the backlog cursor); same-address atomics serialise in L2.
+// Instead every block owns a segment of the backlog and a node -> count table in shared memory;
+// winners take a block-local rank, and when the block has finished its pass it adds each node's
+// count to numVoxels ONCE and patches the entries it wrote with the returned base.
 // ------------------------------------------------------------------------------------------
 #ifndef SIMLOD_VOXTAB_SIZE
 #define SIMLOD_VOXTAB_SIZE 64          // tuning knob (tools/exp_variants.py): power of two, <= 256
@@ -230,70 +287,92 @@ __shared__ uint32_t sh_tabBase[VOXTAB_SIZE];
 __shared__ uint32_t sh_cursor;        // next free entry of this block's backlog segment
 __shared__ uint32_t sh_passStart;     // first entry written in the current pass
 
-__device__ __forceinline__ void voxelPassBegin(const Ctx& c, bool firstPassOfBatch) {
+__device__ __forceinline__ uint32_t tabHash(uint32_t key) { return (key * 0x9E3779B1u) >> 26; }
+__device__ __forceinline__ uint32_t tabFind(const uint32_t* keys, uint32_t key) {
+    uint32_t h = tabHash(key);
+#pragma unroll 1
+    for (uint32_t probe = 0; probe < VOXTAB_SIZE; probe++) {
+        uint32_t s = (h + probe) & (VOXTAB_SIZE - 1);
+        uint32_t k = keys[s];
+        if (k == key) return s;
+        if (k == VOXTAB_EMPTY) break;
+    }
+    return VOXTAB_EMPTY;
+}
+__device__ __forceinline__ uint32_t tabInsert(uint32_t* keys, uint32_t key) {
+    uint32_t h = tabHash(key);
+#pragma unroll 1
+    for (uint32_t probe = 0; probe < VOXTAB_SIZE; probe++) {
+        uint32_t s = (h + probe) & (VOXTAB_SIZE - 1);
+        uint32_t k = atomicCAS(&keys[s], VOXTAB_EMPTY, key);
+        if (k == VOXTAB_EMPTY || k == key) return s;
+    }
+    return VOXTAB_EMPTY;
+}
+
+__device__ __forceinline__ void voxelPassBegin(const Ctx& c, const Batch& b, bool firstPassOfBatch) {
     if (threadIdx.x < VOXTAB_SIZE) { sh_tabKey[threadIdx.x] = VOXTAB_EMPTY; sh_tabCount[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) { sh_cursor = firstPassOfBatch ? 0u : c.blockCursor[blockIdx.x]; sh_passStart = sh_cursor; }
-    __syncthreads();
+    if (threadIdx.x == 0) { sh_cursor = firstPassOfBatch ? 0u : c.blockCursor(b.parity)[blockIdx.x]; sh_passStart = sh_cursor; }
 }
 
 // shared fall-back (block table or block segment full): global atomics, final key at once
-__device__ __noinline__ void recordVoxelShared(const Ctx& c, uint32_t node, uint32_t cell, uint32_t color) {
-    uint32_t vslot = atomicAdd(&c.nodes[node].numVoxels, 1u);
-    if (vslot == ldv(&c.nodes[node].numVoxelsStored)) { uint32_t d = atomicAdd(&c.bc->numDirtyVox, 1u); c.dirtyVox[d] = node; }
-    uint32_t b = atomicAdd(&c.bc->numBacklog, 1u);
-    if (b < scratch::VOXEL_SHARED) {
-        uint64_t at = scratch::VOXEL_CAP - scratch::VOXEL_SHARED + b;
-        c.vkey[at] = (uint64_t)cell | ((uint64_t)node << 21) | ((uint64_t)vslot << 41);
-        c.vcolor[at] = color;
+__device__ __noinline__ void recordVoxelShared(const Ctx c, const Batch b, uint32_t node, uint32_t cell, uint32_t color) {
+    waitAllocThread(c);
+    Node* nd = &c.nodes[node];
+    uint32_t vslot = atomicAdd(&nd->numVoxels, 1u);
+    if (vslot == ldv(&nd->numVoxelsStored)) { uint32_t d = atomicAdd(&b.bc->numDirtyVox, 1u); c.dirtyVox(b.parity)[d] = node; }
+    atomicAdd(&b.bc->voxelsCreated, 1u);
+    uint32_t e = atomicAdd(&b.bc->numBacklog, 1u);
+    if (e < scratch::VOXEL_SHARED) {
+        uint64_t at = scratch::VOXEL_CAP - scratch::VOXEL_SHARED + e;
+        c.vkey(b.parity)[at] = (uint64_t)cell | ((uint64_t)node << 21) | ((uint64_t)vslot << 41);
+        c.vcolor(b.parity)[at] = color;
     } else {
-        atomicOr(&c.ctl->errorFlags, ERR_VOXEL_OVERFLOW);
+        atomicOr(&c.ctl()->errorFlags, ERR_VOXEL_OVERFLOW);
     }
 }
 
-__device__ __forceinline__ void recordVoxel(const Ctx& c, uint32_t node, uint32_t cell, uint32_t color) {
-    uint32_t h = (node * 0x9E3779B1u) >> 26;
-    uint32_t slot = VOXTAB_EMPTY;
-    for (uint32_t probe = 0; probe < VOXTAB_SIZE; probe++) {
-        uint32_t s = (h + probe) & (VOXTAB_SIZE - 1);
-        uint32_t k = atomicCAS(&sh_tabKey[s], VOXTAB_EMPTY, node);
-        if (k == VOXTAB_EMPTY || k == node) { slot = s; break; }
-    }
-    if (slot == VOXTAB_EMPTY) { recordVoxelShared(c, node, cell, color); return; }
+__device__ __forceinline__ void recordVoxel(const Ctx& c, const Batch& b, uint32_t node, uint32_t cell, uint32_t color) {
+    uint32_t slot = tabInsert(sh_tabKey, node);
+    if (slot == VOXTAB_EMPTY) { recordVoxelShared(c, b, node, cell, color); return; }
     uint32_t idx = atomicAdd(&sh_cursor, 1u);
-    if (idx >= c.segCap) { recordVoxelShared(c, node, cell, color); return; }
+    if (idx >= c.segCap) { recordVoxelShared(c, b, node, cell, color); return; }
     uint32_t rank = atomicAdd(&sh_tabCount[slot], 1u);
     uint64_t at = (uint64_t)blockIdx.x * c.segCap + idx;
-    c.vkey[at] = (uint64_t)cell | ((uint64_t)slot << 21) | ((uint64_t)rank << 41);      // node/slot patched in voxelPassEnd
-    c.vcolor[at] = color;
+    c.vkey(b.parity)[at] = (uint64_t)cell | ((uint64_t)slot << 21) | ((uint64_t)rank << 41);      // node/slot patched in voxelPassEnd
+    c.vcolor(b.parity)[at] = color;
 }
 
-__device__ __forceinline__ void voxelPassEnd(const Ctx& c, bool freshPass) {
-    __syncthreads();
+// (the caller has synchronised the block after the pass and after waitAllocBlock)
+__device__ __forceinline__ void voxelPassEnd(const Ctx& c, const Batch& b, bool freshPass) {
     if (threadIdx.x < VOXTAB_SIZE) {
         uint32_t node = sh_tabKey[threadIdx.x], cnt = sh_tabCount[threadIdx.x];
         if (node != VOXTAB_EMPTY && cnt > 0) {
-            uint32_t base = atomicAdd(&c.nodes[node].numVoxels, cnt);
-            if (base == ldv(&c.nodes[node].numVoxelsStored)) {           // first voxels of this node in this batch
-                uint32_t d = atomicAdd(&c.bc->numDirtyVox, 1u);
-                c.dirtyVox[d] = node;
+            Node* nd = &c.nodes[node];
+            uint32_t base = atomicAdd(&nd->numVoxels, cnt);
+            if (base == ldv(&nd->numVoxelsStored)) {           // first voxels of this node in this batch
+                uint32_t d = atomicAdd(&b.bc->numDirtyVox, 1u);
+                c.dirtyVox(b.parity)[d] = node;
             }
             sh_tabBase[threadIdx.x] = base;
         }
     }
     __syncthreads();
     const uint32_t endIdx = min(sh_cursor, c.segCap);
+    uint64_t* vkey = c.vkey(b.parity);
     for (uint32_t e = sh_passStart + threadIdx.x; e < endIdx; e += blockDim.x) {
         uint64_t at = (uint64_t)blockIdx.x * c.segCap + e;
-        uint64_t k = c.vkey[at];
+        uint64_t k = vkey[at];
         uint32_t slot = (uint32_t)(k >> 21) & (VOXTAB_SIZE - 1);
         uint32_t rank = (uint32_t)(k >> 41);
-        c.vkey[at] = (k & 0x1fffffull) | ((uint64_t)sh_tabKey[slot] << 21) | ((uint64_t)(sh_tabBase[slot] + rank) << 41);
+        vkey[at] = (k & 0x1fffffull) | ((uint64_t)sh_tabKey[slot] << 21) | ((uint64_t)(sh_tabBase[slot] + rank) << 41);
     }
     if (threadIdx.x == 0) {
-        c.blockCursor[blockIdx.x] = endIdx;
+        c.blockCursor(b.parity)[blockIdx.x] = endIdx;
         if (endIdx > sh_passStart) {
-            atomicAdd(reinterpret_cast<unsigned long long*>(&c.ctl->voxelsTotal), (unsigned long long)(endIdx - sh_passStart));
-            atomicAdd(reinterpret_cast<unsigned long long*>(&c.ctl->voxelsByPass[freshPass ? 0 : 1]), (unsigned long long)(endIdx - sh_passStart));
+            atomicAdd(&b.bc->voxelsCreated, endIdx - sh_passStart);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&c.ctl()->voxelsTotal), (unsigned long long)(endIdx - sh_passStart));
+            atomicAdd(reinterpret_cast<unsigned long long*>(&c.ctl()->voxelsByPass[freshPass ? 0 : 1]), (unsigned long long)(endIdx - sh_passStart));
         }
     }
     __syncthreads();
@@ -312,97 +391,135 @@ constexpr uint32_t PROVISIONAL = 0x80000000u;
 __shared__ uint32_t sh_leafKey[VOXTAB_SIZE];
 __shared__ uint32_t sh_leafCount[VOXTAB_SIZE];
 __shared__ uint32_t sh_leafBase[VOXTAB_SIZE];
+// Bloom filter over the leaves the block's own run of the batch currently sits in: a re-walk round rescans the
+// run only if one of the leaves that split in that round may be among them (a false positive costs a rescan)
+constexpr uint32_t BLOOM_WORDS = 8;
+__shared__ uint32_t sh_runBloom[BLOOM_WORDS];
+__shared__ uint32_t sh_rescan;            // this block rescans its run in the current re-walk pass
+__device__ __forceinline__ void bloomAdd(uint32_t node) { uint32_t h = (node * 0x9E3779B1u) >> 24; atomicOr(&sh_runBloom[h >> 5], 1u << (h & 31u)); }
+__device__ __forceinline__ bool bloomTest(uint32_t node) { uint32_t h = (node * 0x9E3779B1u) >> 24; return (sh_runBloom[h >> 5] >> (h & 31u)) & 1u; }
 
 // the global step: add `cnt` points to a leaf's counter; first-touch and spill detection (voxels.cu:203-218)
-__device__ __noinline__ uint32_t countGlobal(const Ctx& c, uint32_t node, uint32_t level, uint32_t cnt) {
+__device__ __noinline__ uint32_t countGlobal(const Ctx c, const Batch b, uint32_t node, uint32_t level, uint32_t cnt) {
+    waitAllocThread(c);
     Node* leaf = &c.nodes[node];
     uint32_t old = atomicAdd(&leaf->counter, cnt);
     uint32_t stored = ldv(&leaf->numPoints);
     if (old == stored) {                                     // first points of this leaf in this batch
-        uint32_t d = atomicAdd(&c.bc->numDirtyLeaves, 1u);
-        c.dirtyLeaves[d] = node;
+        uint32_t d = atomicAdd(&b.bc->numDirtyLeaves, 1u);
+        c.dirtyLeaves(b.parity)[d] = node;
     }
-    if (old <= SIMLOD_MAX_POINTS_PER_NODE && old + cnt > SIMLOD_MAX_POINTS_PER_NODE) {
-        // this leaf spills (voxels.cu:211-217). Reserve everything its split needs right here, so the
-        // split round is one phase: room in the spill buffer, 8 node slots, the occupancy grid.
-        uint32_t s = atomicAdd(&c.bc->numSpillTotal, 1u);
-        if (s < scratch::SPILLNODE_CAP) {
+    // The leaf spills when its counter crosses 50 000 (voxels.cu:211-217). Exactly one adder wins the request; it
+    // reserves everything the split needs right here, so the split round is one phase: room in the spill buffer,
+    // 8 node slots, the occupancy grid. A split that cannot be served (our capacities, never reached where the
+    // reference itself is defined) is refused as a whole and requested again by the next add to that leaf.
+    if (old + cnt > SIMLOD_MAX_POINTS_PER_NODE && atomicCAS(&c.splitState()[node], 0u, 1u) == 0u) {
+        uint32_t err = 0;
+        const uint32_t childBase = atomicAdd(&c.stats->numNodes, 8u);                                // voxels.cu:317
+        if ((uint64_t)childBase + 8 > scratch::NODE_CAP) { err = ERR_NODE_OVERFLOW; atomicSub(&c.stats->numNodes, 8u); }
+        uint32_t base = 0;
+        if (!err && stored) {
+            base = atomicAdd(&b.bc->numSpilled, stored);
+            if ((uint64_t)base + stored > scratch::SPILL_CAP) { err = ERR_SPILL_OVERFLOW; atomicSub(&b.bc->numSpilled, stored); atomicSub(&c.stats->numNodes, 8u); }
+        }
+        uint32_t s = 0;
+        if (!err) {
+            s = atomicAdd(&b.bc->numSpillTotal, 1u);
+            if (s >= scratch::SPILLNODE_CAP) {
+                err = ERR_SPILLNODE_OVERFLOW; atomicSub(&b.bc->numSpillTotal, 1u);
+                if (stored) atomicSub(&b.bc->numSpilled, stored);
+                atomicSub(&c.stats->numNodes, 8u);
+            }
+        }
+        if (err) {
+            atomicOr(&c.ctl()->errorFlags, err);
+            atomicExch(&c.splitState()[node], 0u);
+        } else {
             SpillInfo info;
             info.node = node;
             info.stored = stored;
             info.level = level;
-            info.row = c.leafRow[node];
-            info.base = stored ? atomicAdd(&c.bc->numSpilled, stored) : 0u;
-            if ((uint64_t)info.base + stored > scratch::SPILL_CAP) atomicOr(&c.ctl->errorFlags, ERR_SPILL_OVERFLOW);
-            info.childBase = atomicAdd(&c.stats->numNodes, 8u);                                // voxels.cu:317
-            if (info.childBase + 8 > scratch::NODE_CAP) atomicOr(&c.ctl->errorFlags, ERR_NODE_OVERFLOW);
-            uint64_t g = c.gridPtr[node];
-            if (g == 0) g = (uint64_t)(c.heapBytes + atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)SIMLOD_GRID_STRIDE));   // voxels.cu:363-365
+            info.row = c.leafRow()[node];
+            info.base = base;
+            info.childBase = childBase;
+            uint64_t g = c.gridPtr()[node];
+            if (g == 0) g = (uint64_t)(c.heapBytes + atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap()->offset), (unsigned long long)SIMLOD_GRID_STRIDE));   // voxels.cu:363-365
             info.grid = g;
-            c.spill[s] = info;
-        } else {
-            atomicOr(&c.ctl->errorFlags, ERR_SPILLNODE_OVERFLOW);
+            c.spill()[s] = info;
         }
     }
     return old;
 }
 
-__device__ __forceinline__ uint32_t tabFind(const uint32_t* keys, uint32_t key) {
-    uint32_t h = (key * 0x9E3779B1u) >> 26;
-    for (uint32_t probe = 0; probe < VOXTAB_SIZE; probe++) {
-        uint32_t s = (h + probe) & (VOXTAB_SIZE - 1);
-        uint32_t k = keys[s];
-        if (k == key) return s;
-        if (k == VOXTAB_EMPTY) break;
-    }
-    return VOXTAB_EMPTY;
-}
-__device__ __forceinline__ uint32_t tabInsert(uint32_t* keys, uint32_t key) {
-    uint32_t h = (key * 0x9E3779B1u) >> 26;
-    for (uint32_t probe = 0; probe < VOXTAB_SIZE; probe++) {
-        uint32_t s = (h + probe) & (VOXTAB_SIZE - 1);
-        uint32_t k = atomicCAS(&keys[s], VOXTAB_EMPTY, key);
-        if (k == VOXTAB_EMPTY || k == key) return s;
-    }
-    return VOXTAB_EMPTY;
-}
+// ------------------------------------------------------------------------------------------
+// the per-point walk. Warp-synchronous: all 32 lanes call it together, `valid` masks lanes
+// without an item.
+//   descent : voxels.cu:145-187 from (node, level) to the leaf through the first-child table — skipped when
+//             the point falls into the leaf this thread found last (a scan is coherent: nearly always)
+//   sample  : voxels.cu:426-470 + 50-121. The reference probes the grid of every node on the path, root first.
+//             Occupancy bits are nested (see nested()): if the point's cell is set in a node it is set in all its
+//             ancestors, or will be before the pass ends by the thread that set it. So the walk goes UP from the
+//             deepest inner node and stops at the first set bit: one probe per point plus one per created voxel.
+//   count   : voxels.cu:203-218 (doCounting::countPoint)
+// ------------------------------------------------------------------------------------------
+struct LeafCache { uint32_t node, level, kx, ky, kz, parent; };      // node == VOXTAB_EMPTY: nothing cached
 
-// ------------------------------------------------------------------------------------------
-// the per-point walk: descend from (node, level) to the leaf; optionally voxel-sample every
-// node on the way that owns an occupancy grid; optionally count the point into the leaf.
-// Warp-synchronous: all 32 lanes call it together, `valid` masks lanes without an item.
-//   count : voxels.cu:145-220 (doCounting::countPoint)     sample: voxels.cu:426-470 + 50-121
-// ------------------------------------------------------------------------------------------
-template <bool SAMPLE, bool COUNT>
-__device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_t node, uint32_t level,
-                                     uint32_t& leafPacked, uint32_t& slot) {
+template <bool SAMPLE, bool COUNT, bool UNCACHED_GRID>
+__device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& cache, bool valid, uint4 pt, uint32_t node, uint32_t level,
+                                     uint32_t stopLevel, bool runItem, uint32_t& leafPacked, uint32_t& slot) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = laneId();
     const uint32_t ltmask = lanemaskLt();
     Coords q = quantize(c, pt);
-    // per-lane descent (no warp-level synchronisation inside: voxel bookkeeping is block-local).
-    // atomicOr results are not needed to continue the descent, so up to 3 of them stay in flight
-    // per lane and are only looked at when the leaf has been reached (or a 4th one is issued).
-    uint32_t pending = 0;
-    uint32_t old0 = 0, old1 = 0, old2 = 0, key0 = 0, key1 = 0, key2 = 0;      // key = node | (cell & 31) << 20 ... see below
-    uint32_t cel0 = 0, cel1 = 0, cel2 = 0;
-    auto settle = [&]() {
-        if (pending > 0 && (old0 & (1u << (cel0 & 31u))) == 0) recordVoxel(c, key0, cel0, pt.w);
-        if (pending > 1 && (old1 & (1u << (cel1 & 31u))) == 0) recordVoxel(c, key1, cel1, pt.w);
-        if (pending > 2 && (old2 & (1u << (cel2 & 31u))) == 0) recordVoxel(c, key2, cel2, pt.w);
-        pending = 0;
-    };
+    uint32_t parent = VOXTAB_EMPTY;
     if (valid) {
-        for (;;) {
-            if (level >= SIMLOD_MAX_DEPTH) break;                       // voxels.cu:169 loop bound: a level-20 node is the leaf
-            if (SAMPLE) {
-                uint64_t g = c.gridPtr[node];
+        const uint32_t mx = q.X & 0xfffffu, my = q.Y & 0xfffffu, mz = q.Z & 0xfffffu;
+        const uint32_t csh = SIMLOD_MAX_DEPTH - cache.level;
+        if (cache.node != VOXTAB_EMPTY && (mx >> csh) == cache.kx && (my >> csh) == cache.ky && (mz >> csh) == cache.kz) {
+            node = cache.node; level = cache.level; parent = cache.parent;
+        } else {
+            const uint32_t* firstChild = c.firstChild();
+            for (;;) {
+                if (level >= SIMLOD_MAX_DEPTH) break;                       // voxels.cu:169 loop bound: a level-20 node is the leaf
+                uint32_t fc = firstChild[node];
+                if (fc == 0) break;
+                parent = node;
+                node = fc + childIndexAt(q, level);
+                level++;
+            }
+            if (parent == VOXTAB_EMPTY && level > 0) parent = c.parentOf()[node];
+            const uint32_t sh = SIMLOD_MAX_DEPTH - level;
+            cache.node = node; cache.level = level; cache.parent = parent;
+            cache.kx = mx >> sh; cache.ky = my >> sh; cache.kz = mz >> sh;
+        }
+        if (SAMPLE) {
+            // nodes with a grid on the path: the inner nodes, and the root even while it is a leaf (reset.cu:69)
+            uint32_t sNode = level == 0 ? node : parent;
+            uint32_t sLevel = level == 0 ? 0u : level - 1;
+            const bool exhaustive = !nested(q);          // far outside the box: probe every level like the reference does
+            if (exhaustive) atomicOr(&c.ctl()->errorFlags, ERR_FAR_POINT);
+            // atomicOr results are not needed to continue upwards (a speculative probe of the level above is always
+            // correct: every cell has exactly one winner), so up to 3 stay in flight per lane
+            uint32_t pending = 0;
+            uint32_t old0 = 0, old1 = 0, old2 = 0, key0 = 0, key1 = 0, key2 = 0, cel0 = 0, cel1 = 0, cel2 = 0;
+            auto settle = [&]() {
+                if (pending > 0 && (old0 & (1u << (cel0 & 31u))) == 0) recordVoxel(c, b, key0, cel0, pt.w);
+                if (pending > 1 && (old1 & (1u << (cel1 & 31u))) == 0) recordVoxel(c, b, key1, cel1, pt.w);
+                if (pending > 2 && (old2 & (1u << (cel2 & 31u))) == 0) recordVoxel(c, b, key2, cel2, pt.w);
+                pending = 0;
+            };
+            const uint64_t* gridPtr = c.gridPtr();
+            for (;;) {
+                uint64_t g = gridPtr[sNode];
+                bool goUp = exhaustive;
                 if (g != 0) {
-                    uint32_t cell = cellAt(q, level);
+                    uint32_t cell = cellAt(q, sLevel);
                     uint32_t* word = reinterpret_cast<uint32_t*>(g) + (cell >> 5);
                     uint32_t bit = 1u << (cell & 31u);
-                    // non-atomic pre-test (voxels.cu:93-94): a set bit seen through the (non-coherent) L1 is final
-                    uint32_t seen = *word;
+                    // non-atomic pre-test (voxels.cu:93-94): bits are only ever set while a grid is live, so a set bit seen
+                    // through the (non-coherent) L1 is final. The root's grid is cleared in place when the root splits
+                    // (voxels.cu:370-382): the one pass that follows such a clear reads through L2 instead.
+                    uint32_t seen = UNCACHED_GRID ? ldcg(word) : *word;
                     if ((seen & bit) == 0) {
                         // neighbouring points hit the same cell: one atomic per distinct cell among the converged lanes
                         uint32_t active = __activemask();
@@ -410,20 +527,20 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
                         if (lane == (uint32_t)__ffs(peers) - 1u) {
                             if (pending == 3) settle();
                             uint32_t old = atomicOr(word, bit);
-                            if (pending == 0) { old0 = old; key0 = node; cel0 = cell; }
-                            else if (pending == 1) { old1 = old; key1 = node; cel1 = cell; }
-                            else { old2 = old; key2 = node; cel2 = cell; }
+                            if (pending == 0) { old0 = old; key0 = sNode; cel0 = cell; }
+                            else if (pending == 1) { old1 = old; key1 = sNode; cel1 = cell; }
+                            else { old2 = old; key2 = sNode; cel2 = cell; }
                             pending++;
+                            goUp = true;
                         }
                     }
                 }
+                if (!goUp || sLevel <= stopLevel) break;
+                sNode = c.parentOf()[sNode];
+                sLevel--;
             }
-            uint32_t fc = c.firstChild[node];
-            if (fc == 0) break;
-            node = fc + childIndexAt(q, level);
-            level++;
+            settle();
         }
-        if (SAMPLE) settle();
     }
     __syncwarp();
 
@@ -438,7 +555,8 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
             if (lane == leader) {
                 uint32_t t = tabInsert(sh_leafKey, node);
                 if (t != VOXTAB_EMPTY) r = atomicAdd(&sh_leafCount[t], cnt) | PROVISIONAL;     // block-local rank
-                else                   r = countGlobal(c, node, level, cnt);                    // table full: final slot at once
+                else                   r = countGlobal(c, b, node, level, cnt);                // table full: final slot at once
+                if (runItem) bloomAdd(node);
             }
             r = __shfl_sync(peers, r, leader);
             slot = r + __popc(peers & ltmask);
@@ -448,37 +566,27 @@ __device__ __forceinline__ void walk(const Ctx& c, bool valid, uint4 pt, uint32_
 
 // ------------------------------------------------------------------------------------------
 // TMA staging of the batch. In a first-visit pass every block streams its contiguous run of the
-// batch through two 8 KB shared-memory stages with 1-D bulk copies (cp.async.bulk ... mbarrier::
-// complete_tx, SASS: UBLKCP): one elected thread issues the copy of the next 512-point tile while
-// the block walks the current one, so the HBM latency of the batch read leaves the critical path
-// and no registers or LSU slots are spent on it. Threads then read their point with one LDS.128.
+// batch through two shared-memory stages with 1-D bulk copies (cp.async.bulk ... mbarrier::
+// complete_tx, SASS: UBLKCP): one elected thread issues the copy of the next tile while the block
+// walks the current one, so the HBM latency of the batch read leaves the critical path and no
+// registers or LSU slots are spent on it. Threads then read their point with one LDS.128.
 // ------------------------------------------------------------------------------------------
-#ifndef SIMLOD_NO_TMA
-#define SIMLOD_TMA 1
-#else
-#define SIMLOD_TMA 0
-#endif
 #ifndef SIMLOD_TILE_POINTS
-#define SIMLOD_TILE_POINTS 512         // tuning knob (tools/exp_variants.py): a multiple of 256
+#define SIMLOD_TILE_POINTS 512         // tuning knob: a multiple of 256
 #endif
 constexpr uint32_t TILE_POINTS = SIMLOD_TILE_POINTS;
 static_assert(TILE_POINTS % 256 == 0 && TILE_POINTS >= 256, "a tile is walked in 256-point steps");
-#if SIMLOD_TMA
 __shared__ __align__(128) uint4 sh_tile[2][TILE_POINTS];
 __shared__ __align__(8) uint64_t sh_tileBar[2];
-#if defined(SIMLOD_DYNAMIC_TILES)
-constexpr uint32_t MY_TILES_CAP = 64;
-__shared__ uint32_t sh_tileIdx[2];
-__shared__ uint32_t sh_myTiles[MY_TILES_CAP];
-__shared__ uint32_t sh_numMyTiles;
-#endif
+__shared__ uint32_t sh_tilePhase[2];       // parity the next wait on each stage has to see (the barriers live for the whole launch)
 
-__device__ __forceinline__ void tileBarInit() {
+__device__ __forceinline__ void tileBarInit() {      // once per launch
     if (threadIdx.x == 0) {
         uint32_t b0 = (uint32_t)__cvta_generic_to_shared(&sh_tileBar[0]), b1 = (uint32_t)__cvta_generic_to_shared(&sh_tileBar[1]);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b0) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sh_tilePhase[0] = 0; sh_tilePhase[1] = 0;
     }
     __syncthreads();
 }
@@ -498,75 +606,57 @@ __device__ __forceinline__ void tileWait(uint32_t stage, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
-#endif
 
-// one pass over batch points (ring slot) followed by the spilled points of this batch
+// the contiguous run of the batch a block owns in every pass over it
+__device__ __forceinline__ void blockRun(uint32_t numBatch, uint32_t& first, uint32_t& end) {
+    const uint32_t perBlock = ((numBatch + gridDim.x - 1) / gridDim.x + 31u) & ~31u;
+    first = min(numBatch, blockIdx.x * perBlock);
+    end = min(numBatch, first + perBlock);
+}
+
+// ------------------------------------------------------------------------------------------
+// one pass over the batch points (ring slot) followed by the spilled points of this batch
 //   FRESH  : items start at the root (first visit); otherwise only items whose cached leaf has
 //            been split since are walked on, starting at that (now inner) node
-template <bool SAMPLE, bool COUNT, bool FRESH>
-__device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, uint32_t numSpilled) {
+//   the table flush (leaf counters, voxel counters) is left to the caller: passFlush()
+// ------------------------------------------------------------------------------------------
+template <bool SAMPLE, bool COUNT, bool FRESH, bool UNCACHED_GRID>
+__device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t numSpilled, uint32_t spillBegin, uint32_t spillEnd) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t* leafOf = c.leafOf(b.parity);
+    uint32_t* slotOf = c.slotOf(b.parity);
+    uint32_t blockFirst, blockEnd;
+    blockRun(b.size, blockFirst, blockEnd);
+    LeafCache cache;
+    cache.node = VOXTAB_EMPTY; cache.level = 0; cache.kx = cache.ky = cache.kz = 0; cache.parent = VOXTAB_EMPTY;
+
+    // re-walk rounds: can the block's run hold an item whose leaf was split in the round that just ended?
+    bool rescan = false;
+    if (!FRESH) {
+        if (threadIdx.x == 0) sh_rescan = 0;
+        __syncthreads();
+        for (uint32_t k = spillBegin + threadIdx.x; k < spillEnd; k += blockDim.x)
+            if (bloomTest(c.spill()[k].node)) sh_rescan = 1u;
+        __syncthreads();
+        rescan = sh_rescan != 0;
+    }
+    if ((FRESH && COUNT) || rescan) { if (threadIdx.x < BLOOM_WORDS) sh_runBloom[threadIdx.x] = 0; }     // rebuilt by this pass
     if (COUNT && threadIdx.x < VOXTAB_SIZE) { sh_leafKey[threadIdx.x] = VOXTAB_EMPTY; sh_leafCount[threadIdx.x] = 0; }
-    if (SAMPLE) voxelPassBegin(c, FRESH); else __syncthreads();
-    // batch points: every block owns one contiguous run of the batch (scans are spatially coherent, so
-    // all iterations of a block revisit the same upper-level nodes and occupancy words: L1 hits)
-    // (re-walk passes touch a few contiguous runs of items, so they stay grid-strided to spread those runs)
-    const uint32_t perBlock = FRESH ? (((numBatch + gridDim.x - 1) / gridDim.x + 31u) & ~31u) : numBatch;
-    const uint32_t blockFirst = FRESH ? blockIdx.x * perBlock : blockIdx.x * blockDim.x;
-    const uint32_t blockEnd = FRESH ? min(numBatch, blockFirst + perBlock) : numBatch;
-    const uint32_t step = FRESH ? blockDim.x : stride;
-#if SIMLOD_TMA
-#if defined(SIMLOD_DYNAMIC_TILES)
-    // EXPERIMENTAL variant (tools/exp_variants.py, not the shipped configuration): tiles are handed out from a global
-    // cursor instead of fixed runs, so a block that draws cheap tiles takes more of them. The block remembers its
-    // tiles for the rank -> slot pass below.
+    if (SAMPLE) voxelPassBegin(c, b, FRESH);
+    __syncthreads();
+
     if (FRESH) {
-        const uint32_t totalTiles = (numBatch + TILE_POINTS - 1) / TILE_POINTS;
-        uint32_t* cursor = &c.bc->_pad[(SAMPLE && !COUNT) ? 1 : 0];
-        tileBarInit();
-        if (threadIdx.x == 0) {
-            sh_numMyTiles = 0;
-            const uint32_t t0 = atomicAdd(cursor, 1u);
-            sh_tileIdx[0] = t0;
-            if (t0 < totalTiles) tileLoad(0, batch + t0 * TILE_POINTS, min(TILE_POINTS, numBatch - t0 * TILE_POINTS));
-        }
-        for (uint32_t n = 0;; n++) {
-            __syncthreads();                               // sh_tileIdx[n & 1] published; stage (n+1)&1 drained
-            const uint32_t cur = sh_tileIdx[n & 1];
-            if (cur >= totalTiles) break;                  // block-uniform
-            if (threadIdx.x == 0) {
-                const uint32_t nxt = atomicAdd(cursor, 1u);
-                sh_tileIdx[(n + 1) & 1] = nxt;
-                if (nxt < totalTiles) tileLoad((n + 1) & 1, batch + nxt * TILE_POINTS, min(TILE_POINTS, numBatch - nxt * TILE_POINTS));
-                if (sh_numMyTiles < MY_TILES_CAP) sh_myTiles[sh_numMyTiles] = cur; else atomicOr(&c.ctl->errorFlags, ERR_DIR_OVERFLOW);
-                sh_numMyTiles++;
-            }
-            tileWait(n & 1, (n >> 1) & 1);
-            const uint32_t tileFirst = cur * TILE_POINTS, tileEnd = min(numBatch, tileFirst + TILE_POINTS);
-#pragma unroll 1
-            for (uint32_t k = 0; k < TILE_POINTS / 256; k++) {
-                const uint32_t idx = k * 256 + threadIdx.x;
-                const uint32_t i = tileFirst + idx;
-                const bool valid = i < tileEnd;
-                uint4 pt = valid ? sh_tile[n & 1][idx] : make_uint4(0, 0, 0, 0);
-                uint32_t lp = 0, slot = 0;
-                walk<SAMPLE, COUNT>(c, valid, pt, 0, 0, lp, slot);
-                if (valid && COUNT) { c.leafOf[i] = lp; c.slotOf[i] = slot; }
-            }
-        }
-    } else
-#else
-    if (FRESH) {
-        const uint32_t runLen = blockFirst < blockEnd ? blockEnd - blockFirst : 0u;
+        const uint32_t runLen = blockEnd - blockFirst;
         const uint32_t numTiles = (runLen + TILE_POINTS - 1) / TILE_POINTS;
-        tileBarInit();
-        if (threadIdx.x == 0 && numTiles > 0) tileLoad(0, batch + blockFirst, min(TILE_POINTS, runLen));
+        uint32_t ph0 = sh_tilePhase[0], ph1 = sh_tilePhase[1];
+        __syncthreads();
+        if (threadIdx.x == 0 && numTiles > 0) tileLoad(0, b.points + blockFirst, min(TILE_POINTS, runLen));
         for (uint32_t t = 0; t < numTiles; t++) {
             const uint32_t tileFirst = blockFirst + t * TILE_POINTS;
             if (threadIdx.x == 0 && t + 1 < numTiles)      // stage (t+1)&1 was drained at the barrier that ended iteration t-1
-                tileLoad((t + 1) & 1, batch + tileFirst + TILE_POINTS, min(TILE_POINTS, blockEnd - (tileFirst + TILE_POINTS)));
-            tileWait(t & 1, (t >> 1) & 1);
+                tileLoad((t + 1) & 1, b.points + tileFirst + TILE_POINTS, min(TILE_POINTS, blockEnd - (tileFirst + TILE_POINTS)));
+            if (t & 1) { tileWait(1, ph1); ph1 ^= 1; } else { tileWait(0, ph0); ph0 ^= 1; }
 #pragma unroll 1
             for (uint32_t k = 0; k < TILE_POINTS / 256; k++) {
                 const uint32_t idx = k * 256 + threadIdx.x;
@@ -574,29 +664,34 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
                 const bool valid = i < blockEnd;
                 uint4 pt = valid ? sh_tile[t & 1][idx] : make_uint4(0, 0, 0, 0);
                 uint32_t lp = 0, slot = 0;
-                walk<SAMPLE, COUNT>(c, valid, pt, 0, 0, lp, slot);
-                if (valid && COUNT) { c.leafOf[i] = lp; c.slotOf[i] = slot; }
+                walk<SAMPLE, COUNT, UNCACHED_GRID>(c, b, cache, valid, pt, 0, 0, 0, true, lp, slot);
+                if (valid && COUNT) { leafOf[i] = lp; slotOf[i] = slot; }
             }
             __syncthreads();
         }
-    } else
-#endif
-#endif
-    for (uint32_t base = blockFirst + (threadIdx.x - laneId()); base < blockEnd; base += step) {
-        uint32_t i = base + laneId();
-        bool valid = i < blockEnd;
-        uint32_t node = 0, level = 0;
-        if (!FRESH && valid) {
-            uint32_t lp = c.leafOf[i];
-            node = lp & 0xffffffu; level = lp >> 24;
-            valid = c.firstChild[node] != 0 && level < SIMLOD_MAX_DEPTH;
+        if (threadIdx.x == 0) { sh_tilePhase[0] = ph0; sh_tilePhase[1] = ph1; }
+    } else if (rescan) {
+        for (uint32_t base = blockFirst + (threadIdx.x - laneId()); base < blockEnd; base += blockDim.x) {
+            uint32_t i = base + laneId();
+            bool valid = i < blockEnd;
+            uint32_t node = 0, level = 0;
+            if (valid) {
+                uint32_t lp = leafOf[i];
+                node = lp & 0xffffffu; level = lp >> 24;
+                const bool moved = c.firstChild()[node] != 0 && level < SIMLOD_MAX_DEPTH;
+                if (!moved) {                                // stays where it is: keep its leaf in the run's filter
+                    uint32_t peers = __match_any_sync(__activemask(), node);
+                    if (laneId() == (uint32_t)__ffs(peers) - 1u) bloomAdd(node);
+                }
+                valid = moved;
+            }
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            uint4 pt = make_uint4(0, 0, 0, 0);
+            if (valid) pt = ldPoint(b.points + i);
+            uint32_t lp = 0, slot = 0;
+            walk<SAMPLE, COUNT, UNCACHED_GRID>(c, b, cache, valid, pt, node, level, level, true, lp, slot);
+            if (valid && COUNT) { leafOf[i] = lp; slotOf[i] = slot; }
         }
-        if (!FRESH && !__any_sync(0xffffffffu, valid)) continue;
-        uint4 pt = make_uint4(0, 0, 0, 0);
-        if (valid) pt = ldPoint(batch + i);
-        uint32_t lp = 0, slot = 0;
-        walk<SAMPLE, COUNT>(c, valid, pt, node, level, lp, slot);
-        if (valid && COUNT) { c.leafOf[i] = lp; c.slotOf[i] = slot; }
     }
     // spilled points (always carry a cached start node: the leaf they were spilled from)
     for (uint32_t base = tid - laneId(); base < numSpilled; base += stride) {
@@ -604,85 +699,97 @@ __device__ void itemPass(const Ctx& c, const Point* batch, uint32_t numBatch, ui
         bool valid = j < numSpilled;
         uint32_t node = 0, level = 0;
         if (valid && !(FRESH && !COUNT)) {       // sampling-only fresh pass restarts at the root
-            uint32_t lp = c.leafOf[scratch::MAX_BATCH + j];
+            uint32_t lp = leafOf[scratch::MAX_BATCH + j];
             node = lp & 0xffffffu; level = lp >> 24;
-            valid = c.firstChild[node] != 0 && level < SIMLOD_MAX_DEPTH;
+            valid = c.firstChild()[node] != 0 && level < SIMLOD_MAX_DEPTH;
         }
+        if (!__any_sync(0xffffffffu, valid)) continue;
         uint4 pt = make_uint4(0, 0, 0, 0);
-        if (valid) pt = *reinterpret_cast<const uint4*>(c.spilled + j);
+        if (valid) pt = *reinterpret_cast<const uint4*>(c.spilled() + j);
         uint32_t lp = 0, slot = 0;
-        walk<SAMPLE, COUNT>(c, valid, pt, node, level, lp, slot);
-        if (valid && COUNT) { c.leafOf[scratch::MAX_BATCH + j] = lp; c.slotOf[scratch::MAX_BATCH + j] = slot; }
+        walk<SAMPLE, COUNT, UNCACHED_GRID>(c, b, cache, valid, pt, node, level, level, false, lp, slot);
+        if (valid && COUNT) { leafOf[scratch::MAX_BATCH + j] = lp; slotOf[scratch::MAX_BATCH + j] = slot; }
     }
-    if (SAMPLE) voxelPassEnd(c, FRESH);
+    __syncthreads();
+}
+
+// flush the block's tables after passItems: one global add per distinct leaf / voxel node, then provisional
+// ranks -> slots. Must run after waitAllocBlock() when an allocation is in flight.
+template <bool SAMPLE, bool COUNT, bool FRESH>
+__device__ __forceinline__ void passFlush(const Ctx& c, const Batch& b, uint32_t numSpilled) {
+    if (SAMPLE) voxelPassEnd(c, b, FRESH);
     if (COUNT) {
-        // flush the block's leaf table: one global add per distinct leaf, then provisional ranks -> slots
-        __syncthreads();
+        const uint32_t stride = gridDim.x * blockDim.x;
+        const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t* leafOf = c.leafOf(b.parity);
+        uint32_t* slotOf = c.slotOf(b.parity);
         if (threadIdx.x < VOXTAB_SIZE) {
             uint32_t leaf = sh_leafKey[threadIdx.x], cnt = sh_leafCount[threadIdx.x];
-            if (leaf != VOXTAB_EMPTY && cnt > 0) sh_leafBase[threadIdx.x] = countGlobal(c, leaf, c.nodes[leaf].level, cnt);
+            if (leaf != VOXTAB_EMPTY && cnt > 0) sh_leafBase[threadIdx.x] = countGlobal(c, b, leaf, c.nodes[leaf].level, cnt);
         }
         __syncthreads();
-#if SIMLOD_TMA && defined(SIMLOD_DYNAMIC_TILES)
-        if (FRESH) {
-            const uint32_t mine = min(sh_numMyTiles, MY_TILES_CAP);
-            for (uint32_t m = 0; m < mine; m++) {
-                const uint32_t tileFirst = sh_myTiles[m] * TILE_POINTS, tileEnd = min(numBatch, tileFirst + TILE_POINTS);
-                for (uint32_t i = tileFirst + threadIdx.x; i < tileEnd; i += blockDim.x) {
-                    uint32_t sl = c.slotOf[i];
-                    if (sl & PROVISIONAL) c.slotOf[i] = sh_leafBase[tabFind(sh_leafKey, c.leafOf[i] & 0xffffffu)] + (sl & ~PROVISIONAL);
-                }
-            }
-        } else
-#endif
-        for (uint32_t base = blockFirst + (threadIdx.x - laneId()); base < blockEnd; base += step) {
-            uint32_t i = base + laneId();
-            if (i < blockEnd) {
-                uint32_t sl = c.slotOf[i];
-                if (sl & PROVISIONAL) c.slotOf[i] = sh_leafBase[tabFind(sh_leafKey, c.leafOf[i] & 0xffffffu)] + (sl & ~PROVISIONAL);
-            }
+        uint32_t blockFirst, blockEnd;
+        blockRun(b.size, blockFirst, blockEnd);
+        if (!FRESH && sh_rescan == 0) blockEnd = blockFirst;          // the run was not visited in this pass
+        for (uint32_t i = blockFirst + threadIdx.x; i < blockEnd; i += blockDim.x) {
+            uint32_t sl = slotOf[i];
+            if (sl & PROVISIONAL) slotOf[i] = sh_leafBase[tabFind(sh_leafKey, leafOf[i] & 0xffffffu)] + (sl & ~PROVISIONAL);
         }
         for (uint32_t j = tid; j < numSpilled; j += stride) {
-            uint32_t sl = c.slotOf[scratch::MAX_BATCH + j];
-            if (sl & PROVISIONAL) c.slotOf[scratch::MAX_BATCH + j] = sh_leafBase[tabFind(sh_leafKey, c.leafOf[scratch::MAX_BATCH + j] & 0xffffffu)] + (sl & ~PROVISIONAL);
+            uint32_t sl = slotOf[scratch::MAX_BATCH + j];
+            if (sl & PROVISIONAL) slotOf[scratch::MAX_BATCH + j] = sh_leafBase[tabFind(sh_leafKey, leafOf[scratch::MAX_BATCH + j] & 0xffffffu)] + (sl & ~PROVISIONAL);
         }
+        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // split round, ONE phase (voxels.cu:245-289 spill copy, :308-383 doSplitting). Everything a split
-// needs was reserved by the lane that detected it, so for every spilling leaf the three jobs are
-// independent and spread over the whole grid, one warp per item:
-//   parts 0..63  copy chunk k of the leaf's stored points into the spill buffer (16 KB, 128-bit)
-//   parts 64..79 clear 1/16 of the new inner node's occupancy grid (sic: the root's populated grid too)
-//   part  80     create the 8 children, return the chunks to the free stack, publish the node as inner
+// needs was reserved by the lane that detected it, so for every spilling leaf the jobs are
+// independent and spread over the whole grid, one warp per part:
+//   parts 0..255    copy a quarter of chunk k of the leaf's stored points into the spill buffer (4 KB, 128-bit, 8 loads in flight per lane)
+//   parts 256..287  clear 1/32 of the new inner node's occupancy grid (sic: the root's populated grid too)
+//   part  288       create the 8 children, return the chunks to the free stack, publish the node as inner
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t SPLIT_PARTS = 81;
+constexpr uint32_t SPLIT_COPY_PARTS = 256, SPLIT_CLEAR_PARTS = 32, SPLIT_PARTS = SPLIT_COPY_PARTS + SPLIT_CLEAR_PARTS + 1;
 
-__device__ void splitRound(const Ctx& c, uint32_t begin, uint32_t end) {
+__device__ __noinline__ void splitRound(const Ctx c, const Batch b, uint32_t begin, uint32_t end) {
     const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // the warps of a block take parts that are far apart, so that the copy parts of one leaf spread over all SMs
+    const uint32_t warp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     const uint32_t lane = laneId();
     const uint32_t numItems = (end - begin) * SPLIT_PARTS;
+    uint32_t* leafOf = c.leafOf(b.parity);
     for (uint32_t item = warp; item < numItems; item += numWarps) {
-        const SpillInfo info = c.spill[begin + item / SPLIT_PARTS];
+        const SpillInfo info = c.spill()[begin + item / SPLIT_PARTS];
         const uint32_t part = item % SPLIT_PARTS;
         const uint32_t numChunks = (info.stored + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-        if (info.childBase + 8 > scratch::NODE_CAP) continue;
-        if (part < 64) {
-            if (part >= numChunks || info.row == 0 || (uint64_t)info.base + info.stored > scratch::SPILL_CAP) continue;
-            const Chunk* chunk = reinterpret_cast<const Chunk*>(c.rows[(uint64_t)(info.row - 1) * scratch::ROW_SLOTS + part]);
-            const uint32_t first = part * SIMLOD_POINTS_PER_CHUNK;
-            const uint32_t n = min((uint32_t)SIMLOD_POINTS_PER_CHUNK, info.stored - first);
+        if (part < SPLIT_COPY_PARTS) {
+            const uint32_t k = part >> 2, quarter = part & 3u;
+            if (k >= numChunks || info.row == 0) continue;
+            const Chunk* chunk = reinterpret_cast<const Chunk*>(c.rows()[(uint64_t)(info.row - 1) * scratch::ROW_SLOTS + k]);
+            const uint32_t inChunk = min((uint32_t)SIMLOD_POINTS_PER_CHUNK, info.stored - k * SIMLOD_POINTS_PER_CHUNK);
+            const uint32_t first = quarter * 256u;                       // points [first, first + 256) of the chunk (the last quarter holds 232)
+            const uint32_t n = inChunk > first ? min(256u, inChunk - first) : 0u;
             const uint32_t tag = info.node | (info.level << 24);
-            for (uint32_t i = lane; i < n; i += 32) {
-                uint4 v = *reinterpret_cast<const uint4*>(&chunk->points[i]);
-                *reinterpret_cast<uint4*>(c.spilled + info.base + first + i) = v;
-                c.leafOf[scratch::MAX_BATCH + info.base + first + i] = tag;
+            const uint4* src = reinterpret_cast<const uint4*>(&chunk->points[first]);
+            const uint32_t dst = info.base + k * SIMLOD_POINTS_PER_CHUNK + first;
+#pragma unroll 1
+            for (uint32_t h = 0; h < 256u; h += 128u) {                // 4 loads in flight per lane
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (h + lane + 32u * u < n) v[u] = src[h + lane + 32u * u];
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (h + lane + 32u * u < n) {
+                    *reinterpret_cast<uint4*>(c.spilled() + dst + h + lane + 32u * u) = v[u];
+                    leafOf[scratch::MAX_BATCH + dst + h + lane + 32u * u] = tag;
+                }
             }
-        } else if (part < 80) {
-            uint4* g = reinterpret_cast<uint4*>(info.grid) + (uint64_t)(part - 64) * (SIMLOD_GRID_WORDS / 4 / 16);
-            for (uint32_t i = lane; i < SIMLOD_GRID_WORDS / 4 / 16; i += 32) g[i] = make_uint4(0, 0, 0, 0);
+        } else if (part < SPLIT_COPY_PARTS + SPLIT_CLEAR_PARTS) {
+            constexpr uint32_t PER = SIMLOD_GRID_WORDS / 4 / SPLIT_CLEAR_PARTS;       // uint4 per part
+            uint4* g = reinterpret_cast<uint4*>(info.grid) + (uint64_t)(part - SPLIT_COPY_PARTS) * PER;
+#pragma unroll 4
+            for (uint32_t i = lane; i < PER; i += 32) g[i] = make_uint4(0, 0, 0, 0);
         } else {
             Node* parent = &c.nodes[info.node];
             const uint32_t pX = parent->X, pY = parent->Y, pZ = parent->Z;
@@ -696,13 +803,15 @@ __device__ void splitRound(const Ctx& c, uint32_t begin, uint32_t end) {
                 child->X = 2 * pX + ((lane >> 2) & 1);
                 child->Y = 2 * pY + ((lane >> 1) & 1);
                 child->Z = 2 * pZ + (lane & 1);
-                for (int b = 0; b < 20; b++) child->name[b] = parent->name[b];
+                for (int k = 0; k < 20; k++) child->name[k] = parent->name[k];
                 reinterpret_cast<uint8_t*>(child)[offsetof(Node, name) + info.level + 1] = (uint8_t)('0' + lane);   // name[level] (sic: level 20 lands on `visible`)
                 child->isLeaf = 1;
                 parent->children[lane] = child;
-                c.firstChild[info.childBase + lane] = 0;
-                c.gridPtr[info.childBase + lane] = 0;
-                c.leafRow[info.childBase + lane] = 0;
+                c.firstChild()[info.childBase + lane] = 0;
+                c.parentOf()[info.childBase + lane] = info.node;
+                c.gridPtr()[info.childBase + lane] = 0;
+                c.leafRow()[info.childBase + lane] = 0;
+                c.splitState()[info.childBase + lane] = 0;
             }
             // return the leaf's chunks to the free stack (voxels.cu:345-357)
             if (numChunks > 0 && info.row != 0) {
@@ -710,32 +819,32 @@ __device__ void splitRound(const Ctx& c, uint32_t begin, uint32_t end) {
                 if (lane == 0) a0 = atomicAdd(reinterpret_cast<unsigned long long*>(&c.stats->numAllocatedChunks), (unsigned long long)(0ull - numChunks));
                 a0 = __shfl_sync(0xffffffffu, a0, 0);
                 for (uint32_t k = lane; k < numChunks && k < scratch::ROW_SLOTS; k += 32) {
-                    Chunk* chunk = reinterpret_cast<Chunk*>(c.rows[(uint64_t)(info.row - 1) * scratch::ROW_SLOTS + k]);
+                    Chunk* chunk = reinterpret_cast<Chunk*>(c.rows()[(uint64_t)(info.row - 1) * scratch::ROW_SLOTS + k]);
                     chunk->next = nullptr;
                     uint64_t qi = a0 - 1 - k;
-                    if (qi < scratch::QUEUE_CAP) c.chunkQueue[qi] = (uint64_t)chunk;
-                    else atomicOr(&c.ctl->errorFlags, ERR_QUEUE_OVERFLOW);
+                    if (qi < scratch::QUEUE_CAP) c.chunkQueue()[qi] = (uint64_t)chunk;
+                    else atomicOr(&c.ctl()->errorFlags, ERR_QUEUE_OVERFLOW);
                 }
             }
             __syncwarp();
             if (lane == 0) {
                 if (info.row != 0) {                    // the row goes back to the row pool; its contents stay readable for this phase
-                    uint32_t f = atomicAdd(&c.ctl->rowFreeCount, 1u);
-                    c.rowFree[f] = info.row;
-                    c.leafRow[info.node] = 0;
+                    uint32_t f = atomicAdd(&c.ctl()->rowFreeCount, 1u);
+                    c.rowFree()[f] = info.row;
+                    c.leafRow()[info.node] = 0;
                 }
                 parent->numPoints = 0;
                 parent->points = nullptr;
                 parent->grid = reinterpret_cast<SimlodOccupancyGrid*>(info.grid);
-                c.gridPtr[info.node] = info.grid;
-                c.firstChild[info.node] = info.childBase;
+                c.gridPtr()[info.node] = info.grid;
+                c.firstChild()[info.node] = info.childBase;
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// chunk allocation for the nodes touched by this batch (voxels.cu:485-538, 641-672)
+// chunk allocation for the nodes touched by a batch (voxels.cu:485-538, 641-672)
 // ------------------------------------------------------------------------------------------
 // block-wide exclusive prefix sum of one value per thread (256 threads); returns the block total
 __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t& total) {
@@ -755,14 +864,17 @@ __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t& tot
 }
 
 // The reference lets every node thread bump numAllocatedChunks / the heap offset once per chunk
-// (voxels.cu:505-511). All dirty nodes of a batch sit in one or two blocks here, so a block adds its
-// whole demand with ONE atomic per counter and hands out sub-ranges by prefix sum: the same totals,
-// the same pooled-vs-fresh split (indices >= chunkPoolSize are fresh), a handful of atomics.
-__device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
+// (voxels.cu:505-511). Here a block adds its whole demand with ONE atomic per counter and hands out
+// sub-ranges by prefix sum: the same totals, the same pooled-vs-fresh split (indices >= chunkPoolSize
+// are fresh), a handful of atomics.
+__device__ __noinline__ void allocateChunks(const Ctx c, const Batch b) {
     __shared__ uint64_t sh_a0, sh_freshOff, sh_firstFresh;
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t numDirtyLeaves = ldv(&c.bc->numDirtyLeaves);
-    const uint32_t numDirtyVox = ldv(&c.bc->numDirtyVox);
+    const uint32_t numDirtyLeaves = ldv(&b.bc->numDirtyLeaves);
+    const uint32_t numDirtyVox = ldv(&b.bc->numDirtyVox);
+    const uint64_t poolSize = ldv(&c.stats->chunkPoolSize);
+    const uint32_t* dirtyLeaves = c.dirtyLeaves(b.parity);
+    const uint32_t* dirtyVox = c.dirtyVox(b.parity);
 
     for (uint32_t first = blockIdx.x * blockDim.x; first < numDirtyLeaves; first += stride) {      // block-uniform trip count
         const uint32_t d = first + threadIdx.x;
@@ -770,16 +882,16 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
         Node* node = nullptr;
         bool live = false;
         if (d < numDirtyLeaves) {
-            n = c.dirtyLeaves[d];
-            if (c.firstChild[n] == 0) {                       // else: became an inner node in this batch
+            n = dirtyLeaves[d];
+            if (c.firstChild()[n] == 0) {                       // else: became an inner node in this batch
                 node = &c.nodes[n];
                 cnt = node->counter; have = node->numPoints;
                 if (cnt > have) {
                     live = true;
                     existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
                     uint32_t required = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-                    needed = required - existing;
-                    if (required > scratch::ROW_SLOTS) { atomicOr(&c.ctl->errorFlags, ERR_ROW_OVERFLOW); needed = 0; live = false; }
+                    if (required > scratch::ROW_SLOTS) { atomicOr(&c.ctl()->errorFlags, ERR_ROW_OVERFLOW); required = scratch::ROW_SLOTS; }   // insertion drops the excess
+                    needed = required > existing ? required - existing : 0;
                 }
             }
         }
@@ -790,31 +902,31 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
             uint64_t firstFresh = a0 > poolSize ? a0 : poolSize;          // indices >= poolSize are new heap chunks (voxels.cu:509-515)
             uint64_t numFresh = a0 + total > firstFresh ? a0 + total - firstFresh : 0;
             sh_a0 = a0; sh_firstFresh = firstFresh;
-            sh_freshOff = numFresh ? atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)(numFresh * SIMLOD_CHUNK_STRIDE)) : 0;
+            sh_freshOff = numFresh ? atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap()->offset), (unsigned long long)(numFresh * SIMLOD_CHUNK_STRIDE)) : 0;
         }
         __syncthreads();
         if (live) {
             if (needed > 0) {
-                uint32_t row = c.leafRow[n];
+                uint32_t row = c.leafRow()[n];
                 if (row == 0) {                                 // first chunk of this leaf: take a row (recycled first)
-                    uint32_t f = atomicSub(&c.ctl->rowFreeCount, 1u);
+                    uint32_t f = atomicSub(&c.ctl()->rowFreeCount, 1u);
                     if (f >= 1 && f <= scratch::ROW_CAP) {
-                        row = c.rowFree[f - 1];
+                        row = c.rowFree()[f - 1];
                     } else {
-                        atomicAdd(&c.ctl->rowFreeCount, 1u);
-                        uint32_t r = atomicAdd(&c.ctl->rowBump, 1u);
-                        if (r >= scratch::ROW_CAP) { atomicOr(&c.ctl->errorFlags, ERR_ROW_OVERFLOW); row = 0; }
+                        atomicAdd(&c.ctl()->rowFreeCount, 1u);
+                        uint32_t r = atomicAdd(&c.ctl()->rowBump, 1u);
+                        if (r >= scratch::ROW_CAP) { atomicOr(&c.ctl()->errorFlags, ERR_ROW_OVERFLOW); row = 0; }
                         else row = r + 1;
                     }
-                    c.leafRow[n] = row;
+                    c.leafRow()[n] = row;
                 }
                 if (row != 0) {
-                    uint64_t* slots = c.rows + (uint64_t)(row - 1) * scratch::ROW_SLOTS;
+                    uint64_t* slots = c.rows() + (uint64_t)(row - 1) * scratch::ROW_SLOTS;
                     Chunk* tail = existing ? reinterpret_cast<Chunk*>(slots[existing - 1]) : nullptr;
                     const uint64_t a0 = sh_a0 + offset, firstFresh = sh_firstFresh, freshOff = sh_freshOff;
                     for (uint32_t t = 0; t < needed; t++) {
                         uint64_t idx = a0 + t;
-                        Chunk* chunk = idx < poolSize ? reinterpret_cast<Chunk*>(c.chunkQueue[idx])
+                        Chunk* chunk = idx < poolSize ? reinterpret_cast<Chunk*>(c.chunkQueue()[idx])
                                                       : reinterpret_cast<Chunk*>(c.heapBytes + freshOff + (idx - firstFresh) * SIMLOD_CHUNK_STRIDE);
                         chunk->next = nullptr;
                         if (tail) tail->next = chunk; else node->points = chunk;
@@ -834,7 +946,7 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
         Node* node = nullptr;
         bool live = false;
         if (d < numDirtyVox) {
-            n = c.dirtyVox[d];
+            n = dirtyVox[d];
             node = &c.nodes[n];
             cnt = node->numVoxels; have = node->numVoxelsStored;
             if (cnt > have) {
@@ -850,27 +962,28 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
         const uint32_t offSeg = blockExclusiveScan(nseg, totalSeg);
         if (threadIdx.x == 0) {
             // voxel chunks are never recycled: always fresh heap memory (voxels.cu:652-666)
-            sh_freshOff = totalNeeded ? atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap->offset), (unsigned long long)((uint64_t)totalNeeded * SIMLOD_CHUNK_STRIDE)) : 0;
-            sh_a0 = totalSeg ? atomicAdd(&c.bc->dirCursor, totalSeg) : 0;
+            sh_freshOff = totalNeeded ? atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap()->offset), (unsigned long long)((uint64_t)totalNeeded * SIMLOD_CHUNK_STRIDE)) : 0;
+            sh_a0 = totalSeg ? atomicAdd(&b.bc->dirCursor, totalSeg) : 0;
         }
         __syncthreads();
         if (live) {
             const uint32_t base = (uint32_t)sh_a0 + offSeg;
-            if ((uint64_t)base + nseg > scratch::DIR_CAP) { atomicOr(&c.ctl->errorFlags, ERR_DIR_OVERFLOW); }
+            if ((uint64_t)base + nseg > scratch::DIR_CAP) { atomicOr(&c.ctl()->errorFlags, ERR_DIR_OVERFLOW); c.voxelDir()[n] = DirEntry{0xffffffffu, 0}; }
             else {
-                c.voxelDir[n] = DirEntry{base, k0};
-                Chunk* tail = node->voxelChunks ? reinterpret_cast<Chunk*>(c.voxelTail[n]) : nullptr;
+                uint64_t* chunkDir = c.chunkDir(b.parity);
+                c.voxelDir()[n] = DirEntry{base, k0};
+                Chunk* tail = node->voxelChunks ? reinterpret_cast<Chunk*>(c.voxelTail()[n]) : nullptr;
                 uint32_t j = 0;
-                if (have % SIMLOD_POINTS_PER_CHUNK != 0) c.chunkDir[base + j++] = (uint64_t)tail;
+                if (have % SIMLOD_POINTS_PER_CHUNK != 0) chunkDir[base + j++] = (uint64_t)tail;
                 const uint64_t freshOff = sh_freshOff + (uint64_t)offNeeded * SIMLOD_CHUNK_STRIDE;
                 for (uint32_t t = 0; t < needed; t++) {
                     Chunk* chunk = reinterpret_cast<Chunk*>(c.heapBytes + freshOff + (uint64_t)t * SIMLOD_CHUNK_STRIDE);
                     chunk->next = nullptr;
                     if (tail) tail->next = chunk; else node->voxelChunks = chunk;
                     tail = chunk;
-                    c.chunkDir[base + j++] = (uint64_t)chunk;
+                    chunkDir[base + j++] = (uint64_t)chunk;
                 }
-                if (needed > 0) c.voxelTail[n] = (uint64_t)tail;
+                if (needed > 0) c.voxelTail()[n] = (uint64_t)tail;
                 node->numVoxelsStored = cnt;
             }
         }
@@ -884,12 +997,14 @@ __device__ void allocateChunks(const Ctx& c, uint64_t poolSize) {
 // (voxels.cu:540-639 insertPoints, 674-698 insertVoxels walk slot/1000 list links instead)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ Point* pointSlotAddress(const Ctx& c, uint32_t row, uint32_t slot) {
-    Chunk* chunk = reinterpret_cast<Chunk*>(c.rows[(uint64_t)(row - 1) * scratch::ROW_SLOTS + slot / SIMLOD_POINTS_PER_CHUNK]);
+    const uint32_t k = slot / SIMLOD_POINTS_PER_CHUNK;
+    if (row == 0 || k >= scratch::ROW_SLOTS) return nullptr;       // row / node capacity exceeded (flagged): the point is dropped, never misplaced
+    Chunk* chunk = reinterpret_cast<Chunk*>(c.rows()[(uint64_t)(row - 1) * scratch::ROW_SLOTS + k]);
     return &chunk->points[slot % SIMLOD_POINTS_PER_CHUNK];
 }
 
-__device__ __forceinline__ void insertVoxel(const Ctx& c, uint64_t at) {
-    uint64_t key = c.vkey[at];
+__device__ __forceinline__ void insertVoxel(const Ctx& c, uint32_t parity, uint64_t at) {
+    uint64_t key = c.vkey(parity)[at];
     uint32_t cell = (uint32_t)(key & 0x1fffffu);
     uint32_t node = (uint32_t)((key >> 21) & 0xfffffu);
     uint32_t vslot = (uint32_t)(key >> 41);
@@ -903,45 +1018,52 @@ __device__ __forceinline__ void insertVoxel(const Ctx& c, uint64_t at) {
                         fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f((cell >> 7) & 127u), 0.5f)), 0.0078125f));
     float vz = fpx::add(fpx::fma(nodeSize, fpx::u2f(Z), c.minz),
                         fpx::mul_ftz(fpx::mul(nodeSize, fpx::add(fpx::u2f((cell >> 14) & 127u), 0.5f)), 0.0078125f));
-    uint4 v = make_uint4(__float_as_uint(vx), __float_as_uint(vy), __float_as_uint(vz), c.vcolor[at]);
-    DirEntry d = c.voxelDir[node];
-    Chunk* chunk = reinterpret_cast<Chunk*>(c.chunkDir[d.base + (vslot / SIMLOD_POINTS_PER_CHUNK - d.k0)]);
+    uint4 v = make_uint4(__float_as_uint(vx), __float_as_uint(vy), __float_as_uint(vz), c.vcolor(parity)[at]);
+    DirEntry d = c.voxelDir()[node];
+    if (d.base == 0xffffffffu) return;                               // directory overflow (flagged)
+    Chunk* chunk = reinterpret_cast<Chunk*>(c.chunkDir(parity)[d.base + (vslot / SIMLOD_POINTS_PER_CHUNK - d.k0)]);
     stPoint(&chunk->points[vslot % SIMLOD_POINTS_PER_CHUNK], v);
 }
 
-__device__ void insertAll(const Ctx& c, const Point* batch, uint32_t numBatch, uint32_t numSpilled, uint32_t numSharedVoxels) {
+__device__ __noinline__ void insertAll(const Ctx c, const Batch b, uint32_t numSpilled, uint32_t numSharedVoxels) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t* leafOf = c.leafOf(b.parity);
+    const uint32_t* slotOf = c.slotOf(b.parity);
+    const uint32_t* leafRow = c.leafRow();
     // two independent items per iteration: the three dependent lookups (item -> leaf row -> chunk) of one
     // overlap with those of the other
-    for (uint32_t i = tid; i < numBatch; i += 2 * stride) {
+    for (uint32_t i = tid; i < b.size; i += 2 * stride) {
         const uint32_t i2 = i + stride;
-        const bool has2 = i2 < numBatch;
-        uint4 p1 = ldPoint(batch + i);
-        uint4 p2 = has2 ? ldPoint(batch + i2) : make_uint4(0, 0, 0, 0);
-        uint32_t n1 = c.leafOf[i] & 0xffffffu, s1 = c.slotOf[i];
-        uint32_t n2 = has2 ? (c.leafOf[i2] & 0xffffffu) : 0u, s2 = has2 ? c.slotOf[i2] : 0u;
-        uint32_t r1 = c.leafRow[n1], r2 = has2 ? c.leafRow[n2] : 0u;
-        if (r1) stPoint(pointSlotAddress(c, r1, s1), p1);
-        if (r2) stPoint(pointSlotAddress(c, r2, s2), p2);
+        const bool has2 = i2 < b.size;
+        uint4 p1 = ldPoint(b.points + i);
+        uint4 p2 = has2 ? ldPoint(b.points + i2) : make_uint4(0, 0, 0, 0);
+        uint32_t n1 = leafOf[i] & 0xffffffu, s1 = slotOf[i];
+        uint32_t n2 = has2 ? (leafOf[i2] & 0xffffffu) : 0u, s2 = has2 ? slotOf[i2] : 0u;
+        uint32_t r1 = leafRow[n1], r2 = has2 ? leafRow[n2] : 0u;
+        Point* d1 = pointSlotAddress(c, r1, s1);
+        Point* d2 = has2 ? pointSlotAddress(c, r2, s2) : nullptr;
+        if (d1) stPoint(d1, p1);
+        if (d2) stPoint(d2, p2);
     }
     for (uint32_t j = tid; j < numSpilled; j += stride) {
-        uint4 pt = *reinterpret_cast<const uint4*>(c.spilled + j);
-        uint32_t node = c.leafOf[scratch::MAX_BATCH + j] & 0xffffffu;
-        uint32_t row = c.leafRow[node];
-        if (row) stPoint(pointSlotAddress(c, row, c.slotOf[scratch::MAX_BATCH + j]), pt);
+        uint4 pt = *reinterpret_cast<const uint4*>(c.spilled() + j);
+        uint32_t node = leafOf[scratch::MAX_BATCH + j] & 0xffffffu;
+        Point* d = pointSlotAddress(c, leafRow[node], slotOf[scratch::MAX_BATCH + j]);
+        if (d) stPoint(d, pt);
     }
     // voxels: the per-block backlog segments are uneven, so every block first builds the prefix sums of
     // the segment fills in shared memory and the whole grid then strides over the concatenation
     __shared__ uint32_t sh_segStart[1025];
+    const uint32_t* blockCursor = c.blockCursor(b.parity);
     if (gridDim.x <= 1024) {
         uint32_t total = 0;
         for (uint32_t b0 = 0; b0 < gridDim.x; b0 += blockDim.x) {
-            uint32_t b = b0 + threadIdx.x;
-            uint32_t v = b < gridDim.x ? c.blockCursor[b] : 0u;
+            uint32_t blk = b0 + threadIdx.x;
+            uint32_t v = blk < gridDim.x ? blockCursor[blk] : 0u;
             uint32_t chunkTotal = 0;
             uint32_t off = blockExclusiveScan(v, chunkTotal);
-            if (b < gridDim.x) sh_segStart[b] = total + off;
+            if (blk < gridDim.x) sh_segStart[blk] = total + off;
             total += chunkTotal;
         }
         if (threadIdx.x == 0) sh_segStart[gridDim.x] = total;
@@ -949,20 +1071,37 @@ __device__ void insertAll(const Ctx& c, const Point* batch, uint32_t numBatch, u
         for (uint32_t v = tid; v < total; v += stride) {
             uint32_t lo = 0, hi = gridDim.x;                     // last segment with start <= v
             while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (sh_segStart[mid] <= v) lo = mid; else hi = mid; }
-            insertVoxel(c, (uint64_t)lo * c.segCap + (v - sh_segStart[lo]));
+            insertVoxel(c, b.parity, (uint64_t)lo * c.segCap + (v - sh_segStart[lo]));
         }
     } else {
-        const uint32_t own = c.blockCursor[blockIdx.x];
-        for (uint32_t e = threadIdx.x; e < own; e += blockDim.x) insertVoxel(c, (uint64_t)blockIdx.x * c.segCap + e);
+        const uint32_t own = blockCursor[blockIdx.x];
+        for (uint32_t e = threadIdx.x; e < own; e += blockDim.x) insertVoxel(c, b.parity, (uint64_t)blockIdx.x * c.segCap + e);
     }
-    for (uint32_t b = tid; b < numSharedVoxels; b += stride) insertVoxel(c, scratch::VOXEL_CAP - scratch::VOXEL_SHARED + b);
+    for (uint32_t e = tid; e < numSharedVoxels; e += stride) insertVoxel(c, b.parity, scratch::VOXEL_CAP - scratch::VOXEL_SHARED + e);
+    __syncthreads();
 }
 
 __device__ __forceinline__ void clearBatchCounters(BatchCounters* b) {
-    b->numSpillTotal = 0; b->numSpilled = 0; b->numBacklog = 0; b->numDirtyLeaves = 0; b->numDirtyVox = 0; b->dirCursor = 0;
-#if defined(SIMLOD_DYNAMIC_TILES)
-    b->_pad[0] = 0; b->_pad[1] = 0;            // tile cursors of the experimental dynamic hand-out
-#endif
+    b->numSpillTotal = 0; b->numSpilled = 0; b->numBacklog = 0; b->numDirtyLeaves = 0; b->numDirtyVox = 0; b->dirCursor = 0; b->voxelsCreated = 0;
+}
+
+// Upper bound of what the allocation of a counted batch can still take from the heap (for the capacity guard,
+// which the reference evaluates with that batch already allocated, voxels.cu:896-912)
+__device__ __forceinline__ uint64_t pendingAllocationBound(const Batch& b) {
+    const uint64_t chunks = ((uint64_t)b.size + ldv(&b.bc->numSpilled) + ldv(&b.bc->voxelsCreated)) / SIMLOD_POINTS_PER_CHUNK
+                          + ldv(&b.bc->numDirtyLeaves) + ldv(&b.bc->numDirtyVox) + 2;
+    return chunks * SIMLOD_CHUNK_STRIDE;
+}
+
+// first thread of the grid: what the reference does at the end of a batch (voxels.cu:925-949)
+__device__ __forceinline__ void finishBatchBookkeeping(const Ctx& c, const Batch& b, uint64_t tStart) {
+    uint64_t allocated = ldv(&c.stats->numAllocatedChunks);
+    if (allocated > ldv(&c.stats->chunkPoolSize)) c.stats->chunkPoolSize = allocated;        // voxels.cu:535-537
+    c.stats->batchletIndex = b.index + 1;
+    c.stats->numPointsProcessed += b.size;
+    c.ctl()->spilledTotal += min(ldv(&b.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&c.ctl()->voxelsTotal), (unsigned long long)min(ldv(&b.bc->numBacklog), (uint32_t)scratch::VOXEL_SHARED));   // other blocks are adding theirs
+    c.ctl()->memUsed = ldv(&c.heap()->offset);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -977,32 +1116,11 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
     const uint64_t tStart = globaltimer();
 
     Ctx c;
+    c.buf = reinterpret_cast<uint8_t*>(buffer);
     c.nodes = nodes;
     c.stats = stats;
-    c.heap = reinterpret_cast<Heap*>(buffer_persistent);
     c.heapBytes = buffer_persistent;
-    c.ctl = carve<Ctl>(buffer, scratch::OFF_CTL);
-    c.bc = &c.ctl->batch[0];
-    c.firstChild = carve<uint32_t>(buffer, scratch::OFF_FIRSTCHILD);
-    c.gridPtr = carve<uint64_t>(buffer, scratch::OFF_GRIDPTR);
-    c.leafRow = carve<uint32_t>(buffer, scratch::OFF_LEAFROW);
-    c.rows = carve<uint64_t>(buffer, scratch::OFF_ROWS);
-    c.rowFree = carve<uint32_t>(buffer, scratch::OFF_ROWFREE);
-    c.voxelTail = carve<uint64_t>(buffer, scratch::OFF_VTAIL);
-    c.voxelDir = carve<DirEntry>(buffer, scratch::OFF_VDIR);
-    c.dirtyLeaves = carve<uint32_t>(buffer, scratch::OFF_DIRTYLEAF);
-    c.dirtyVox = carve<uint32_t>(buffer, scratch::OFF_DIRTYVOX);
-    c.spill = carve<SpillInfo>(buffer, scratch::OFF_SPILLINFO);
-    c.blockCursor = carve<uint32_t>(buffer, scratch::OFF_BLOCKCUR);
     c.segCap = gridDim.x <= scratch::BLOCK_CAP ? (uint32_t)((scratch::VOXEL_CAP - scratch::VOXEL_SHARED) / gridDim.x) : 0u;
-    c.chunkDir = carve<uint64_t>(buffer, scratch::OFF_CHUNKDIR);
-    c.chunkQueue = carve<uint64_t>(buffer, scratch::OFF_QUEUE);
-    c.leafOf = carve<uint32_t>(buffer, scratch::OFF_LEAFOF);
-    c.slotOf = carve<uint32_t>(buffer, scratch::OFF_SLOTOF);
-    c.spilled = carve<Point>(buffer, scratch::OFF_SPILLED);
-    c.vkey = carve<uint64_t>(buffer, scratch::OFF_VKEY);
-    c.vcolor = carve<uint32_t>(buffer, scratch::OFF_VCOLOR);
-
     // octree cube = boxMin + max extent on every axis (voxels.cu:860-863)
     float sx = fpx::sub(uniforms.boxMax[0], uniforms.boxMin[0]);
     float sy = fpx::sub(uniforms.boxMax[1], uniforms.boxMin[1]);
@@ -1010,112 +1128,137 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
     c.size = fmaxf(fmaxf(sx, sy), sz);
     c.rcpSize = fpx::rcp(c.size);
     c.minx = uniforms.boxMin[0]; c.miny = uniforms.boxMin[1]; c.minz = uniforms.boxMin[2];
+    Ctl* ctl = c.ctl();
 
     if (first) {
         *frameStartTimestamp = tStart;
-        c.ctl->numBatchesUploaded = *(volatile uint32_t*)numBatchesUploaded_volatile;   // one snapshot for all threads
-        c.ctl->errorFlags = 0;
-        c.ctl->elapsedNanos = 0;
-        c.ctl->memUsed = c.heap->offset;
-        clearBatchCounters(&c.ctl->batch[0]);
-        clearBatchCounters(&c.ctl->batch[1]);
-        for (int i = 0; i < 8; i++) c.ctl->statCounters[i] = 0;
+        ctl->numBatchesUploaded = *(volatile uint32_t*)numBatchesUploaded_volatile;   // one snapshot for all threads
+        ctl->elapsedNanos = 0;
+        ctl->memUsed = c.heap()->offset;
+        ctl->allocDone = 0;
+        for (int i = 0; i < 3; i++) clearBatchCounters(&ctl->batch[i]);
+        for (int i = 0; i < 8; i++) ctl->statCounters[i] = 0;
         if (stats->batchletIndex == 0) {       // fresh after the reset kernel: the tree is the root alone
-            c.ctl->spilledTotal = 0; c.ctl->voxelsTotal = 0; c.ctl->voxelsByPass[0] = 0; c.ctl->voxelsByPass[1] = 0;
-            for (int i = 0; i < 8; i++) c.ctl->phaseNanos[i] = 0;
-            c.ctl->rowBump = 0; c.ctl->rowFreeCount = 0;
-            c.firstChild[0] = 0;
-            c.leafRow[0] = 0;
-            c.gridPtr[0] = (uint64_t)nodes[0].grid;
+            ctl->errorFlags = 0;
+            ctl->spilledTotal = 0; ctl->voxelsTotal = 0; ctl->voxelsByPass[0] = 0; ctl->voxelsByPass[1] = 0;
+            for (int i = 0; i < 8; i++) ctl->phaseNanos[i] = 0;
+            ctl->rowBump = 0; ctl->rowFreeCount = 0;
+            c.firstChild()[0] = 0;
+            c.parentOf()[0] = 0;
+            c.leafRow()[0] = 0;
+            c.splitState()[0] = 0;
+            c.gridPtr()[0] = (uint64_t)nodes[0].grid;
         }
     }
+    if (threadIdx.x == 0) { sh_allocTarget = 0; sh_allocSeen = 0; sh_rescan = 0; }
+    if (threadIdx.x < BLOOM_WORDS) sh_runBloom[threadIdx.x] = 0xffffffffu;
+    tileBarInit();
     grid.sync();
     uint64_t tPhase = tStart;
-#define PHASE_DONE(k) do { if (first) { uint64_t _t = globaltimer(); c.ctl->phaseNanos[k] += _t - tPhase; tPhase = _t; } } while (0)
+#define PHASE_DONE(k) do { if (first) { uint64_t _t = globaltimer(); ctl->phaseNanos[k] += _t - tPhase; tPhase = _t; } } while (0)
     PHASE_DONE(7);
 
-    const uint32_t numBatchesUploaded = ldv(&c.ctl->numBatchesUploaded);
+    const uint32_t numBatchesUploaded = ldv(&ctl->numBatchesUploaded);
     const uint32_t firstBatch = ldv(&stats->batchletIndex);
     const uint32_t numBatches = min(numBatchesUploaded - firstBatch, 20u);     // voxels.cu:883
     const uint32_t lastBatch = firstBatch + numBatches;
 
+    bool havePending = false;          // a counted batch whose allocation + insertion has not run yet
+    Batch pending{};
+    uint32_t pendingSpilled = 0;
+    uint32_t allocEpochs = 0;          // in-phase allocations of this launch so far
+
     for (uint32_t batchIndex = firstBatch; batchIndex < lastBatch; batchIndex++) {
+        Batch b;
         const uint32_t ringSlot = batchIndex % SIMLOD_BATCH_STREAM_SIZE;
-        const uint32_t batchSize = min(ldv(&batchSizes[ringSlot]), (uint32_t)SIMLOD_MAX_BATCH_SIZE);
-        const Point* batch = points + (uint64_t)ringSlot * SIMLOD_MAX_BATCH_SIZE;
-        c.bc = &c.ctl->batch[batchIndex & 1];
-        BatchCounters* other = &c.ctl->batch[(batchIndex + 1) & 1];
+        b.size = min(ldv(&batchSizes[ringSlot]), (uint32_t)SIMLOD_MAX_BATCH_SIZE);
+        b.points = points + (uint64_t)ringSlot * SIMLOD_MAX_BATCH_SIZE;
+        b.index = batchIndex;
+        b.parity = batchIndex & 1u;
+        b.bc = &ctl->batch[batchIndex % 3u];
 
         // capacity guard (voxels.cu:896-912): stop consuming batches 200 MB before the heap is full
-        const bool memCapacityReached = ldv(&c.ctl->memUsed) + 200000000ull >= uniforms.persistentBufferCapacity;
+        const uint64_t memUsed = ldv(&ctl->memUsed) + (havePending ? pendingAllocationBound(pending) : 0ull);
+        const bool memCapacityReached = memUsed + 200000000ull >= uniforms.persistentBufferCapacity;
         if (first) stats->memCapacityReached = memCapacityReached ? 1 : 0;
         if (memCapacityReached) break;
 
-        const bool deferSampling = ldv(&c.firstChild[0]) == 0;    // root still a leaf: see DESIGN.md §4 (root grid is wiped when it splits)
-        const uint64_t poolSize = ldv(&stats->chunkPoolSize);
+        const bool deferSampling = ldv(&c.firstChild()[0]) == 0;    // root still a leaf: see DESIGN.md §4 (root grid is wiped when it splits)
 
-        // ---- pass 1: count (+ sample) every batch point ------------------------------------
-        if (deferSampling) itemPass<false, true, true>(c, batch, batchSize, 0);
-        else               itemPass<true, true, true>(c, batch, batchSize, 0);
+        // ---- fused phase: allocate b-1 | count (+ sample) b | insert b-1 ------------------------------
+        if (havePending) {
+            allocEpochs++;
+            if (threadIdx.x == 0) { sh_allocTarget = allocEpochs * gridDim.x; sh_allocSeen = 0; }
+            __syncthreads();
+            allocateChunks(c, pending);
+            __syncthreads();
+            if (threadIdx.x == 0) { __threadfence(); atomicAdd(&ctl->allocDone, 1u); }
+        }
+        if (first) clearBatchCounters(&ctl->batch[(batchIndex + 1) % 3u]);      // idle set: last used by batch b-2, next by b+1
+        if (deferSampling) passItems<false, true, true, false>(c, b, 0, 0, 0);
+        else               passItems<true, true, true, false>(c, b, 0, 0, 0);
+        waitAllocBlock(c);
+        if (deferSampling) passFlush<false, true, true>(c, b, 0);
+        else               passFlush<true, true, true>(c, b, 0);
+        if (havePending) {
+            if (first) finishBatchBookkeeping(c, pending, tStart);          // all allocations of b-1 are complete (waitAllocBlock)
+            insertAll(c, pending, pendingSpilled, min(ldv(&pending.bc->numBacklog), (uint32_t)scratch::VOXEL_SHARED));
+            if (threadIdx.x == 0) sh_allocTarget = 0;
+            havePending = false;
+        }
+        if (first) ctl->elapsedNanos = globaltimer() - tStart;
         grid.sync();
         PHASE_DONE(0);
 
         // ---- split rounds (voxels.cu:385-415 expand): 2 barriers each ------------------------
         uint32_t spillBegin = 0;
-        for (int round = 0; round < 20; round++) {
-            const uint32_t spillEnd = min(ldv(&c.bc->numSpillTotal), (uint32_t)scratch::SPILLNODE_CAP);
+        for (int round = 0; round < 24; round++) {
+            const uint32_t spillEnd = min(ldv(&b.bc->numSpillTotal), (uint32_t)scratch::SPILLNODE_CAP);
             if (spillEnd == spillBegin) break;
-            splitRound(c, spillBegin, spillEnd);
+            splitRound(c, b, spillBegin, spillEnd);
             grid.sync();
             PHASE_DONE(1);
-            const uint32_t numSpilled = min(ldv(&c.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
-            if (deferSampling) itemPass<false, true, false>(c, batch, batchSize, numSpilled);
-            else               itemPass<true, true, false>(c, batch, batchSize, numSpilled);
+            if (first) ctl->phaseNanos[6] += 1;
+            const uint32_t numSpilled = min(ldv(&b.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
+            if (deferSampling) { passItems<false, true, false, false>(c, b, numSpilled, spillBegin, spillEnd); passFlush<false, true, false>(c, b, numSpilled); }
+            else               { passItems<true, true, false, false>(c, b, numSpilled, spillBegin, spillEnd);  passFlush<true, true, false>(c, b, numSpilled); }
             grid.sync();
             PHASE_DONE(2);
             spillBegin = spillEnd;
         }
-        const uint32_t numSpilled = min(ldv(&c.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
+        const uint32_t numSpilled = min(ldv(&b.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
         if (deferSampling) {
-            // the root was a leaf when the batch started: sample along the final paths, as the
-            // reference does after expand() (voxels.cu:738-742)
-            itemPass<true, false, true>(c, batch, batchSize, numSpilled);
+            // the root was a leaf when the batch started: sample along the final paths, as the reference does after
+            // expand() (voxels.cu:738-742). The root's grid may just have been cleared in place: probe it through L2.
+            passItems<true, false, true, true>(c, b, numSpilled, 0, 0);
+            passFlush<true, false, true>(c, b, numSpilled);
             grid.sync();
             PHASE_DONE(3);
         }
-
-        // ---- chunk allocation for touched nodes --------------------------------------------
-        allocateChunks(c, poolSize);
-        if (first) clearBatchCounters(other);           // the next batch's counter set is idle during this phase
-        grid.sync();
-        PHASE_DONE(4);
-
-        // ---- insertion + bookkeeping (voxels.cu:925-949) --------------------------------------
-        const uint32_t numVoxels = min(ldv(&c.bc->numBacklog), (uint32_t)scratch::VOXEL_SHARED);     // shared overflow part only
-        if (first) {
-            uint64_t allocated = ldv(&stats->numAllocatedChunks);
-            if (allocated > poolSize) stats->chunkPoolSize = allocated;        // voxels.cu:535-537
-            stats->batchletIndex = batchIndex + 1;
-            stats->numPointsProcessed += batchSize;
-            c.ctl->spilledTotal += numSpilled; c.ctl->voxelsTotal += numVoxels;
-            c.ctl->memUsed = ldv(&c.heap->offset);
-            c.ctl->elapsedNanos = globaltimer() - tStart;
-        }
-        insertAll(c, batch, batchSize, numSpilled, numVoxels);
-        grid.sync();
-        PHASE_DONE(5);
-        const float elapsedMs = float(ldv(&c.ctl->elapsedNanos)) / 1000000.0f;
+        havePending = true;
+        pending = b;
+        pendingSpilled = numSpilled;
+        const float elapsedMs = float(ldv(&ctl->elapsedNanos)) / 1000000.0f;
         if (elapsedMs > 10.0f) break;          // MAX_PROCESSING_TIME (voxels.cu:22,940)
     }
 
-    // ---- octree statistics (voxels.cu:958-1009) --------------------------------------------
+    // ---- the last counted batch: allocate, then insert ------------------------------------------
+    if (havePending) {
+        allocateChunks(c, pending);
+        grid.sync();
+        PHASE_DONE(4);
+        if (first) finishBatchBookkeeping(c, pending, tStart);
+        insertAll(c, pending, pendingSpilled, min(ldv(&pending.bc->numBacklog), (uint32_t)scratch::VOXEL_SHARED));
+    }
+
+    // ---- octree statistics (voxels.cu:958-1009), same phase as the last insertion --------------------
     {
-        const uint32_t numNodes = ldv(&stats->numNodes);
+        const uint32_t numNodes = min(ldv(&stats->numNodes), (uint32_t)scratch::NODE_CAP);
         const uint32_t stride = gridDim.x * blockDim.x;
         uint32_t inner = 0, leaves = 0, nonempty = 0, pts = 0, vox = 0, chP = 0, chV = 0;
         for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < numNodes; n += stride) {
             const Node* node = &nodes[n];
-            if (c.firstChild[n] == 0) {
+            if (c.firstChild()[n] == 0) {
                 uint32_t np = node->numPoints;
                 leaves++; pts += np; chP += (np + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
                 if (np > 0) nonempty++;
@@ -1129,22 +1272,22 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         for (int k = 0; k < 7; k++) {
             uint32_t v = vals[k];
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (laneId() == 0 && v) atomicAdd(&c.ctl->statCounters[k], v);
+            if (laneId() == 0 && v) atomicAdd(&ctl->statCounters[k], v);
         }
     }
     grid.sync();
-    PHASE_DONE(6);
+    PHASE_DONE(5);
     if (first) {
-        stats->numInner = ldv(&c.ctl->statCounters[0]);
-        stats->numLeaves = ldv(&c.ctl->statCounters[1]);
-        stats->numNonemptyLeaves = ldv(&c.ctl->statCounters[2]);
-        stats->numPoints = ldv(&c.ctl->statCounters[3]);
-        stats->numVoxels = ldv(&c.ctl->statCounters[4]);
-        stats->numChunksPoints = ldv(&c.ctl->statCounters[5]);
-        stats->numChunksVoxels = ldv(&c.ctl->statCounters[6]);
+        stats->numInner = ldv(&ctl->statCounters[0]);
+        stats->numLeaves = ldv(&ctl->statCounters[1]);
+        stats->numNonemptyLeaves = ldv(&ctl->statCounters[2]);
+        stats->numPoints = ldv(&ctl->statCounters[3]);
+        stats->numVoxels = ldv(&ctl->statCounters[4]);
+        stats->numChunksPoints = ldv(&ctl->statCounters[5]);
+        stats->numChunksVoxels = ldv(&ctl->statCounters[6]);
         stats->allocatedBytes_momentary = scratch::TOTAL;
-        stats->allocatedBytes_persistent = ldv(&c.heap->offset);
+        stats->allocatedBytes_persistent = ldv(&c.heap()->offset);
         stats->frameID = (uint32_t)uniforms.frameCounter;
-        stats->dbg = ldv(&c.ctl->errorFlags);
+        stats->dbg = ldv(&ctl->errorFlags);
     }
 }

@@ -250,6 +250,14 @@ int readStats(SimlodContext* ctx) {
     return SIMLOD_OK;
 }
 
+// Stats::dbg carries kernel_construct's sticky capacity flags (construct.cu: ERR_*); bit 7 (a point far outside the
+// box) is informational, the others mean samples were dropped or a split was postponed
+int checkOverflow(SimlodContext* ctx) {
+    const uint32_t flags = ctx->hStats->dbg & 0x7fu;
+    if (flags) return fail(SIMLOD_ERR_OVERFLOW, "kernel_construct exceeded a per-batch capacity (Stats::dbg = 0x%x: 1 spill, 2 voxels, 4 directory, 8 nodes, 16 chunk stack, 32 splits, 64 leaf rows); reset to clear", flags);
+    return SIMLOD_OK;
+}
+
 int publishBatch(SimlodContext* ctx, uint32_t slot, uint32_t count) {
     // main.cpp:1047-1050: the size of the slot first, then the global counter, in stream order after the copy
     CU(D(cuMemsetD32Async)(ctx->batchSizes + 4ull * slot, count, 1, ctx->streamUpload));
@@ -393,6 +401,8 @@ static int createResources(SimlodContext* ctx, const SimlodConfig* config) {
 int simlod_create(const SimlodConfig* config, SimlodContext** out) {
     if (!config || !out) return fail(SIMLOD_ERR_INVALID, "null argument");
     if (config->width == 0 || config->height == 0) return fail(SIMLOD_ERR_INVALID, "render target must be non-empty");
+    if (config->nodes_bytes && config->nodes_bytes < 40000000ull)     // kernel_construct's node capacity is the reference's 40 MB array (main.cpp:552-555)
+        return fail(SIMLOD_ERR_INVALID, "nodes_bytes %llu is below the 40 000 000 bytes the kernels are built for", (unsigned long long)config->nodes_bytes);
     { int rc0 = loadDriver(); if (rc0) return rc0; }
     CU(D(cuInit)(0));
     SimlodContext* ctx = new SimlodContext();
@@ -475,7 +485,16 @@ int simlod_get_uniforms(SimlodContext* ctx, SimlodUniforms* out) {
 }
 
 int simlod_reset(SimlodContext* ctx) {
+    // The reference launches the reset kernel with 1 block x 1 thread (main.cpp:348-354); one thread then zeroes the
+    // root's 256 KiB grid, 330 us on a B200. The kernel is grid-stride (reference reset.cu:78-85 and ours), so the
+    // launch surface gives it one block per SM; simlod_reset_with_grid(ctx, 1, 1) is the reference's shape.
+    if (!ctx) return fail(SIMLOD_ERR_INVALID, "null context");
+    return simlod_reset_with_grid(ctx, (uint32_t)ctx->numSMs, 256);
+}
+
+int simlod_reset_with_grid(SimlodContext* ctx, uint32_t blocks, uint32_t threads) {
     int rc = setCurrent(ctx); if (rc) return rc;
+    if (blocks == 0 || threads == 0 || threads > 1024) return fail(SIMLOD_ERR_INVALID, "bad reset launch shape %u x %u", blocks, threads);
     CU(D(cuStreamSynchronize)(ctx->streamUpload));
     CU(D(cuStreamSynchronize)(ctx->streamMain));
     CU(D(cuMemsetD8Async)(ctx->buf.nodes, 0, ctx->buf.nodes_bytes, ctx->streamMain));
@@ -484,7 +503,7 @@ int simlod_reset(SimlodContext* ctx) {
     CUdeviceptr persistent = ctx->buf.persistent, nodes = ctx->buf.nodes, stats = ctx->buf.stats, cudaprint = ctx->cudaprint,
                 nbu = ctx->numBatchesUploaded, bs = ctx->batchSizes;
     void* args[] = {&u, &persistent, &nodes, &stats, &cudaprint, &nbu, &bs};      // main.cpp:337-345
-    CU(D(cuLaunchCooperativeKernel)(ctx->programs[SIMLOD_PROGRAM_RESET].fn, 1, 1, 1, 1, 1, 1, 0, ctx->streamMain, args));   // 1 block x 1 thread (main.cpp:348-354)
+    CU(D(cuLaunchCooperativeKernel)(ctx->programs[SIMLOD_PROGRAM_RESET].fn, blocks, 1, 1, threads, 1, 1, 0, ctx->streamMain, args));
     ctx->launches++;
     CU(D(cuStreamSynchronize)(ctx->streamMain));
     ctx->uploaded = 0;
@@ -564,7 +583,8 @@ int simlod_upload_batch_las_device(SimlodContext* ctx, uint64_t device_records, 
 int simlod_update_octree(SimlodContext* ctx, float* kernel_ms) {
     int rc = setCurrent(ctx); if (rc) return rc;
     rc = launchConstruct(ctx, kernel_ms); if (rc) return rc;
-    return readStats(ctx);
+    rc = readStats(ctx); if (rc) return rc;
+    return checkOverflow(ctx);
 }
 
 static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr dev, uint64_t count, float* kernel_ms, float* total_ms) {
@@ -608,6 +628,7 @@ static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr
             total += ms;
         }
         if (ctx->hStats->memCapacityReached) return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed);
+        rc = checkOverflow(ctx); if (rc) return rc;
     }
     CU(D(cuEventRecord)(ctx->evTotalEnd, ctx->streamMain));
     CU(D(cuEventSynchronize)(ctx->evTotalEnd));
@@ -727,7 +748,14 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
         if (abort.load()) { joinAll(); return fail(SIMLOD_ERR_INVALID, "read error in %s", path); }
         if (k == 0) tFirst = since();
         if (k + 1 == numBatches) tAllLoaded = since();
-        if (ctx->uploaded - ctx->processed >= RING_SLOTS - 1) { rc = readStats(ctx); if (rc) { joinAll(); return rc; } }   // back-pressure (main.cpp:1012)
+        // back-pressure (main.cpp:1012): when the ring is full, launch until a slot frees (or the device stops consuming)
+        while (ctx->uploaded - ctx->processed >= RING_SLOTS - 1) {
+            rc = readStats(ctx); if (rc) { joinAll(); return rc; }
+            if (ctx->uploaded - ctx->processed < RING_SLOTS - 1) break;
+            if (ctx->hStats->memCapacityReached) { joinAll(); return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed); }
+            rc = checkOverflow(ctx); if (rc) { joinAll(); return rc; }
+            rc = launch(ctx->uploaded - 1); if (rc) { joinAll(); return rc; }
+        }
         uint64_t first = k * SLOT_POINTS;
         uint32_t n = (uint32_t)std::min<uint64_t>(SLOT_POINTS, numPoints - first);
         const SimlodPoint* src = (const SimlodPoint*)((char*)ctx->pinnedPool + (k % POOL_SLOTS) * slotBytes);
@@ -755,6 +783,7 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
         rc = launch(ctx->uploaded - 1); if (rc) return rc;
         rc = readStats(ctx); if (rc) return rc;
         if (ctx->hStats->memCapacityReached) return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed);
+        rc = checkOverflow(ctx); if (rc) return rc;
     }
     CU(D(cuEventRecord)(ctx->evTotalEnd, ctx->streamMain));
     CU(D(cuEventSynchronize)(ctx->evTotalEnd));

@@ -53,11 +53,11 @@ sim = SimLOD(1920, 1080, persistent_bytes=8 << 30)
 sim.set_box(mn, mx)
 dptr = sim.device_alloc(K * bench.BATCH * 16)
 sim.memcpy_htod(dptr, np.concatenate(batches).view(np.uint8))
-names = ["count+sample", "split", "rewalk", "deferred", "alloc", "insert", "stats", "prologue"]
+names = ["fused(alloc|count+sample|insert)", "split", "rewalk", "deferred", "final_alloc", "final_insert+stats", "split_rounds(count)", "prologue"]
 
 
 def phases():
-    return sim.memcpy_dtoh(sim.buffers().momentary + 160, 64).view(np.uint64).astype(np.float64) / 1e3
+    return sim.memcpy_dtoh(sim.buffers().momentary + 96, 64).view(np.uint64).astype(np.float64) / 1e3
 
 
 def full_build(module):

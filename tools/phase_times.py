@@ -15,8 +15,8 @@ sim.memcpy_htod(dptr, np.concatenate(batches).view(np.uint8))
 for rep in range(2):
     sim.reset(); sim.flush_l2()
     kms, tms = sim.insert_device(dptr, n)
-    ph = sim.memcpy_dtoh(sim.buffers().momentary + 160, 64).view(np.uint64) / 1e3
-    names = ["count+sample", "split", "rewalk", "deferred", "alloc", "insert", "stats", "prologue"]
+    ph = sim.memcpy_dtoh(sim.buffers().momentary + 96, 64).view(np.uint64) / 1e3
+    names = ["fused(alloc|count+sample|insert)", "split", "rewalk", "deferred", "final_alloc", "final_insert+stats", "split_rounds(count)", "prologue"]
     print("kernel ms %.3f total ms %.3f Mpts/s %.1f" % (kms, tms, n / kms / 1e3))
     vb = sim.memcpy_dtoh(sim.buffers().momentary + 64, 32).view(np.uint64)
     print("voxels first-visit / re-walk:", int(vb[0]), int(vb[1]), "spilled", int(vb[2]), "total", int(vb[3]))

@@ -24,8 +24,8 @@ for l in range(L):
         sim.upload_batch_device(dptr + (l * B + b) * bench.BATCH * 16, bench.BATCH)
     ms = sim.update_octree()
     print("launch", l, "ms", ms, "batches done", sim.stats().batchletIndex, flush=True)
-ph = sim.memcpy_dtoh(sim.buffers().momentary + 160, 64).view(np.uint64) / 1e3
-names = ["count+sample", "split", "rewalk", "deferred", "alloc", "insert", "stats", "prologue"]
+ph = sim.memcpy_dtoh(sim.buffers().momentary + 96, 64).view(np.uint64) / 1e3
+names = ["fused(alloc|count+sample|insert)", "split", "rewalk", "deferred", "final_alloc", "final_insert+stats", "split_rounds(count)", "prologue"]
 print("phase us:", {n: round(float(v), 1) for n, v in zip(names, ph)}, "total", round(float(ph.sum()), 1), flush=True)
 view, proj = camera.orbit_camera(width=1920, height=1080, **camera.MORRO_BIRD)
 sim.set_camera(view, proj)
