@@ -73,7 +73,9 @@ constexpr uint64_t OFF_DIRTYLEAF  = align256(OFF_VDIR + NODE_TAB * 8);          
 constexpr uint64_t OFF_DIRTYVOX   = align256(OFF_DIRTYLEAF + 2 * NODE_TAB * 4);        // [2]
 constexpr uint64_t OFF_SPILLINFO  = align256(OFF_DIRTYVOX + 2 * NODE_TAB * 4);
 constexpr uint64_t OFF_BLOCKCUR   = align256(OFF_SPILLINFO + SPILLNODE_CAP * 32);      // [2]
-constexpr uint64_t OFF_ROWFREE    = align256(OFF_BLOCKCUR + 2 * BLOCK_CAP * 4);
+constexpr uint64_t OFF_RUNBLOOM   = align256(OFF_BLOCKCUR + 2 * BLOCK_CAP * 4);          // [BLOCK_CAP][8]
+constexpr uint64_t OFF_RUNFLAG    = align256(OFF_RUNBLOOM + BLOCK_CAP * 32);             // [BLOCK_CAP]
+constexpr uint64_t OFF_ROWFREE    = align256(OFF_RUNFLAG + BLOCK_CAP * 4);
 constexpr uint64_t OFF_ROWS       = align256(OFF_ROWFREE + ROW_CAP * 4);
 constexpr uint64_t OFF_CHUNKDIR   = align256(OFF_ROWS + ROW_CAP * ROW_SLOTS * 8);      // [2]
 constexpr uint64_t OFF_QUEUE      = align256(OFF_CHUNKDIR + 2 * DIR_CAP * 8);
@@ -105,7 +107,7 @@ struct BatchCounters {              // one set per batch, index = batch % 3; the
     uint32_t numDirtyVox;
     uint32_t dirCursor;
     uint32_t voxelsCreated;        // voxels of this batch (bound for the capacity guard)
-    uint32_t _pad;
+    uint32_t insertCursor;         // next tile of the batch's insertion work to hand out
 };
 
 struct Ctl {
@@ -125,9 +127,11 @@ struct Ctl {
     BatchCounters batch[3];        // @160
     uint32_t allocDone;            // @256 blocks that have finished their share of the in-phase allocations of this launch (monotonic)
     uint32_t _pad[3];
+    uint64_t subNanos[16];         // @272 block 0's own timeline inside the phases (developer aid): fused = 0 allocate, 1 count+sample, 2 wait for the
+                                   //      allocation, 3 flush, 4 insert, 5 barrier; split = 6 work, 7 barrier; re-walk = 8 items, 9 flush, 10 barrier; 11 top of the batch loop, 12 re-walk list
 };
 static_assert(offsetof(Ctl, spilledTotal) == 80, "bench.py reads Ctl::spilledTotal at byte 80");
-static_assert(offsetof(Ctl, phaseNanos) == 96 && offsetof(Ctl, batch) == 160 && offsetof(Ctl, allocDone) == 256, "tools read Ctl by offset");
+static_assert(offsetof(Ctl, phaseNanos) == 96 && offsetof(Ctl, batch) == 160 && offsetof(Ctl, allocDone) == 256 && offsetof(Ctl, subNanos) == 272, "tools read Ctl by offset");
 
 // what the lane that sees a leaf cross 50 000 records about it (everything the split round needs)
 struct SpillInfo {
@@ -167,6 +171,8 @@ struct Ctx {
     __device__ __forceinline__ uint32_t*  dirtyVox(uint32_t p)    const { return at<uint32_t>(scratch::OFF_DIRTYVOX) + p * scratch::NODE_TAB; }
     __device__ __forceinline__ SpillInfo* spill()       const { return at<SpillInfo>(scratch::OFF_SPILLINFO); }
     __device__ __forceinline__ uint32_t*  blockCursor(uint32_t p) const { return at<uint32_t>(scratch::OFF_BLOCKCUR) + p * scratch::BLOCK_CAP; }
+    __device__ __forceinline__ uint32_t*  runBloom()    const { return at<uint32_t>(scratch::OFF_RUNBLOOM); }     // [block][8]: leaves the block's run of the batch sits in
+    __device__ __forceinline__ uint32_t*  runFlag()     const { return at<uint32_t>(scratch::OFF_RUNFLAG); }      // [block]: the run must be revisited in the coming re-walk pass
     __device__ __forceinline__ uint32_t*  rowFree()     const { return at<uint32_t>(scratch::OFF_ROWFREE); }
     __device__ __forceinline__ uint64_t*  rows()        const { return at<uint64_t>(scratch::OFF_ROWS); }         // [ROW_CAP][64] chunk pointers of leaves, in list order
     __device__ __forceinline__ uint64_t*  chunkDir(uint32_t p) const { return at<uint64_t>(scratch::OFF_CHUNKDIR) + p * scratch::DIR_CAP; }
@@ -279,7 +285,7 @@ __device__ __forceinline__ void waitAllocBlock(const Ctx& c) {       // whole bl
 #define SIMLOD_VOXTAB_SIZE 64          // tuning knob (tools/exp_variants.py): power of two, <= 256
 #endif
 constexpr uint32_t VOXTAB_SIZE = SIMLOD_VOXTAB_SIZE;
-static_assert((VOXTAB_SIZE & (VOXTAB_SIZE - 1)) == 0 && VOXTAB_SIZE <= 256, "table size must be a power of two that one block can sweep");
+static_assert((VOXTAB_SIZE & (VOXTAB_SIZE - 1)) == 0 && VOXTAB_SIZE <= 128, "table size: a power of two, two tables are flushed by one 256-thread block, the index is packed into 7 bits");
 constexpr uint32_t VOXTAB_EMPTY = 0xffffffffu;
 __shared__ uint32_t sh_tabKey[VOXTAB_SIZE];
 __shared__ uint32_t sh_tabCount[VOXTAB_SIZE];
@@ -333,31 +339,54 @@ __device__ __noinline__ void recordVoxelShared(const Ctx c, const Batch b, uint3
 }
 
 __device__ __forceinline__ void recordVoxel(const Ctx& c, const Batch& b, uint32_t node, uint32_t cell, uint32_t color) {
+    // the lanes that arrive here together mostly created their voxel in the same node (a re-walk fills the grid of the
+    // node that was just split): one table probe and one add per warp then, instead of one per lane
+    const uint32_t active = __activemask();
+    const uint32_t leader = __ffs(active) - 1u;
+    const uint32_t node0 = __shfl_sync(active, node, leader);
+    if (__all_sync(active, node == node0)) {
+        const uint32_t n = __popc(active), mine = __popc(active & lanemaskLt());
+        uint32_t slot = 0, idx0 = 0, rank0 = 0, fit = 0;      // fit: how many of the n entries still fit the block's segment
+        if (laneId() == leader) {
+            slot = tabInsert(sh_tabKey, node0);
+            if (slot != VOXTAB_EMPTY) {
+                idx0 = atomicAdd(&sh_cursor, n);
+                fit = idx0 < c.segCap ? min(n, c.segCap - idx0) : 0u;
+                if (fit) rank0 = atomicAdd(&sh_tabCount[slot], fit);
+            }
+        }
+        slot = __shfl_sync(active, slot, leader); idx0 = __shfl_sync(active, idx0, leader); rank0 = __shfl_sync(active, rank0, leader); fit = __shfl_sync(active, fit, leader);
+        if (mine >= fit) { recordVoxelShared(c, b, node, cell, color); return; }
+        const uint64_t at = (uint64_t)blockIdx.x * c.segCap + idx0 + mine;
+        c.vkey(b.parity)[at] = (uint64_t)cell | ((uint64_t)slot << 21) | ((uint64_t)(rank0 + mine) << 41);      // node/slot patched in voxelFlushPatch
+        c.vcolor(b.parity)[at] = color;
+        return;
+    }
     uint32_t slot = tabInsert(sh_tabKey, node);
     if (slot == VOXTAB_EMPTY) { recordVoxelShared(c, b, node, cell, color); return; }
     uint32_t idx = atomicAdd(&sh_cursor, 1u);
     if (idx >= c.segCap) { recordVoxelShared(c, b, node, cell, color); return; }
     uint32_t rank = atomicAdd(&sh_tabCount[slot], 1u);
     uint64_t at = (uint64_t)blockIdx.x * c.segCap + idx;
-    c.vkey(b.parity)[at] = (uint64_t)cell | ((uint64_t)slot << 21) | ((uint64_t)rank << 41);      // node/slot patched in voxelPassEnd
+    c.vkey(b.parity)[at] = (uint64_t)cell | ((uint64_t)slot << 21) | ((uint64_t)rank << 41);      // node/slot patched in voxelFlushPatch
     c.vcolor(b.parity)[at] = color;
 }
 
-// (the caller has synchronised the block after the pass and after waitAllocBlock)
-__device__ __forceinline__ void voxelPassEnd(const Ctx& c, const Batch& b, bool freshPass) {
-    if (threadIdx.x < VOXTAB_SIZE) {
-        uint32_t node = sh_tabKey[threadIdx.x], cnt = sh_tabCount[threadIdx.x];
-        if (node != VOXTAB_EMPTY && cnt > 0) {
-            Node* nd = &c.nodes[node];
-            uint32_t base = atomicAdd(&nd->numVoxels, cnt);
-            if (base == ldv(&nd->numVoxelsStored)) {           // first voxels of this node in this batch
-                uint32_t d = atomicAdd(&b.bc->numDirtyVox, 1u);
-                c.dirtyVox(b.parity)[d] = node;
-            }
-            sh_tabBase[threadIdx.x] = base;
+// flush, step 1 (one thread per table entry): add the block's count to the node's numVoxels, remember the base
+__device__ __forceinline__ void voxelFlushEntry(const Ctx& c, const Batch& b, uint32_t entry) {
+    uint32_t node = sh_tabKey[entry], cnt = sh_tabCount[entry];
+    if (node != VOXTAB_EMPTY && cnt > 0) {
+        Node* nd = &c.nodes[node];
+        uint32_t base = atomicAdd(&nd->numVoxels, cnt);
+        if (base == ldv(&nd->numVoxelsStored)) {           // first voxels of this node in this batch
+            uint32_t d = atomicAdd(&b.bc->numDirtyVox, 1u);
+            c.dirtyVox(b.parity)[d] = node;
         }
+        sh_tabBase[entry] = base;
     }
-    __syncthreads();
+}
+// flush, step 2 (whole block, after a barrier): block-local (table slot, rank) -> (node, slot in the node's list)
+__device__ __forceinline__ void voxelFlushPatch(const Ctx& c, const Batch& b, bool freshPass) {
     const uint32_t endIdx = min(sh_cursor, c.segCap);
     uint64_t* vkey = c.vkey(b.parity);
     for (uint32_t e = sh_passStart + threadIdx.x; e < endIdx; e += blockDim.x) {
@@ -375,7 +404,6 @@ __device__ __forceinline__ void voxelPassEnd(const Ctx& c, const Batch& b, bool 
             atomicAdd(reinterpret_cast<unsigned long long*>(&c.ctl()->voxelsByPass[freshPass ? 0 : 1]), (unsigned long long)(endIdx - sh_passStart));
         }
     }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -387,17 +415,75 @@ __device__ __forceinline__ void voxelPassEnd(const Ctx& c, const Batch& b, bool 
 // leaf's total to the global counter once (where the spill / first-touch detection now happens)
 // and turns the provisional ranks of its items into slots.
 // ------------------------------------------------------------------------------------------
+// A provisional slot carries its table entry: bit 31 | entry << 24 | block-local rank (< 2^24: a block never
+// counts more than ITEM_CAP items); a final slot (table full, counted globally at once) is the plain index.
 constexpr uint32_t PROVISIONAL = 0x80000000u;
+static_assert(scratch::ITEM_CAP < (1u << 24), "block-local ranks must fit 24 bits");
 __shared__ uint32_t sh_leafKey[VOXTAB_SIZE];
 __shared__ uint32_t sh_leafCount[VOXTAB_SIZE];
 __shared__ uint32_t sh_leafBase[VOXTAB_SIZE];
-// Bloom filter over the leaves the block's own run of the batch currently sits in: a re-walk round rescans the
-// run only if one of the leaves that split in that round may be among them (a false positive costs a rescan)
+__shared__ uint8_t  sh_leafLevel[VOXTAB_SIZE];
+__device__ __forceinline__ uint32_t finalSlot(uint32_t sl) { return (sl & PROVISIONAL) ? sh_leafBase[(sl >> 24) & 127u] + (sl & 0xffffffu) : sl; }
+// the first-visit pass keeps the slots of the block's own run in shared memory until they are final
+constexpr uint32_t RUNSLOT_CAP = 2048;
+__shared__ uint32_t sh_runSlot[RUNSLOT_CAP];
+// block-wide exclusive prefix sum of one value per thread (256 threads); returns the block total
+__device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t& total) {
+    __shared__ uint32_t sh_warpSum[8];
+    __shared__ uint32_t sh_total;
+    const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+    __syncthreads();                       // protects sh_* against the previous call
+    if (lane == 31) sh_warpSum[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int w = 0; w < 8; w++) { uint32_t t = sh_warpSum[w]; sh_warpSum[w] = run; run += t; } sh_total = run; }
+    __syncthreads();
+    total = sh_total;
+    return sh_warpSum[warp] + incl - v;
+}
+
+// Re-walk rounds visit only the runs of the batch that can hold an item whose leaf was split in the round: every
+// run (= the contiguous piece of the batch one block counted in the first-visit pass) keeps a 256-bit Bloom filter of
+// the leaves its items sit in — built in shared memory during the first-visit pass, kept in global memory, extended
+// when a re-walk moves items of the run into new leaves. A round tests the few leaves it split against all filters,
+// and the items of the runs that may be affected are shared out evenly over the WHOLE grid (a false positive costs
+// a rescan of that run, never a missed item).
 constexpr uint32_t BLOOM_WORDS = 8;
+constexpr uint32_t AFFECTED_CAP = 1024;   // grids up to this many blocks build the list; larger ones rescan every run
 __shared__ uint32_t sh_runBloom[BLOOM_WORDS];
-__shared__ uint32_t sh_rescan;            // this block rescans its run in the current re-walk pass
-__device__ __forceinline__ void bloomAdd(uint32_t node) { uint32_t h = (node * 0x9E3779B1u) >> 24; atomicOr(&sh_runBloom[h >> 5], 1u << (h & 31u)); }
-__device__ __forceinline__ bool bloomTest(uint32_t node) { uint32_t h = (node * 0x9E3779B1u) >> 24; return (sh_runBloom[h >> 5] >> (h & 31u)) & 1u; }
+__shared__ uint32_t sh_affected[AFFECTED_CAP];
+__shared__ uint32_t sh_numAffected;
+__device__ __forceinline__ uint32_t bloomHash(uint32_t node) { return (node * 0x9E3779B1u) >> 24; }
+__device__ __forceinline__ void bloomAdd(uint32_t* bloom, uint32_t node) { uint32_t h = bloomHash(node); atomicOr(&bloom[h >> 5], 1u << (h & 31u)); }
+
+// The items of a re-walk pass, as one index space shared out evenly over the grid:
+//   [0, A * perRun)              the affected runs of the batch, concatenated
+//   then numSpilled entries      the spilled points of this batch (index MAX_BATCH + j in leafOf / slotOf)
+// It is handed out in warp-sized granules, round-robin over ALL warps of the grid (consecutive granules to different
+// SMs): a moved item costs a walk and usually a new voxel, an unmoved one a look-up, and both kinds as well as the
+// spilled points come in long stretches — every block gets the same mix this way.
+struct Rewalk { uint32_t perRun, runItems, total, spilledBefore; bool listed; };
+__device__ __forceinline__ Rewalk rewalkSlice(uint32_t numBatch, uint32_t numSpilled, uint32_t spilledBefore) {
+    Rewalk r;
+    r.perRun = ((numBatch + gridDim.x - 1) / gridDim.x + 31u) & ~31u;
+    r.listed = gridDim.x <= AFFECTED_CAP;
+    r.runItems = (r.listed ? sh_numAffected : gridDim.x) * r.perRun;
+    r.total = r.runItems + numSpilled;
+    r.spilledBefore = spilledBefore;
+    return r;
+}
+__device__ __forceinline__ uint32_t rewalkFirstGranule() { return ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u; }
+__device__ __forceinline__ uint32_t rewalkGranuleStride() { return gridDim.x * blockDim.x; }
+// index into leafOf / slotOf of item u (0xffffffff: padding of a run); run = the run it belongs to (spilled: none)
+__device__ __forceinline__ uint32_t rewalkItem(const Rewalk& r, uint32_t u, uint32_t& run) {
+    run = 0xffffffffu;
+    if (u >= r.runItems) return (uint32_t)scratch::MAX_BATCH + (u - r.runItems);
+    const uint32_t k = u / r.perRun;
+    run = r.listed ? sh_affected[k] : k;
+    return run * r.perRun + (u - k * r.perRun);
+}
 
 // the global step: add `cnt` points to a leaf's counter; first-touch and spill detection (voxels.cu:203-218)
 __device__ __noinline__ uint32_t countGlobal(const Ctx c, const Batch b, uint32_t node, uint32_t level, uint32_t cnt) {
@@ -464,9 +550,9 @@ __device__ __noinline__ uint32_t countGlobal(const Ctx c, const Batch b, uint32_
 // ------------------------------------------------------------------------------------------
 struct LeafCache { uint32_t node, level, kx, ky, kz, parent; };      // node == VOXTAB_EMPTY: nothing cached
 
-template <bool SAMPLE, bool COUNT, bool UNCACHED_GRID>
+template <bool SAMPLE, bool COUNT, bool UNCACHED_GRID, bool DEDUP>
 __device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& cache, bool valid, uint4 pt, uint32_t node, uint32_t level,
-                                     uint32_t stopLevel, bool runItem, uint32_t& leafPacked, uint32_t& slot) {
+                                     uint32_t stopLevel, uint32_t* bloom, uint32_t& leafPacked, uint32_t& slot) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = laneId();
     const uint32_t ltmask = lanemaskLt();
@@ -521,10 +607,16 @@ __device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& ca
                     // (voxels.cu:370-382): the one pass that follows such a clear reads through L2 instead.
                     uint32_t seen = UNCACHED_GRID ? ldcg(word) : *word;
                     if ((seen & bit) == 0) {
-                        // neighbouring points hit the same cell: one atomic per distinct cell among the converged lanes
-                        uint32_t active = __activemask();
-                        uint32_t peers = __match_any_sync(active, (uint64_t)(uintptr_t)word * 32ull + (cell & 31u));
-                        if (lane == (uint32_t)__ffs(peers) - 1u) {
+                        // first-visit passes: neighbouring points of a scan hit the same cell, so one atomic per distinct cell
+                        // among the converged lanes. Re-walk passes fill freshly cleared grids, where the cells of a warp's
+                        // items are mostly distinct and the match would cost more than the few atomics it saves.
+                        bool mine = true;
+                        if (DEDUP) {
+                            uint32_t active = __activemask();
+                            uint32_t peers = __match_any_sync(active, (uint64_t)(uintptr_t)word * 32ull + (cell & 31u));
+                            mine = lane == (uint32_t)__ffs(peers) - 1u;
+                        }
+                        if (mine) {
                             if (pending == 3) settle();
                             uint32_t old = atomicOr(word, bit);
                             if (pending == 0) { old0 = old; key0 = sNode; cel0 = cell; }
@@ -554,9 +646,9 @@ __device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& ca
             uint32_t r = 0;
             if (lane == leader) {
                 uint32_t t = tabInsert(sh_leafKey, node);
-                if (t != VOXTAB_EMPTY) r = atomicAdd(&sh_leafCount[t], cnt) | PROVISIONAL;     // block-local rank
+                if (t != VOXTAB_EMPTY) { r = atomicAdd(&sh_leafCount[t], cnt) | PROVISIONAL | (t << 24); sh_leafLevel[t] = (uint8_t)level; }   // block-local rank
                 else                   r = countGlobal(c, b, node, level, cnt);                // table full: final slot at once
-                if (runItem) bloomAdd(node);
+                if (bloom) bloomAdd(bloom, node);
             }
             r = __shfl_sync(peers, r, leader);
             slot = r + __popc(peers & ltmask);
@@ -614,6 +706,24 @@ __device__ __forceinline__ void blockRun(uint32_t numBatch, uint32_t& first, uin
     end = min(numBatch, first + perBlock);
 }
 
+// Split phase, every block for its own run: can the run hold an item of one of the leaves split in this round?
+// (The filters are only extended during re-walk passes, and the verdicts are read after the barrier that ends the
+// split phase, so every block sees the same set of affected runs.)
+__device__ __forceinline__ void markAffectedRun(const Ctx& c, const Batch& b, uint32_t spillBegin, uint32_t spillEnd) {
+    if (threadIdx.x >= 32) return;
+    const uint32_t perRun = ((b.size + gridDim.x - 1) / gridDim.x + 31u) & ~31u;
+    uint32_t flag = 0;
+    if (blockIdx.x * perRun < b.size) {
+        const uint32_t* bloom = c.runBloom() + blockIdx.x * BLOOM_WORDS;
+        for (uint32_t k = spillBegin + threadIdx.x; k < spillEnd; k += 32) {
+            const uint32_t h = bloomHash(c.spill()[k].node);
+            flag |= (ldcg(&bloom[h >> 5]) >> (h & 31u)) & 1u;
+        }
+        flag = __any_sync(0xffffffffu, flag != 0) ? 1u : 0u;
+    }
+    if (threadIdx.x == 0) c.runFlag()[blockIdx.x] = flag;
+}
+
 // ------------------------------------------------------------------------------------------
 // one pass over the batch points (ring slot) followed by the spilled points of this batch
 //   FRESH  : items start at the root (first visit); otherwise only items whose cached leaf has
@@ -621,7 +731,7 @@ __device__ __forceinline__ void blockRun(uint32_t numBatch, uint32_t& first, uin
 //   the table flush (leaf counters, voxel counters) is left to the caller: passFlush()
 // ------------------------------------------------------------------------------------------
 template <bool SAMPLE, bool COUNT, bool FRESH, bool UNCACHED_GRID>
-__device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t numSpilled, uint32_t spillBegin, uint32_t spillEnd) {
+__device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t numSpilled, uint32_t spilledBefore, uint32_t spillBegin, uint32_t spillEnd) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t* leafOf = c.leafOf(b.parity);
@@ -631,18 +741,8 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
     LeafCache cache;
     cache.node = VOXTAB_EMPTY; cache.level = 0; cache.kx = cache.ky = cache.kz = 0; cache.parent = VOXTAB_EMPTY;
 
-    // re-walk rounds: can the block's run hold an item whose leaf was split in the round that just ended?
-    bool rescan = false;
-    if (!FRESH) {
-        if (threadIdx.x == 0) sh_rescan = 0;
-        __syncthreads();
-        for (uint32_t k = spillBegin + threadIdx.x; k < spillEnd; k += blockDim.x)
-            if (bloomTest(c.spill()[k].node)) sh_rescan = 1u;
-        __syncthreads();
-        rescan = sh_rescan != 0;
-    }
-    if ((FRESH && COUNT) || rescan) { if (threadIdx.x < BLOOM_WORDS) sh_runBloom[threadIdx.x] = 0; }     // rebuilt by this pass
     if (COUNT && threadIdx.x < VOXTAB_SIZE) { sh_leafKey[threadIdx.x] = VOXTAB_EMPTY; sh_leafCount[threadIdx.x] = 0; }
+    if (FRESH && COUNT && threadIdx.x < BLOOM_WORDS) sh_runBloom[threadIdx.x] = 0;
     if (SAMPLE) voxelPassBegin(c, b, FRESH);
     __syncthreads();
 
@@ -664,83 +764,113 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
                 const bool valid = i < blockEnd;
                 uint4 pt = valid ? sh_tile[t & 1][idx] : make_uint4(0, 0, 0, 0);
                 uint32_t lp = 0, slot = 0;
-                walk<SAMPLE, COUNT, UNCACHED_GRID>(c, b, cache, valid, pt, 0, 0, 0, true, lp, slot);
-                if (valid && COUNT) { leafOf[i] = lp; slotOf[i] = slot; }
+                walk<SAMPLE, COUNT, UNCACHED_GRID, true>(c, b, cache, valid, pt, 0, 0, 0, COUNT ? sh_runBloom : nullptr, lp, slot);
+                if (valid && COUNT) {
+                    leafOf[i] = lp;
+                    if (runLen <= RUNSLOT_CAP) sh_runSlot[i - blockFirst] = slot; else slotOf[i] = slot;
+                }
             }
             __syncthreads();
         }
         if (threadIdx.x == 0) { sh_tilePhase[0] = ph0; sh_tilePhase[1] = ph1; }
-    } else if (rescan) {
-        for (uint32_t base = blockFirst + (threadIdx.x - laneId()); base < blockEnd; base += blockDim.x) {
-            uint32_t i = base + laneId();
-            bool valid = i < blockEnd;
-            uint32_t node = 0, level = 0;
+        if (COUNT && threadIdx.x < BLOOM_WORDS) c.runBloom()[blockIdx.x * BLOOM_WORDS + threadIdx.x] = sh_runBloom[threadIdx.x];
+    } else {
+        // ---- the runs that can hold an item whose leaf was split in the round that just ended: every block published
+        // its own run's verdict before the barrier (markAffectedRun), so all blocks build the same list
+        if (gridDim.x <= AFFECTED_CAP) {
+            const uint32_t* flags = c.runFlag();
+            uint32_t numAffected = 0;
+            for (uint32_t g0 = 0; g0 < gridDim.x; g0 += blockDim.x) {          // block-uniform trip count
+                const uint32_t g = g0 + threadIdx.x;
+                const uint32_t flag = g < gridDim.x ? ldcg(&flags[g]) : 0u;
+                uint32_t total = 0;
+                const uint32_t off = blockExclusiveScan(flag, total);
+                if (flag) sh_affected[numAffected + off] = g;
+                numAffected += total;
+            }
+            if (threadIdx.x == 0) sh_numAffected = numAffected;
+            __syncthreads();
+        }
+        // ---- the affected runs and the spilled points as one item space --------------------------------------------
+        const Rewalk rw = rewalkSlice(b.size, numSpilled, spilledBefore);
+#if SIMLOD_TIMERS >= 2
+        uint64_t tList = 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { tList = globaltimer(); c.ctl()->subNanos[14] += rw.total; c.ctl()->subNanos[15] += rw.runItems; }
+#endif
+        for (uint32_t base = rewalkFirstGranule(); base < rw.total; base += rewalkGranuleStride()) {
+            const uint32_t u = base + laneId();
+            uint32_t run = 0xffffffffu, i = 0xffffffffu, node = 0, level = 0;
+            bool valid = u < rw.total;
+            const bool spilledItem = valid && u >= rw.runItems;
+            if (valid) { i = rewalkItem(rw, u, run); valid = spilledItem || i < b.size; }      // (the last run is padded)
+            uint4 pt = make_uint4(0, 0, 0, 0);
+            if (spilledItem) pt = *reinterpret_cast<const uint4*>(c.spilled() + (i - scratch::MAX_BATCH));     // independent of the leaf look-up
             if (valid) {
                 uint32_t lp = leafOf[i];
                 node = lp & 0xffffffu; level = lp >> 24;
-                const bool moved = c.firstChild()[node] != 0 && level < SIMLOD_MAX_DEPTH;
-                if (!moved) {                                // stays where it is: keep its leaf in the run's filter
-                    uint32_t peers = __match_any_sync(__activemask(), node);
-                    if (laneId() == (uint32_t)__ffs(peers) - 1u) bloomAdd(node);
-                }
-                valid = moved;
+                // points spilled in the round that just ended sit in a leaf that was split in it: no need to look
+                if (!(spilledItem && i - scratch::MAX_BATCH >= rw.spilledBefore)) valid = c.firstChild()[node] != 0 && level < SIMLOD_MAX_DEPTH;
             }
             if (!__any_sync(0xffffffffu, valid)) continue;
-            uint4 pt = make_uint4(0, 0, 0, 0);
-            if (valid) pt = ldPoint(b.points + i);
+            if (valid && !spilledItem) pt = ldPoint(b.points + i);
             uint32_t lp = 0, slot = 0;
-            walk<SAMPLE, COUNT, UNCACHED_GRID>(c, b, cache, valid, pt, node, level, level, true, lp, slot);
+            walk<SAMPLE, COUNT, UNCACHED_GRID, false>(c, b, cache, valid, pt, node, level, level, run != 0xffffffffu ? c.runBloom() + run * BLOOM_WORDS : nullptr, lp, slot);
             if (valid && COUNT) { leafOf[i] = lp; slotOf[i] = slot; }
         }
+#if SIMLOD_TIMERS >= 2
+        if (blockIdx.x == 0 && threadIdx.x == 0) c.ctl()->subNanos[13] += globaltimer() - tList;      // warp 0's loop alone
+#endif
     }
-    // spilled points (always carry a cached start node: the leaf they were spilled from)
-    for (uint32_t base = tid - laneId(); base < numSpilled; base += stride) {
-        uint32_t j = base + laneId();
-        bool valid = j < numSpilled;
-        uint32_t node = 0, level = 0;
-        if (valid && !(FRESH && !COUNT)) {       // sampling-only fresh pass restarts at the root
-            uint32_t lp = leafOf[scratch::MAX_BATCH + j];
-            node = lp & 0xffffffu; level = lp >> 24;
-            valid = c.firstChild()[node] != 0 && level < SIMLOD_MAX_DEPTH;
+    if (FRESH) {
+        // spilled points of this batch, from the root (sampling-only pass after a root split)
+        for (uint32_t base = tid - laneId(); base < numSpilled; base += stride) {
+            uint32_t j = base + laneId();
+            bool valid = j < numSpilled;
+            uint4 pt = make_uint4(0, 0, 0, 0);
+            if (valid) pt = *reinterpret_cast<const uint4*>(c.spilled() + j);
+            uint32_t lp = 0, slot = 0;
+            walk<SAMPLE, COUNT, UNCACHED_GRID, true>(c, b, cache, valid, pt, 0, 0, 0, nullptr, lp, slot);
         }
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        uint4 pt = make_uint4(0, 0, 0, 0);
-        if (valid) pt = *reinterpret_cast<const uint4*>(c.spilled() + j);
-        uint32_t lp = 0, slot = 0;
-        walk<SAMPLE, COUNT, UNCACHED_GRID>(c, b, cache, valid, pt, node, level, level, false, lp, slot);
-        if (valid && COUNT) { leafOf[scratch::MAX_BATCH + j] = lp; slotOf[scratch::MAX_BATCH + j] = slot; }
     }
     __syncthreads();
 }
 
-// flush the block's tables after passItems: one global add per distinct leaf / voxel node, then provisional
-// ranks -> slots. Must run after waitAllocBlock() when an allocation is in flight.
+// flush the block's tables after passItems: one global add per distinct leaf / voxel node (the two tables side by
+// side), then block-local ranks -> slots. Must run after waitAllocBlock() when an allocation is in flight.
 template <bool SAMPLE, bool COUNT, bool FRESH>
-__device__ __forceinline__ void passFlush(const Ctx& c, const Batch& b, uint32_t numSpilled) {
-    if (SAMPLE) voxelPassEnd(c, b, FRESH);
-    if (COUNT) {
-        const uint32_t stride = gridDim.x * blockDim.x;
-        const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-        uint32_t* leafOf = c.leafOf(b.parity);
-        uint32_t* slotOf = c.slotOf(b.parity);
-        if (threadIdx.x < VOXTAB_SIZE) {
-            uint32_t leaf = sh_leafKey[threadIdx.x], cnt = sh_leafCount[threadIdx.x];
-            if (leaf != VOXTAB_EMPTY && cnt > 0) sh_leafBase[threadIdx.x] = countGlobal(c, b, leaf, c.nodes[leaf].level, cnt);
-        }
-        __syncthreads();
-        uint32_t blockFirst, blockEnd;
-        blockRun(b.size, blockFirst, blockEnd);
-        if (!FRESH && sh_rescan == 0) blockEnd = blockFirst;          // the run was not visited in this pass
-        for (uint32_t i = blockFirst + threadIdx.x; i < blockEnd; i += blockDim.x) {
-            uint32_t sl = slotOf[i];
-            if (sl & PROVISIONAL) slotOf[i] = sh_leafBase[tabFind(sh_leafKey, leafOf[i] & 0xffffffu)] + (sl & ~PROVISIONAL);
-        }
-        for (uint32_t j = tid; j < numSpilled; j += stride) {
-            uint32_t sl = slotOf[scratch::MAX_BATCH + j];
-            if (sl & PROVISIONAL) slotOf[scratch::MAX_BATCH + j] = sh_leafBase[tabFind(sh_leafKey, leafOf[scratch::MAX_BATCH + j] & 0xffffffu)] + (sl & ~PROVISIONAL);
-        }
-        __syncthreads();
+__device__ __forceinline__ void passFlush(const Ctx& c, const Batch& b, uint32_t numSpilled, uint32_t spilledBefore) {
+    if (COUNT && threadIdx.x < VOXTAB_SIZE) {
+        uint32_t leaf = sh_leafKey[threadIdx.x], cnt = sh_leafCount[threadIdx.x];
+        if (leaf != VOXTAB_EMPTY && cnt > 0) sh_leafBase[threadIdx.x] = countGlobal(c, b, leaf, sh_leafLevel[threadIdx.x], cnt);
+    } else if (SAMPLE && threadIdx.x >= 128 && threadIdx.x < 128 + VOXTAB_SIZE) {
+        voxelFlushEntry(c, b, threadIdx.x - 128);
     }
+    __syncthreads();
+    if (SAMPLE) voxelFlushPatch(c, b, FRESH);
+    if (COUNT) {
+        uint32_t* slotOf = c.slotOf(b.parity);
+        if (FRESH) {
+            uint32_t blockFirst, blockEnd;
+            blockRun(b.size, blockFirst, blockEnd);
+            if (blockEnd - blockFirst <= RUNSLOT_CAP) {
+                for (uint32_t i = blockFirst + threadIdx.x; i < blockEnd; i += blockDim.x) slotOf[i] = finalSlot(sh_runSlot[i - blockFirst]);
+            } else {
+                for (uint32_t i = blockFirst + threadIdx.x; i < blockEnd; i += blockDim.x) { uint32_t sl = slotOf[i]; if (sl & PROVISIONAL) slotOf[i] = finalSlot(sl); }
+            }
+        } else {                                                          // the items this block visited in passItems
+            const Rewalk rw = rewalkSlice(b.size, numSpilled, spilledBefore);
+            for (uint32_t base = rewalkFirstGranule(); base < rw.total; base += rewalkGranuleStride()) {
+                const uint32_t u = base + laneId();
+                if (u >= rw.total) continue;
+                uint32_t run;
+                const uint32_t i = rewalkItem(rw, u, run);
+                if (u < rw.runItems && i >= b.size) continue;               // padding of the last run
+                uint32_t sl = slotOf[i];
+                if (sl & PROVISIONAL) slotOf[i] = finalSlot(sl);
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -846,68 +976,41 @@ __device__ __noinline__ void splitRound(const Ctx c, const Batch b, uint32_t beg
 // ------------------------------------------------------------------------------------------
 // chunk allocation for the nodes touched by a batch (voxels.cu:485-538, 641-672)
 // ------------------------------------------------------------------------------------------
-// block-wide exclusive prefix sum of one value per thread (256 threads); returns the block total
-__device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t& total) {
-    __shared__ uint32_t sh_warpSum[8];
-    __shared__ uint32_t sh_total;
-    const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
-    __syncthreads();                       // protects sh_* against the previous call
-    if (lane == 31) sh_warpSum[warp] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) { uint32_t run = 0; for (int w = 0; w < 8; w++) { uint32_t t = sh_warpSum[w]; sh_warpSum[w] = run; run += t; } sh_total = run; }
-    __syncthreads();
-    total = sh_total;
-    return sh_warpSum[warp] + incl - v;
-}
-
-// The reference lets every node thread bump numAllocatedChunks / the heap offset once per chunk
-// (voxels.cu:505-511). Here a block adds its whole demand with ONE atomic per counter and hands out
-// sub-ranges by prefix sum: the same totals, the same pooled-vs-fresh split (indices >= chunkPoolSize
-// are fresh), a handful of atomics.
+// One WARP per touched node, the nodes spread over all warps of the grid (a batch touches a few hundred): the lanes
+// fetch / link the node's new chunks side by side, so a node costs a handful of dependent memory round trips
+// whatever the number of chunks — the reference walks every node's list with one thread and bumps
+// numAllocatedChunks / the heap offset once per chunk (voxels.cu:505-511). The totals, and the pooled-vs-fresh
+// split (stack indices >= chunkPoolSize are fresh heap chunks), are the same.
 __device__ __noinline__ void allocateChunks(const Ctx c, const Batch b) {
-    __shared__ uint64_t sh_a0, sh_freshOff, sh_firstFresh;
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = laneId();
+    const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;        // consecutive nodes go to different SMs
     const uint32_t numDirtyLeaves = ldv(&b.bc->numDirtyLeaves);
     const uint32_t numDirtyVox = ldv(&b.bc->numDirtyVox);
     const uint64_t poolSize = ldv(&c.stats->chunkPoolSize);
     const uint32_t* dirtyLeaves = c.dirtyLeaves(b.parity);
     const uint32_t* dirtyVox = c.dirtyVox(b.parity);
 
-    for (uint32_t first = blockIdx.x * blockDim.x; first < numDirtyLeaves; first += stride) {      // block-uniform trip count
-        const uint32_t d = first + threadIdx.x;
-        uint32_t n = 0, cnt = 0, have = 0, existing = 0, needed = 0;
-        Node* node = nullptr;
-        bool live = false;
-        if (d < numDirtyLeaves) {
-            n = dirtyLeaves[d];
-            if (c.firstChild()[n] == 0) {                       // else: became an inner node in this batch
-                node = &c.nodes[n];
-                cnt = node->counter; have = node->numPoints;
-                if (cnt > have) {
-                    live = true;
-                    existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-                    uint32_t required = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-                    if (required > scratch::ROW_SLOTS) { atomicOr(&c.ctl()->errorFlags, ERR_ROW_OVERFLOW); required = scratch::ROW_SLOTS; }   // insertion drops the excess
-                    needed = required > existing ? required - existing : 0;
-                }
-            }
-        }
-        uint32_t total = 0;
-        const uint32_t offset = blockExclusiveScan(needed, total);
-        if (threadIdx.x == 0 && total > 0) {
-            uint64_t a0 = atomicAdd(reinterpret_cast<unsigned long long*>(&c.stats->numAllocatedChunks), (unsigned long long)total);
-            uint64_t firstFresh = a0 > poolSize ? a0 : poolSize;          // indices >= poolSize are new heap chunks (voxels.cu:509-515)
-            uint64_t numFresh = a0 + total > firstFresh ? a0 + total - firstFresh : 0;
-            sh_a0 = a0; sh_firstFresh = firstFresh;
-            sh_freshOff = numFresh ? atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap()->offset), (unsigned long long)(numFresh * SIMLOD_CHUNK_STRIDE)) : 0;
-        }
-        __syncthreads();
-        if (live) {
-            if (needed > 0) {
-                uint32_t row = c.leafRow()[n];
+    for (uint32_t d = warp; d < numDirtyLeaves; d += numWarps) {
+        const uint32_t n = dirtyLeaves[d];
+        if (c.firstChild()[n] != 0) continue;                       // became an inner node in this batch
+        Node* node = &c.nodes[n];
+        const uint32_t cnt = node->counter, have = node->numPoints;
+        if (cnt <= have) continue;
+        const uint32_t existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        uint32_t required = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        if (required > scratch::ROW_SLOTS) { if (lane == 0) atomicOr(&c.ctl()->errorFlags, ERR_ROW_OVERFLOW); required = scratch::ROW_SLOTS; }   // insertion drops the excess
+        const uint32_t needed = required > existing ? required - existing : 0;       // <= 64
+        if (needed > 0) {
+            uint64_t a0 = 0, freshOff = 0;
+            uint32_t row = 0;
+            if (lane == 0) {
+                a0 = atomicAdd(reinterpret_cast<unsigned long long*>(&c.stats->numAllocatedChunks), (unsigned long long)needed);
+                const uint64_t firstFresh = a0 > poolSize ? a0 : poolSize;          // indices >= poolSize are new heap chunks (voxels.cu:509-515)
+                const uint64_t numFresh = a0 + needed > firstFresh ? a0 + needed - firstFresh : 0;
+                if (numFresh) freshOff = atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap()->offset), (unsigned long long)(numFresh * SIMLOD_CHUNK_STRIDE));
+                row = c.leafRow()[n];
                 if (row == 0) {                                 // first chunk of this leaf: take a row (recycled first)
                     uint32_t f = atomicSub(&c.ctl()->rowFreeCount, 1u);
                     if (f >= 1 && f <= scratch::ROW_CAP) {
@@ -920,74 +1023,74 @@ __device__ __noinline__ void allocateChunks(const Ctx c, const Batch b) {
                     }
                     c.leafRow()[n] = row;
                 }
-                if (row != 0) {
-                    uint64_t* slots = c.rows() + (uint64_t)(row - 1) * scratch::ROW_SLOTS;
-                    Chunk* tail = existing ? reinterpret_cast<Chunk*>(slots[existing - 1]) : nullptr;
-                    const uint64_t a0 = sh_a0 + offset, firstFresh = sh_firstFresh, freshOff = sh_freshOff;
-                    for (uint32_t t = 0; t < needed; t++) {
-                        uint64_t idx = a0 + t;
-                        Chunk* chunk = idx < poolSize ? reinterpret_cast<Chunk*>(c.chunkQueue()[idx])
-                                                      : reinterpret_cast<Chunk*>(c.heapBytes + freshOff + (idx - firstFresh) * SIMLOD_CHUNK_STRIDE);
-                        chunk->next = nullptr;
-                        if (tail) tail->next = chunk; else node->points = chunk;
-                        tail = chunk;
-                        slots[existing + t] = (uint64_t)chunk;
+            }
+            a0 = __shfl_sync(FULL, a0, 0); freshOff = __shfl_sync(FULL, freshOff, 0); row = __shfl_sync(FULL, row, 0);
+            if (row != 0) {
+                const uint64_t firstFresh = a0 > poolSize ? a0 : poolSize;
+                uint64_t* slots = c.rows() + (uint64_t)(row - 1) * scratch::ROW_SLOTS;
+                // lane l owns new chunks l and l + 32; every chunk's `next` is written by its owner only
+                uint64_t ch[2] = {0, 0};
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t t = lane + 32u * h;
+                    if (t < needed) {
+                        const uint64_t idx = a0 + t;
+                        ch[h] = idx < poolSize ? c.chunkQueue()[idx] : (uint64_t)(c.heapBytes + freshOff + (idx - firstFresh) * SIMLOD_CHUNK_STRIDE);
+                        slots[existing + t] = ch[h];
                     }
                 }
+                const uint64_t nextA = __shfl_down_sync(FULL, ch[0], 1), firstB = __shfl_sync(FULL, ch[1], 0), nextB = __shfl_down_sync(FULL, ch[1], 1);
+                if (lane < needed) reinterpret_cast<Chunk*>(ch[0])->next = reinterpret_cast<Chunk*>(lane + 1 < needed ? (lane == 31 ? firstB : nextA) : 0ull);
+                if (lane + 32u < needed) reinterpret_cast<Chunk*>(ch[1])->next = reinterpret_cast<Chunk*>(lane + 33u < needed ? nextB : 0ull);
+                if (lane == 0) {
+                    if (existing) reinterpret_cast<Chunk*>(slots[existing - 1])->next = reinterpret_cast<Chunk*>(ch[0]);
+                    else node->points = reinterpret_cast<Chunk*>(ch[0]);
+                }
             }
-            node->numPoints = cnt;      // slots [have, cnt) were handed out by the counting pass; filled by insertAll
         }
+        if (lane == 0) node->numPoints = cnt;      // slots [have, cnt) were handed out by the counting pass; filled by insertAll
     }
 
-    // (served from the other end of the grid, so that leaf and voxel-node allocation run side by side)
-    for (uint32_t first = (gridDim.x - 1 - blockIdx.x) * blockDim.x; first < numDirtyVox; first += stride) {
-        const uint32_t d = first + threadIdx.x;
-        uint32_t n = 0, cnt = 0, have = 0, existing = 0, needed = 0, nseg = 0, k0 = 0;
-        Node* node = nullptr;
-        bool live = false;
-        if (d < numDirtyVox) {
-            n = dirtyVox[d];
-            node = &c.nodes[n];
-            cnt = node->numVoxels; have = node->numVoxelsStored;
-            if (cnt > have) {
-                live = true;
-                k0 = have / SIMLOD_POINTS_PER_CHUNK;
-                nseg = (cnt - 1) / SIMLOD_POINTS_PER_CHUNK - k0 + 1;
-                existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-                needed = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK - existing;
+    // voxel lists: always fresh heap memory, never recycled (voxels.cu:652-666), so a node's new chunks are contiguous.
+    // (served from the other end of the warp order, so that leaf and voxel-node allocation land on different warps)
+    for (uint32_t d = numWarps - 1 - warp; d < numDirtyVox; d += numWarps) {
+        const uint32_t n = dirtyVox[d];
+        Node* node = &c.nodes[n];
+        const uint32_t cnt = node->numVoxels, have = node->numVoxelsStored;
+        if (cnt <= have) continue;
+        const uint32_t k0 = have / SIMLOD_POINTS_PER_CHUNK;
+        const uint32_t nseg = (cnt - 1) / SIMLOD_POINTS_PER_CHUNK - k0 + 1;
+        const uint32_t existing = (have + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+        const uint32_t needed = (cnt + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK - existing;
+        uint64_t freshOff = 0, tailPtr = 0;
+        uint32_t base = 0;
+        if (lane == 0) {
+            if (needed) freshOff = atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap()->offset), (unsigned long long)((uint64_t)needed * SIMLOD_CHUNK_STRIDE));
+            base = atomicAdd(&b.bc->dirCursor, nseg);
+            tailPtr = node->voxelChunks ? c.voxelTail()[n] : 0ull;
+        }
+        freshOff = __shfl_sync(FULL, freshOff, 0); base = __shfl_sync(FULL, base, 0); tailPtr = __shfl_sync(FULL, tailPtr, 0);
+        if ((uint64_t)base + nseg > scratch::DIR_CAP) {
+            if (lane == 0) { atomicOr(&c.ctl()->errorFlags, ERR_DIR_OVERFLOW); c.voxelDir()[n] = DirEntry{0xffffffffu, 0}; }
+            continue;
+        }
+        uint64_t* chunkDir = c.chunkDir(b.parity);
+        const uint32_t j0 = (have % SIMLOD_POINTS_PER_CHUNK != 0) ? 1u : 0u;         // the partly filled tail chunk takes this batch's first voxels
+        uint8_t* first = c.heapBytes + freshOff;
+        for (uint32_t t = lane; t < needed; t += 32) {
+            Chunk* chunk = reinterpret_cast<Chunk*>(first + (uint64_t)t * SIMLOD_CHUNK_STRIDE);
+            chunk->next = t + 1 < needed ? reinterpret_cast<Chunk*>(first + (uint64_t)(t + 1) * SIMLOD_CHUNK_STRIDE) : nullptr;
+            chunkDir[base + j0 + t] = (uint64_t)chunk;
+        }
+        if (lane == 0) {
+            c.voxelDir()[n] = DirEntry{base, k0};
+            if (j0) chunkDir[base] = tailPtr;
+            if (needed > 0) {
+                if (tailPtr) reinterpret_cast<Chunk*>(tailPtr)->next = reinterpret_cast<Chunk*>(first); else node->voxelChunks = reinterpret_cast<Chunk*>(first);
+                c.voxelTail()[n] = (uint64_t)(first + (uint64_t)(needed - 1) * SIMLOD_CHUNK_STRIDE);
             }
+            node->numVoxelsStored = cnt;
         }
-        uint32_t totalNeeded = 0, totalSeg = 0;
-        const uint32_t offNeeded = blockExclusiveScan(needed, totalNeeded);
-        const uint32_t offSeg = blockExclusiveScan(nseg, totalSeg);
-        if (threadIdx.x == 0) {
-            // voxel chunks are never recycled: always fresh heap memory (voxels.cu:652-666)
-            sh_freshOff = totalNeeded ? atomicAdd(reinterpret_cast<unsigned long long*>(&c.heap()->offset), (unsigned long long)((uint64_t)totalNeeded * SIMLOD_CHUNK_STRIDE)) : 0;
-            sh_a0 = totalSeg ? atomicAdd(&b.bc->dirCursor, totalSeg) : 0;
-        }
-        __syncthreads();
-        if (live) {
-            const uint32_t base = (uint32_t)sh_a0 + offSeg;
-            if ((uint64_t)base + nseg > scratch::DIR_CAP) { atomicOr(&c.ctl()->errorFlags, ERR_DIR_OVERFLOW); c.voxelDir()[n] = DirEntry{0xffffffffu, 0}; }
-            else {
-                uint64_t* chunkDir = c.chunkDir(b.parity);
-                c.voxelDir()[n] = DirEntry{base, k0};
-                Chunk* tail = node->voxelChunks ? reinterpret_cast<Chunk*>(c.voxelTail()[n]) : nullptr;
-                uint32_t j = 0;
-                if (have % SIMLOD_POINTS_PER_CHUNK != 0) chunkDir[base + j++] = (uint64_t)tail;
-                const uint64_t freshOff = sh_freshOff + (uint64_t)offNeeded * SIMLOD_CHUNK_STRIDE;
-                for (uint32_t t = 0; t < needed; t++) {
-                    Chunk* chunk = reinterpret_cast<Chunk*>(c.heapBytes + freshOff + (uint64_t)t * SIMLOD_CHUNK_STRIDE);
-                    chunk->next = nullptr;
-                    if (tail) tail->next = chunk; else node->voxelChunks = chunk;
-                    tail = chunk;
-                    chunkDir[base + j++] = (uint64_t)chunk;
-                }
-                if (needed > 0) c.voxelTail()[n] = (uint64_t)tail;
-                node->numVoxelsStored = cnt;
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -1025,64 +1128,94 @@ __device__ __forceinline__ void insertVoxel(const Ctx& c, uint32_t parity, uint6
     stPoint(&chunk->points[vslot % SIMLOD_POINTS_PER_CHUNK], v);
 }
 
+// The insertion work of a batch — its points, its spilled points, its voxels — is one index space handed out in
+// tiles from an atomic cursor: insertion shares a phase with the counting of the next batch, whose cost per block
+// depends on the data, so blocks that finish counting early take more tiles and the phase ends together.
+constexpr uint32_t INSERT_TILE = 1024;      // 4 items per thread
+
 __device__ __noinline__ void insertAll(const Ctx c, const Batch b, uint32_t numSpilled, uint32_t numSharedVoxels) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t* leafOf = c.leafOf(b.parity);
     const uint32_t* slotOf = c.slotOf(b.parity);
     const uint32_t* leafRow = c.leafRow();
-    // two independent items per iteration: the three dependent lookups (item -> leaf row -> chunk) of one
-    // overlap with those of the other
-    for (uint32_t i = tid; i < b.size; i += 2 * stride) {
-        const uint32_t i2 = i + stride;
-        const bool has2 = i2 < b.size;
-        uint4 p1 = ldPoint(b.points + i);
-        uint4 p2 = has2 ? ldPoint(b.points + i2) : make_uint4(0, 0, 0, 0);
-        uint32_t n1 = leafOf[i] & 0xffffffu, s1 = slotOf[i];
-        uint32_t n2 = has2 ? (leafOf[i2] & 0xffffffu) : 0u, s2 = has2 ? slotOf[i2] : 0u;
-        uint32_t r1 = leafRow[n1], r2 = has2 ? leafRow[n2] : 0u;
-        Point* d1 = pointSlotAddress(c, r1, s1);
-        Point* d2 = has2 ? pointSlotAddress(c, r2, s2) : nullptr;
-        if (d1) stPoint(d1, p1);
-        if (d2) stPoint(d2, p2);
-    }
-    for (uint32_t j = tid; j < numSpilled; j += stride) {
-        uint4 pt = *reinterpret_cast<const uint4*>(c.spilled() + j);
-        uint32_t node = leafOf[scratch::MAX_BATCH + j] & 0xffffffu;
-        Point* d = pointSlotAddress(c, leafRow[node], slotOf[scratch::MAX_BATCH + j]);
-        if (d) stPoint(d, pt);
-    }
-    // voxels: the per-block backlog segments are uneven, so every block first builds the prefix sums of
-    // the segment fills in shared memory and the whole grid then strides over the concatenation
+    // voxels: the per-block backlog segments are uneven; prefix sums of the segment fills (in shared memory, every
+    // block the same) turn a position in their concatenation into (segment, entry) by binary search
     __shared__ uint32_t sh_segStart[1025];
+    __shared__ uint32_t sh_insTile;
     const uint32_t* blockCursor = c.blockCursor(b.parity);
-    if (gridDim.x <= 1024) {
-        uint32_t total = 0;
+    const bool listed = gridDim.x <= 1024;
+    uint32_t segTotal = 0;
+    if (listed) {
         for (uint32_t b0 = 0; b0 < gridDim.x; b0 += blockDim.x) {
             uint32_t blk = b0 + threadIdx.x;
             uint32_t v = blk < gridDim.x ? blockCursor[blk] : 0u;
             uint32_t chunkTotal = 0;
             uint32_t off = blockExclusiveScan(v, chunkTotal);
-            if (blk < gridDim.x) sh_segStart[blk] = total + off;
-            total += chunkTotal;
+            if (blk < gridDim.x) sh_segStart[blk] = segTotal + off;
+            segTotal += chunkTotal;
         }
-        if (threadIdx.x == 0) sh_segStart[gridDim.x] = total;
-        __syncthreads();
-        for (uint32_t v = tid; v < total; v += stride) {
+        if (threadIdx.x == 0) sh_segStart[gridDim.x] = segTotal;
+    }
+    const uint32_t endPoints = b.size, endSpilled = endPoints + numSpilled, endSeg = endSpilled + segTotal, total = endSeg + numSharedVoxels;
+
+    auto insertOne = [&](uint32_t i) {
+        if (i < endSpilled) {
+            const bool sp = i >= endPoints;
+            const uint32_t item = sp ? (uint32_t)scratch::MAX_BATCH + (i - endPoints) : i;
+            uint4 pt = sp ? *reinterpret_cast<const uint4*>(c.spilled() + (i - endPoints)) : ldPoint(b.points + i);
+            Point* d = pointSlotAddress(c, leafRow[leafOf[item] & 0xffffffu], slotOf[item]);
+            if (d) stPoint(d, pt);
+        } else if (i < endSeg) {
+            const uint32_t v = i - endSpilled;
             uint32_t lo = 0, hi = gridDim.x;                     // last segment with start <= v
             while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (sh_segStart[mid] <= v) lo = mid; else hi = mid; }
             insertVoxel(c, b.parity, (uint64_t)lo * c.segCap + (v - sh_segStart[lo]));
+        } else {
+            insertVoxel(c, b.parity, scratch::VOXEL_CAP - scratch::VOXEL_SHARED + (i - endSeg));
         }
-    } else {
+    };
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh_insTile = atomicAdd(&b.bc->insertCursor, 1u);
+        __syncthreads();
+        const uint64_t base64 = (uint64_t)sh_insTile * INSERT_TILE;
+        if (base64 >= total) break;
+        const uint32_t base = (uint32_t)base64;
+        if (base + INSERT_TILE <= endPoints) {
+            // a tile of batch points: four independent items per thread, so that the three dependent lookups
+            // (item -> leaf row -> chunk) of one overlap with those of the others
+            constexpr int U = INSERT_TILE / 256;
+            uint4 p[U]; uint32_t n[U], sl[U], r[U]; Point* dst[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = base + threadIdx.x + 256u * u;
+                p[u] = ldPoint(b.points + i);
+                n[u] = leafOf[i] & 0xffffffu;
+                sl[u] = slotOf[i];
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) r[u] = leafRow[n[u]];
+#pragma unroll
+            for (int u = 0; u < U; u++) dst[u] = pointSlotAddress(c, r[u], sl[u]);
+#pragma unroll
+            for (int u = 0; u < U; u++) if (dst[u]) stPoint(dst[u], p[u]);
+        } else {
+#pragma unroll 1
+            for (uint32_t u = 0; u < INSERT_TILE / 256; u++) {
+                const uint32_t i = base + threadIdx.x + 256u * u;
+                if (i < total) insertOne(i);
+            }
+        }
+    }
+    if (!listed) {       // grids beyond 1024 blocks: every block inserts the voxels of its own segment
         const uint32_t own = blockCursor[blockIdx.x];
         for (uint32_t e = threadIdx.x; e < own; e += blockDim.x) insertVoxel(c, b.parity, (uint64_t)blockIdx.x * c.segCap + e);
     }
-    for (uint32_t e = tid; e < numSharedVoxels; e += stride) insertVoxel(c, b.parity, scratch::VOXEL_CAP - scratch::VOXEL_SHARED + e);
     __syncthreads();
 }
 
 __device__ __forceinline__ void clearBatchCounters(BatchCounters* b) {
-    b->numSpillTotal = 0; b->numSpilled = 0; b->numBacklog = 0; b->numDirtyLeaves = 0; b->numDirtyVox = 0; b->dirCursor = 0; b->voxelsCreated = 0;
+    b->numSpillTotal = 0; b->numSpilled = 0; b->numBacklog = 0; b->numDirtyLeaves = 0; b->numDirtyVox = 0; b->dirCursor = 0; b->voxelsCreated = 0; b->insertCursor = 0;
 }
 
 // Upper bound of what the allocation of a counted batch can still take from the heap (for the capacity guard,
@@ -1107,7 +1240,13 @@ __device__ __forceinline__ void finishBatchBookkeeping(const Ctx& c, const Batch
 // ------------------------------------------------------------------------------------------
 // kernel_construct — voxels.cu:804-1010
 // ------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(256, 4)
+#ifndef SIMLOD_TIMERS
+#define SIMLOD_TIMERS 0
+#endif
+#ifndef SIMLOD_BLOCKS_PER_SM
+#define SIMLOD_BLOCKS_PER_SM 4         // tuning knob (tools/exp_variants.py)
+#endif
+extern "C" __global__ void __launch_bounds__(256, SIMLOD_BLOCKS_PER_SM)
 kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8_t* buffer_persistent, Node* nodes,
                  Stats* stats, uint64_t* frameStartTimestamp, CudaPrint* cudaprint,
                  uint32_t* numBatchesUploaded_volatile, uint32_t* batchSizes) {
@@ -1142,6 +1281,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             ctl->errorFlags = 0;
             ctl->spilledTotal = 0; ctl->voxelsTotal = 0; ctl->voxelsByPass[0] = 0; ctl->voxelsByPass[1] = 0;
             for (int i = 0; i < 8; i++) ctl->phaseNanos[i] = 0;
+            for (int i = 0; i < 16; i++) ctl->subNanos[i] = 0;
             ctl->rowBump = 0; ctl->rowFreeCount = 0;
             c.firstChild()[0] = 0;
             c.parentOf()[0] = 0;
@@ -1150,12 +1290,23 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             c.gridPtr()[0] = (uint64_t)nodes[0].grid;
         }
     }
-    if (threadIdx.x == 0) { sh_allocTarget = 0; sh_allocSeen = 0; sh_rescan = 0; }
-    if (threadIdx.x < BLOOM_WORDS) sh_runBloom[threadIdx.x] = 0xffffffffu;
+    if (threadIdx.x == 0) { sh_allocTarget = 0; sh_allocSeen = 0; sh_numAffected = 0; }
     tileBarInit();
     grid.sync();
     uint64_t tPhase = tStart;
-#define PHASE_DONE(k) do { if (first) { uint64_t _t = globaltimer(); ctl->phaseNanos[k] += _t - tPhase; tPhase = _t; } } while (0)
+    // developer timers (tools/dev_check.py): -DSIMLOD_TIMERS=1 per phase, =2 also block 0's timeline inside the phases.
+    // Off in the shipped build: every warp pays for the `first` test at each site.
+#if SIMLOD_TIMERS >= 1
+#define PHASE_DONE(k) do { if (first) { uint64_t _t = globaltimer(); ctl->phaseNanos[k] += _t - tPhase; tPhase = _t; tSub = _t; } } while (0)
+    uint64_t tSub = tStart;
+#else
+#define PHASE_DONE(k) do { } while (0)
+#endif
+#if SIMLOD_TIMERS >= 2
+#define SUB_DONE(k) do { if (first) { uint64_t _t = globaltimer(); ctl->subNanos[k] += _t - tSub; tSub = _t; } } while (0)
+#else
+#define SUB_DONE(k) do { } while (0)
+#endif
     PHASE_DONE(7);
 
     const uint32_t numBatchesUploaded = ldv(&ctl->numBatchesUploaded);
@@ -1186,6 +1337,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         const bool deferSampling = ldv(&c.firstChild()[0]) == 0;    // root still a leaf: see DESIGN.md §4 (root grid is wiped when it splits)
 
         // ---- fused phase: allocate b-1 | count (+ sample) b | insert b-1 ------------------------------
+        SUB_DONE(11);
         if (havePending) {
             allocEpochs++;
             if (threadIdx.x == 0) { sh_allocTarget = allocEpochs * gridDim.x; sh_allocSeen = 0; }
@@ -1194,12 +1346,16 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             __syncthreads();
             if (threadIdx.x == 0) { __threadfence(); atomicAdd(&ctl->allocDone, 1u); }
         }
+        SUB_DONE(0);
         if (first) clearBatchCounters(&ctl->batch[(batchIndex + 1) % 3u]);      // idle set: last used by batch b-2, next by b+1
-        if (deferSampling) passItems<false, true, true, false>(c, b, 0, 0, 0);
-        else               passItems<true, true, true, false>(c, b, 0, 0, 0);
+        if (deferSampling) passItems<false, true, true, false>(c, b, 0, 0, 0, 0);
+        else               passItems<true, true, true, false>(c, b, 0, 0, 0, 0);
+        SUB_DONE(1);
         waitAllocBlock(c);
-        if (deferSampling) passFlush<false, true, true>(c, b, 0);
-        else               passFlush<true, true, true>(c, b, 0);
+        SUB_DONE(2);
+        if (deferSampling) passFlush<false, true, true>(c, b, 0, 0);
+        else               passFlush<true, true, true>(c, b, 0, 0);
+        SUB_DONE(3);
         if (havePending) {
             if (first) finishBatchBookkeeping(c, pending, tStart);          // all allocations of b-1 are complete (waitAllocBlock)
             insertAll(c, pending, pendingSpilled, min(ldv(&pending.bc->numBacklog), (uint32_t)scratch::VOXEL_SHARED));
@@ -1207,31 +1363,44 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             havePending = false;
         }
         if (first) ctl->elapsedNanos = globaltimer() - tStart;
+        SUB_DONE(4);
         grid.sync();
+        SUB_DONE(5);
         PHASE_DONE(0);
 
         // ---- split rounds (voxels.cu:385-415 expand): 2 barriers each ------------------------
-        uint32_t spillBegin = 0;
+        uint32_t spillBegin = 0, spilledBefore = 0;
         for (int round = 0; round < 24; round++) {
             const uint32_t spillEnd = min(ldv(&b.bc->numSpillTotal), (uint32_t)scratch::SPILLNODE_CAP);
             if (spillEnd == spillBegin) break;
+            markAffectedRun(c, b, spillBegin, spillEnd);
             splitRound(c, b, spillBegin, spillEnd);
+            SUB_DONE(6);
             grid.sync();
+            SUB_DONE(7);
             PHASE_DONE(1);
+#if SIMLOD_TIMERS >= 1
             if (first) ctl->phaseNanos[6] += 1;
+#endif
             const uint32_t numSpilled = min(ldv(&b.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
-            if (deferSampling) { passItems<false, true, false, false>(c, b, numSpilled, spillBegin, spillEnd); passFlush<false, true, false>(c, b, numSpilled); }
-            else               { passItems<true, true, false, false>(c, b, numSpilled, spillBegin, spillEnd);  passFlush<true, true, false>(c, b, numSpilled); }
+            if (deferSampling) passItems<false, true, false, false>(c, b, numSpilled, spilledBefore, spillBegin, spillEnd);
+            else               passItems<true, true, false, false>(c, b, numSpilled, spilledBefore, spillBegin, spillEnd);
+            SUB_DONE(8);
+            if (deferSampling) passFlush<false, true, false>(c, b, numSpilled, spilledBefore);
+            else               passFlush<true, true, false>(c, b, numSpilled, spilledBefore);
+            SUB_DONE(9);
             grid.sync();
+            SUB_DONE(10);
             PHASE_DONE(2);
             spillBegin = spillEnd;
+            spilledBefore = numSpilled;
         }
         const uint32_t numSpilled = min(ldv(&b.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
         if (deferSampling) {
             // the root was a leaf when the batch started: sample along the final paths, as the reference does after
             // expand() (voxels.cu:738-742). The root's grid may just have been cleared in place: probe it through L2.
-            passItems<true, false, true, true>(c, b, numSpilled, 0, 0);
-            passFlush<true, false, true>(c, b, numSpilled);
+            passItems<true, false, true, true>(c, b, numSpilled, 0, 0, 0);
+            passFlush<true, false, true>(c, b, numSpilled, 0);
             grid.sync();
             PHASE_DONE(3);
         }

@@ -144,6 +144,17 @@ def shell(n_total, first=0, count=None, seed=1234, tiles_lat=64, tiles_lon=128):
     return pts, (0.0, 0.0, 0.0), (SHELL_CUBE, SHELL_CUBE, SHELL_CUBE)
 
 
+def terrain_batches(total_batches, mine, threads=None, seed=7, batch_size=1_000_000):
+    """Host copies of the batches `mine` of a (total_batches x batch_size)-point terrain scan (numpy, several threads)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    n_total = total_batches * batch_size
+    threads = threads or min(16, os.cpu_count() or 4)
+    with ThreadPoolExecutor(threads) as ex:
+        out = list(ex.map(lambda b: terrain(n_total, b * batch_size, batch_size, seed)[0], mine))
+    return out, (0.0, 0.0, 0.0), TERRAIN_EXTENT
+
+
 def batches(points, batch_size=1_000_000):
     for s in range(0, points.shape[0], batch_size):
         yield points[s:s + batch_size]

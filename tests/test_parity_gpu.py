@@ -263,9 +263,8 @@ def test_render_is_idempotent_and_does_not_modify_the_octree(sim):
 # ---- BASELINE.json full size (configs[1]: 36 M points streamed in 1 M-point batches): size-independent properties ----
 
 def test_full_size_36m_stream_invariants(sim):
-    import bench
     K = 36
-    batches, mn, mx = bench.generate_batches(K, list(range(K)))
+    batches, mn, mx = data.terrain_batches(K, list(range(K)))
     sim.set_box(mn, mx)
     sim.reset()
     # two ragged batches in the middle of the stream, the rest full

@@ -21,7 +21,6 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench  # noqa: E402
 import oracle  # noqa: E402  (checker only: canonical forms of the two device octrees)
 from simlod_b200 import SimLOD, data  # noqa: E402
 from simlod_b200 import dist as sdist  # noqa: E402
@@ -35,10 +34,10 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-B = bench.BATCH
+B = 1_000_000
 total_batches = K * world
 mine = sdist.shard_batches(total_batches, rank, world)
-batches, mn, mx = bench.generate_batches(total_batches, mine)
+batches, mn, mx = data.terrain_batches(total_batches, mine)
 sim = SimLOD(640, 360, device=local, persistent_bytes=max(6 << 30, K * world * (260 << 20)))
 sim.set_box(mn, mx)
 src = sim.device_alloc(K * B * 16)

@@ -10,14 +10,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench  # noqa: E402
 import oracle  # noqa: E402
-from simlod_b200 import SimLOD, camera  # noqa: E402
+from simlod_b200 import SimLOD, camera, data# noqa: E402
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 36
 out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "reference_gpu.json")
-batches, mn, mx = bench.generate_batches(K, list(range(K)))
-npts = K * bench.BATCH
+batches, mn, mx = data.terrain_batches(K, list(range(K)))
+npts = K * 1_000_000
 res = {"workload": "terrain_synth_%dM, %d x 1M batches" % (K, K)}
 for impl in ("reference", "ours"):
     sim = SimLOD(1920, 1080, momentary_bytes=oracle.REF_MOMENTARY_BYTES, persistent_bytes=max(8 << 30, K * (220 << 20)),
@@ -28,7 +27,7 @@ for impl in ("reference", "ours"):
     sim.set_box(mn, mx)
     dptr = sim.device_alloc(npts * 16)
     sim.memcpy_htod(dptr, np.concatenate(batches).view(np.uint8))
-    sim.reset(); sim.insert_device(dptr, 3 * bench.BATCH); sim.reset(); sim.flush_l2()
+    sim.reset(); sim.insert_device(dptr, 3 * 1_000_000); sim.reset(); sim.flush_l2()
     kms, tms = sim.insert_device(dptr, npts)
     st = sim.stats()
     assert st.numPoints == npts, (st.numPoints, st.dbg)

@@ -19,7 +19,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench  # noqa: E402
 import oracle  # noqa: E402
 from simlod_b200 import SimLOD, camera, data  # noqa: E402
 
@@ -39,8 +38,8 @@ def det_stats(s):
 
 # ------------------------------------------------------------------ config 5
 if KT > 0:
-    batches, mn, mx = bench.generate_batches(KT, list(range(KT)))
-    n = KT * bench.BATCH
+    batches, mn, mx = data.terrain_batches(KT, list(range(KT)))
+    n = KT * 1_000_000
     cams = [("morro_bird", camera.orbit_camera(width=W, height=H, **camera.MORRO_BIRD)),
             ("morro_close", camera.orbit_camera(width=W, height=H, **camera.MORRO_CLOSE))]
     cams += [("autofocus+%d*pi/2" % k, camera.autofocus(mx, W, H, yaw_offset=k * np.pi / 2)) for k in range(4)]
@@ -50,8 +49,8 @@ if KT > 0:
         sim.set_box(mn, mx)
         dptr = sim.device_alloc(n * 16)
         for b, pts in enumerate(batches):
-            sim.memcpy_htod(dptr + b * bench.BATCH * 16, pts.view(np.uint8))
-        sim.reset(); sim.insert_device(dptr, 3 * bench.BATCH); sim.reset(); sim.flush_l2()
+            sim.memcpy_htod(dptr + b * 1_000_000 * 16, pts.view(np.uint8))
+        sim.reset(); sim.insert_device(dptr, 3 * 1_000_000); sim.reset(); sim.flush_l2()
         kms, tms = sim.insert_device(dptr, n)
         st = sim.stats()
         assert st.numPoints == n and st.dbg == 0, (st.numPoints, st.dbg)
@@ -115,9 +114,9 @@ if KT > 0:
 
 # ------------------------------------------------------------------ config 4 (one GPU's share)
 if KS > 0:
-    n = KS * bench.BATCH
+    n = KS * 1_000_000
     with ThreadPoolExecutor(min(16, os.cpu_count() or 4)) as ex:
-        parts = list(ex.map(lambda b: data.shell(n, b * bench.BATCH, bench.BATCH)[0], range(KS)))
+        parts = list(ex.map(lambda b: data.shell(n, b * 1_000_000, 1_000_000)[0], range(KS)))
     mn, mx = (0.0, 0.0, 0.0), (data.SHELL_CUBE,) * 3
     r4 = {"workload": "sphere shell R=1800+-0.25 in 4096^3, %d x 1M-point batches in lat/lon tile order" % KS}
     for impl in ("reference", "ours"):
@@ -129,8 +128,8 @@ if KS > 0:
         sim.set_box(mn, mx)
         dptr = sim.device_alloc(n * 16)
         for b, pts in enumerate(parts):
-            sim.memcpy_htod(dptr + b * bench.BATCH * 16, pts.view(np.uint8))
-        sim.reset(); sim.insert_device(dptr, 3 * bench.BATCH); sim.reset(); sim.flush_l2()
+            sim.memcpy_htod(dptr + b * 1_000_000 * 16, pts.view(np.uint8))
+        sim.reset(); sim.insert_device(dptr, 3 * 1_000_000); sim.reset(); sim.flush_l2()
         kms, tms = sim.insert_device(dptr, n)
         st = sim.stats()
         r4[impl] = {"kernel_ms": kms, "total_ms": tms, "mpoints_per_s_kernel": n / kms / 1e3, "mpoints_per_s_total": n / tms / 1e3,

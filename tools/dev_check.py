@@ -104,26 +104,45 @@ for name, batches, box, rcp in cases:
     print("     (%.1f s)" % (time.time() - t0), flush=True)
 
 # ---- timing on device-generated terrain streams ---------------------------------------------------
+# the shipped kernel carries no timers; a -DSIMLOD_TIMERS=2 build of the same source gives the per-phase picture
+import subprocess  # noqa: E402
+timed = os.path.join(ROOT, "tools", "exp", "dev_timers2.cubin")
+os.makedirs(os.path.dirname(timed), exist_ok=True)
+r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-cubin", "-DSIMLOD_TIMERS=2", "-o", timed,
+                    os.path.join(ROOT, "simlod_b200", "csrc", "construct.cu")], capture_output=True, text=True)
+if r.returncode != 0:
+    print("timers build failed:", r.stderr[-300:]); timed = None
+SUBS = ["f.alloc", "f.count", "f.wait", "f.flush", "f.insert", "f.barrier", "s.work", "s.barrier", "r.items", "r.flush", "r.barrier", "f.top", "-", "r.loop(warp0)"]
 for K in sizes:
     n = K * BATCH
     dptr = sim.device_alloc(n * 16)
     sim.generate(sim.GEN_TERRAIN, dptr, n, 0, n, 7)
     sim.set_box((0, 0, 0), data.TERRAIN_EXTENT)
-    best = None
-    for rep in range(3):
-        sim.reset(); sim.flush_l2()
-        kms, tms = sim.insert_device(dptr, n)
-        st = sim.stats()
-        assert st.numPoints == n and st.dbg == 0, (st.numPoints, st.dbg)
-        ph = sim.memcpy_dtoh(sim.buffers().momentary + 96, 64).view(np.uint64).astype(np.float64)
-        if best is None or kms < best[0]:
-            best = (kms, tms, ph)
-    kms, tms, ph = best
-    rounds = ph[6]
-    per = {k: round(float(v) / 1e3 / K, 1) for k, v in zip(PHASES, ph) if k != "rounds(count)"}
-    vb = sim.memcpy_dtoh(sim.buffers().momentary + 64, 32).view(np.uint64)
-    print("terrain %dM: kernel %.3f ms = %.0f Mpts/s, total %.3f ms = %.0f Mpts/s | us/batch %s | rounds/batch %.2f | voxels fresh/rewalk %d/%d spilled %d | nodes %d"
-          % (K, kms, n / kms / 1e3, tms, n / tms / 1e3, per, rounds / K, int(vb[0]), int(vb[1]), int(vb[2]), st.numNodes), flush=True)
+    for module in (None, timed):
+        if module is None and False:
+            continue
+        sim.use_module(0, module)
+        best = None
+        for rep in range(3):
+            sim.reset(); sim.flush_l2()
+            kms, tms = sim.insert_device(dptr, n)
+            st = sim.stats()
+            assert st.numPoints == n and st.dbg == 0, (st.numPoints, st.dbg)
+            ph = sim.memcpy_dtoh(sim.buffers().momentary + 96, 64).view(np.uint64).astype(np.float64)
+            sub = sim.memcpy_dtoh(sim.buffers().momentary + 272, 128).view(np.uint64).astype(np.float64)
+            if best is None or kms < best[0]:
+                best = (kms, tms, ph, sub)
+        kms, tms, ph, sub = best
+        vb = sim.memcpy_dtoh(sim.buffers().momentary + 64, 32).view(np.uint64)
+        print("terrain %dM [%s]: kernel %.3f ms = %.0f Mpts/s, total %.3f ms = %.0f Mpts/s | voxels fresh/rewalk %d/%d spilled %d | nodes %d"
+              % (K, "shipped" if module is None else "timers=2 build", kms, n / kms / 1e3, tms, n / tms / 1e3, int(vb[0]), int(vb[1]), int(vb[2]), st.numNodes), flush=True)
+        if ph.sum() > 0:
+            print("   us/batch %s | rounds/batch %.2f" % ({k: round(float(v) / 1e3 / K, 1) for k, v in zip(PHASES, ph) if k != "rounds(count)"}, ph[6] / K), flush=True)
+            print("   block 0 timeline, us/batch:", {k: round(float(v) / 1e3 / K, 1) for k, v in zip(SUBS, sub)}, flush=True)
+            print("   re-walk item space per batch: %.0f items, of which %.0f in affected runs" % (sub[14] / K, sub[15] / K), flush=True)
+        if timed is None:
+            break
+    sim.use_module(0, None)
     if K == sizes[0]:
         # the device generator against numpy on a slice in the middle of the stream
         f0 = (n // 2) - 50_000

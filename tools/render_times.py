@@ -3,13 +3,12 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench
-from simlod_b200 import SimLOD, camera
+from simlod_b200 import SimLOD, camera, data
 K = 36
-batches, mn, mx = bench.generate_batches(K, list(range(K)))
+batches, mn, mx = data.terrain_batches(K, list(range(K)))
 sim = SimLOD(1920, 1080, persistent_bytes=8 << 30)
 sim.set_box(mn, mx)
-n = K * bench.BATCH
+n = K * 1_000_000
 dptr = sim.device_alloc(n * 16)
 sim.memcpy_htod(dptr, np.concatenate(batches).view(np.uint8))
 sim.reset(); sim.insert_device(dptr, n)
