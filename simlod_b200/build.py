@@ -143,7 +143,25 @@ def build_oracle(force=False):
     return lib
 
 
+def build_test_harness(force=False):
+    """tests/native/dropin_harness: the reference host's launch sequence over the shipped cubins (driver API only, linked
+    against the toolkit's stub libcuda so that it builds on a machine without a driver). Test infrastructure."""
+    src = os.path.join(ROOT, "tests", "native", "dropin_harness.cpp")
+    out = os.path.join(ROOT, "tests", "native", "dropin_harness")
+    if not os.path.exists(src):
+        return None
+    digest = _digest([src, os.path.join(ROOT, "include", "simlod_abi.h")], "-O1")
+    stamp = out + ".stamp"
+    if force or not _stamp_matches(stamp, digest, [out]):
+        _run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(CUDA, "include"), src, "-o", out,
+              "-L" + os.path.join(CUDA, "lib64", "stubs"), "-lcuda"])
+        with open(stamp, "w") as f:
+            f.write(digest + "\n")
+    return out
+
+
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose=True))
     if os.path.exists(os.path.join(ROOT, "oracle", "oracle.cpp")):
         print(build_oracle(force="--force" in sys.argv))
+    print(build_test_harness(force="--force" in sys.argv))

@@ -401,6 +401,8 @@ static int createResources(SimlodContext* ctx, const SimlodConfig* config) {
 int simlod_create(const SimlodConfig* config, SimlodContext** out) {
     if (!config || !out) return fail(SIMLOD_ERR_INVALID, "null argument");
     if (config->width == 0 || config->height == 0) return fail(SIMLOD_ERR_INVALID, "render target must be non-empty");
+    if (config->renderbuffer_bytes && config->renderbuffer_bytes < 200000000ull)   // kernel_render lays its scratch out for the reference's 200 MB buffer (main.cpp:556)
+        return fail(SIMLOD_ERR_INVALID, "renderbuffer_bytes %llu is below the 200 000 000 bytes the kernels are built for", (unsigned long long)config->renderbuffer_bytes);
     if (config->nodes_bytes && config->nodes_bytes < 40000000ull)     // kernel_construct's node capacity is the reference's 40 MB array (main.cpp:552-555)
         return fail(SIMLOD_ERR_INVALID, "nodes_bytes %llu is below the 40 000 000 bytes the kernels are built for", (unsigned long long)config->nodes_bytes);
     { int rc0 = loadDriver(); if (rc0) return rc0; }

@@ -31,35 +31,51 @@ struct CudaPrint;
 
 // render-buffer layout. The framebuffer and the HQS targets sit where the reference's bump
 // allocator puts them (render.cu:1108-1123,172,224-231), so both kernels can be read back with
-// the same offsets; the area the reference uses for 100 000 Node copies holds our queues.
+// the same offsets; the area the reference uses for 100 000 Node copies holds our work queue, and the
+// unused tail of the 200 000 000-byte buffer (main.cpp:556) a cache of the nodes' chunk lists.
 namespace rbuf {
 constexpr uint64_t OFF_CTL       = 0;
-constexpr uint64_t OFF_VISLIST   = 4096;                           // u32 node indices of the LOD cut
-constexpr uint64_t VIS_CAP       = 263168;
-constexpr uint64_t ITEM_CAP      = 1048576;                        // chunk items per frame = 1 G samples (the reference: 100 000 nodes)
-constexpr uint64_t OFF_ITEMS     = OFF_VISLIST + VIS_CAP * 4;      // u64 per item, see packItem()
+constexpr uint64_t ITEM_CAP      = 2097152;                        // chunk items per frame = 2 G samples (the reference: 100 000 nodes)
+constexpr uint64_t OFF_ITEMS     = 4096;                           // u64 per item, see packItem()
 constexpr uint64_t OFF_FB        = 31200144;                       // 15 200 000 + 7*16 + 32 + 16 000 000
+constexpr uint64_t TOTAL_BYTES   = 200000000;                      // what the host allocates (main.cpp:556)
+constexpr uint64_t NODE_TAB      = 263168;                         // >= floor(40 000 000 / 152) nodes
 static_assert(OFF_ITEMS + ITEM_CAP * 8 <= OFF_FB, "render scratch overlaps the framebuffer");
 }
 
 // One work item = one chunk of <= 1000 samples, packed into a single 64-bit word:
-//   [63:20] chunk address >> 4 (chunks are 16-byte aligned)   [19:10] sample count (1..1000)   [9:5] node level
+//   [63:26] (chunk address - heap base) >> 4   [25:16] sample count (1..1000)   [15:11] node level   [10:4] node colour id   [0] valid
 // ITEM_EMPTY = nothing to draw (list shorter than the counters say).
 typedef uint64_t WorkItem;
 constexpr WorkItem ITEM_EMPTY = ~0ull;
-__device__ __forceinline__ WorkItem packItem(const void* chunk, uint32_t count, uint32_t level) {
-    return (((uint64_t)(uintptr_t)chunk >> 4) << 20) | ((uint64_t)count << 10) | ((uint64_t)(level & 31u) << 5) | 1ull;
+__device__ __forceinline__ WorkItem packItem(const uint8_t* heapBase, const void* chunk, uint32_t count, uint32_t level, uint32_t colorId) {
+    return ((uint64_t)((const uint8_t*)chunk - heapBase) >> 4 << 26) | ((uint64_t)count << 16) | ((uint64_t)(level & 31u) << 11) | ((uint64_t)(colorId & 127u) << 4) | 1ull;
 }
-__device__ __forceinline__ const uint4* itemChunk(WorkItem w) { return reinterpret_cast<const uint4*>((uintptr_t)((w >> 20) << 4)); }
-__device__ __forceinline__ uint32_t itemCount(WorkItem w) { return (uint32_t)(w >> 10) & 1023u; }
-__device__ __forceinline__ uint32_t itemLevel(WorkItem w) { return (uint32_t)(w >> 5) & 31u; }
+__device__ __forceinline__ const uint4* itemChunk(const uint8_t* heapBase, WorkItem w) { return reinterpret_cast<const uint4*>(heapBase + ((w >> 26) << 4)); }
+__device__ __forceinline__ uint32_t itemCount(WorkItem w) { return (uint32_t)(w >> 16) & 1023u; }
+__device__ __forceinline__ uint32_t itemLevel(WorkItem w) { return (uint32_t)(w >> 11) & 31u; }
+__device__ __forceinline__ uint32_t itemColorId(WorkItem w) { return (uint32_t)(w >> 4) & 127u; }
 
 struct RCtl {
     uint32_t numItems;
     uint32_t head[3];            // queue heads: single pass / HQS depth pass / HQS colour pass
     uint32_t numVisibleNodes, numVisiblePoints, numVisibleVoxels, numVisibleInner, numVisibleLeaves;
     uint32_t overflow;
+    uint32_t cacheHits, cacheWalks;      // lists served from the chunk-list cache / walked (developer counters)
 };
+
+// ---- chunk-list cache ---------------------------------------------------------------------------------------
+// Chunk lists are singly linked, so the k-th chunk of a node is k dependent loads away; the reference makes every
+// thread of a block walk the list (render.cu:116-121). Frames follow each other with the same nodes in view, so the
+// chunk pointers of a drawn node are kept, per node and list, in the tail of the render buffer. A cached array is only
+// a HINT: it is used after it has been verified against the octree — entry 0 is the list head and every chunk's `next`
+// is the following entry — which takes independent loads (32 per warp step) instead of a dependent chain, and proves
+// the array equals the list whatever happened in between (growth, a reset, another render kernel scribbling over
+// the buffer). Pointers are range-checked against the heap before they are followed. A list that fails, or has grown,
+// is walked (from the verified prefix on) and cached again.
+struct ListEntry { uint32_t off, n, cap, pad; };           // pool[off .. off + n) = the first n chunks of the list; cap reserved
+struct CacheHeader { uint32_t magic, cursor, poolCap, pad; };
+constexpr uint32_t CACHE_MAGIC = 0x51D0CAC3u;
 
 __constant__ uint32_t SPECTRAL[8] = {0x4f3ed5, 0x436df4, 0x61aefd, 0x8be0fe, 0x98f5e6, 0xa4ddab, 0xa5c266, 0xbd8832};
 
@@ -142,17 +158,21 @@ __device__ void computeVisibilityFlags(const Uniforms& u, Node* nodes, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------
-// visibility, pass 2: LOD cut (render.cu:906-933). Emits the indices of the nodes to draw; a
-// second step turns every drawn node into chunk-granular work items (one thread per node walks
-// its two chunk lists — all lists are walked concurrently).
+// visibility, pass 2: LOD cut (render.cu:906-933) + chunk items, one phase. A warp takes 32 nodes; every node
+// that is drawn (a visible non-large child of a large node, or a large visible leaf) is then handled by the whole
+// warp: its two chunk lists are turned into work items through the cache above.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void makeVisible(RCtl* ctl, uint32_t* visList, const Node* nodes, const Node* node) {
-    uint32_t numPoints = node->numPoints, numVoxels = node->numVoxels;
-    uint32_t v = atomicAdd(&ctl->numVisibleNodes, 1u);
-    visList[v] = (uint32_t)(node - nodes);
-    if (numPoints > 0) { atomicAdd(&ctl->numVisibleLeaves, 1u); atomicAdd(&ctl->numVisiblePoints, numPoints); }
-    else if (numVoxels > 0) { atomicAdd(&ctl->numVisibleInner, 1u); atomicAdd(&ctl->numVisibleVoxels, numVoxels); }
-}
+struct EmitCtx {
+    RCtl* ctl;
+    WorkItem* items;
+    const Node* nodes;
+    const uint8_t* heapBase;
+    uint64_t heapUsed;           // bytes of the heap in use (AllocatorGlobal::offset): chunk pointers must lie below
+    CacheHeader* cache;
+    ListEntry* entries;          // [node][2]
+    uint64_t* pool;
+    uint32_t poolCap;            // 0: cache disabled (render buffer too small for this resolution)
+};
 
 __device__ __forceinline__ bool isLeaf(const Node* node) {
     bool leaf = true;
@@ -161,54 +181,142 @@ __device__ __forceinline__ bool isLeaf(const Node* node) {
     return leaf;
 }
 
-__device__ void lodCut(RCtl* ctl, uint32_t* visList, Node* nodes, uint32_t numNodes) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < numNodes; n += stride) {
-        const Node* node = &nodes[n];
-        if (!node->isLarge) continue;
-        if (!isLeaf(node)) {
-            for (int i = 0; i < 8; i++) {
-                const Node* child = node->children[i];
-                if (child == nullptr || child->isLarge || !child->visible) continue;
-                makeVisible(ctl, visList, nodes, child);
-            }
-        } else if (node->visible) {
-            makeVisible(ctl, visList, nodes, node);
-        }
+// Node::getID() % 127 (structures.cuh:116-143, render.cu:74-76), with its arithmetic as compiled: the first nine digits
+// are shifted as 32-bit ints (wrap, then sign-extend into the 64-bit id), the rest as 64-bit values; unused name bytes
+// are 0, i.e. digit -48
+__device__ __forceinline__ uint32_t nodeColorId(const Node* node) {
+    uint64_t id = node->name[0] == 'r' ? 1ull : 0ull;
+#pragma unroll
+    for (int k = 1; k <= 9; k++) {
+        int32_t d = (int32_t)node->name[k] - 48;
+        id |= (uint64_t)(int64_t)(int32_t)((uint32_t)d << (3 * k));
     }
+    const int sh[9] = {30, 33, 36, 39, 42, 45, 48, 51, 53};
+#pragma unroll
+    for (int k = 10; k <= 18; k++) {
+        int64_t d = (int64_t)((int32_t)node->name[k] - 48);
+        id |= (uint64_t)d << sh[k - 10];
+    }
+    return (uint32_t)(id % 127ull);
 }
 
-// ---- chunk items ----------------------------------------------------------------------------------
-// Chunk lists are singly linked, so the k-th chunk of a node is k dependent loads away (the reference
-// makes every thread of a block walk the list, render.cu:116-121). Here one thread per drawn node
-// walks its two lists once — all nodes concurrently, both chains of a node interleaved — and emits one
-// packed item per chunk; the draw pass then runs at chunk granularity over the whole grid.
-// (Measured alternative, kept out: publishing items while other warps already draw them saves the
-// walk on frames with > 10 M samples but costs 20 % on small frames; see profiles/r01/render_notes.md.)
-__device__ void emitItems(RCtl* ctl, WorkItem* items, const uint32_t* visList, const Node* nodes, uint32_t numVisible) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < numVisible; v += stride) {
-        const Node* node = &nodes[visList[v]];
-        uint32_t numPoints = node->numPoints, numVoxels = node->numVoxels;
-        uint32_t nP = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-        uint32_t nV = (numVoxels + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
-        if (nP + nV == 0) continue;
-        uint32_t base = atomicAdd(&ctl->numItems, nP + nV);
-        if ((uint64_t)base + nP + nV > rbuf::ITEM_CAP) { atomicOr(&ctl->overflow, 1u); continue; }
-        uint32_t level = node->level;
-        const Chunk* cp = node->points;
-        const Chunk* cv = node->voxelChunks;
-        uint32_t leftP = numPoints, leftV = numVoxels;
-        for (uint32_t k = 0; k < max(nP, nV); k++) {
-            if (k < nP) {
-                uint32_t cnt = leftP < SIMLOD_POINTS_PER_CHUNK ? leftP : SIMLOD_POINTS_PER_CHUNK;
-                items[base + k] = cp ? packItem(cp, cnt, level) : ITEM_EMPTY;
-                leftP -= cnt; if (cp) cp = cp->next;
+__device__ __forceinline__ bool validChunkPointer(const EmitCtx& e, uint64_t p) {
+    const uint64_t base = (uint64_t)e.heapBase;
+    return p >= base + 16 && p + sizeof(Chunk) <= base + e.heapUsed && ((p - base) & 15ull) == 0;
+}
+
+// one chunk list of a drawn node -> n work items at items[0..n). Warp-cooperative (all 32 lanes).
+__device__ void emitList(const EmitCtx& e, const Chunk* head, uint32_t n, uint32_t count, uint32_t level, uint32_t colorId, ListEntry* entry, WorkItem* items) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = laneId();
+    if (n == 0) return;
+    auto samplesOf = [&](uint32_t k) { return k + 1 < n ? (uint32_t)SIMLOD_POINTS_PER_CHUNK : count - (n - 1) * SIMLOD_POINTS_PER_CHUNK; };
+
+    ListEntry le = *entry;
+    uint32_t m = 0;                                       // chunks of the list the cache claims to know
+    if (e.poolCap != 0 && le.n != 0 && le.n <= le.cap && (uint64_t)le.off + le.cap <= e.poolCap) m = min(le.n, n);
+    // ---- verify the cached prefix with independent loads, and emit it
+    uint64_t carriedNext = 0;                             // `next` of the last verified chunk
+    bool ok = true;
+    for (uint32_t k0 = 0; k0 < m && ok; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool have = k < m;
+        const uint64_t p = have ? e.pool[le.off + k] : 0ull;
+        if (!__all_sync(FULL, !have || validChunkPointer(e, p))) { ok = false; break; }
+        const uint64_t nx = have ? (uint64_t)reinterpret_cast<const Chunk*>(p)->next : 0ull;
+        uint64_t nxPrev = __shfl_up_sync(FULL, nx, 1);
+        if (lane == 0) nxPrev = carriedNext;
+        const bool good = !have || (k == 0 ? p == (uint64_t)head : nxPrev == p);
+        if (!__all_sync(FULL, good)) { ok = false; break; }
+        const uint32_t lastLane = min(31u, m - 1 - k0);
+        carriedNext = __shfl_sync(FULL, nx, lastLane);
+        if (have) items[k] = packItem(e.heapBase, reinterpret_cast<const void*>(p), samplesOf(k), level, colorId);
+    }
+    if (!ok) m = 0;
+    if (m == n) { if (lane == 0) atomicAdd(&e.ctl->cacheHits, 1u); return; }
+
+    // ---- the rest of the list (all of it when nothing was cached, or the cache was wrong): a dependent walk by one lane.
+    // The pointers go to the cache: in place while the reserved room lasts, else to a fresh, larger array.
+    if (lane == 0) atomicAdd(&e.ctl->cacheWalks, 1u);
+    uint32_t off = le.off, cap = le.cap;
+    bool caching = e.poolCap != 0;
+    if (caching && (m == 0 || n > cap)) {
+        uint32_t want = n + max(8u, n / 4u);
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(&e.cache->cursor, want);
+        at = __shfl_sync(FULL, at, 0);
+        if ((uint64_t)at + want > e.poolCap) caching = false;            // pool exhausted: drawn without caching; the pool restarts next frame
+        else {
+            for (uint32_t k = lane; k < m; k += 32) e.pool[at + k] = e.pool[off + k];       // keep the verified prefix
+            off = at; cap = want;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const Chunk* cur = m == 0 ? head : reinterpret_cast<const Chunk*>(carriedNext);
+        uint32_t k = m;
+        for (; k < n; k++) {
+            if (cur == nullptr || !validChunkPointer(e, (uint64_t)cur)) break;
+            if (caching) e.pool[off + k] = (uint64_t)cur;
+            items[k] = packItem(e.heapBase, cur, samplesOf(k), level, colorId);
+            cur = cur->next;
+        }
+        const uint32_t known = k;
+        for (; k < n; k++) items[k] = ITEM_EMPTY;
+        if (caching) *entry = ListEntry{off, known, cap, 0};
+    }
+    __syncwarp();
+}
+
+__device__ void emitNode(const EmitCtx& e, const Node* node) {
+    const uint32_t lane = laneId();
+    const uint32_t numPoints = node->numPoints, numVoxels = node->numVoxels, level = node->level;
+    const uint32_t nP = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+    const uint32_t nV = (numVoxels + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
+    uint32_t base = 0;
+    if (lane == 0) {
+        atomicAdd(&e.ctl->numVisibleNodes, 1u);                                      // render.cu:918-932 bookkeeping
+        if (numPoints > 0) { atomicAdd(&e.ctl->numVisibleLeaves, 1u); atomicAdd(&e.ctl->numVisiblePoints, numPoints); }
+        else if (numVoxels > 0) { atomicAdd(&e.ctl->numVisibleInner, 1u); atomicAdd(&e.ctl->numVisibleVoxels, numVoxels); }
+        if (nP + nV) base = atomicAdd(&e.ctl->numItems, nP + nV);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (nP + nV == 0) return;
+    if ((uint64_t)base + nP + nV > rbuf::ITEM_CAP) { if (lane == 0) atomicOr(&e.ctl->overflow, 1u); return; }
+    const uint32_t colorId = nodeColorId(node);
+    const uint32_t index = (uint32_t)(node - e.nodes);
+    emitList(e, node->points, nP, numPoints, level, colorId, &e.entries[2 * index + 0], e.items + base);
+    emitList(e, node->voxelChunks, nV, numVoxels, level, colorId, &e.entries[2 * index + 1], e.items + base + nP);
+}
+
+__device__ void lodCutAndEmit(const EmitCtx& e, uint32_t numNodes) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = laneId();
+    const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;          // neighbouring nodes go to different SMs
+    for (uint32_t first = warp * 32u; first < numNodes; first += numWarps * 32u) {
+        const uint32_t n = first + lane;
+        const Node* node = &e.nodes[n];
+        const bool large = n < numNodes && node->isLarge;
+        const bool leaf = large && isLeaf(node);
+        // candidates of this lane: its children (render.cu:918-927), or the node itself when it is a large visible leaf
+#pragma unroll 1
+        for (int i = 0; i < 9; i++) {
+            const Node* cand = nullptr;
+            if (large) {
+                if (i < 8) {
+                    if (!leaf) {
+                        const Node* child = node->children[i];
+                        if (child != nullptr && !child->isLarge && child->visible) cand = child;
+                    }
+                } else if (leaf && node->visible) cand = node;
             }
-            if (k < nV) {
-                uint32_t cnt = leftV < SIMLOD_POINTS_PER_CHUNK ? leftV : SIMLOD_POINTS_PER_CHUNK;
-                items[base + nP + k] = cv ? packItem(cv, cnt, level) : ITEM_EMPTY;
-                leftV -= cnt; if (cv) cv = cv->next;
+            uint32_t mask = __ballot_sync(FULL, cand != nullptr);
+            while (mask) {
+                const uint32_t src = __ffs(mask) - 1u;
+                mask &= mask - 1u;
+                const Node* drawn = reinterpret_cast<const Node*>(__shfl_sync(FULL, (uint64_t)cand, src));
+                emitNode(e, drawn);
             }
         }
     }
@@ -216,7 +324,7 @@ __device__ void emitItems(RCtl* ctl, WorkItem* items, const uint32_t* visList, c
 
 // one pass over the frame's items: persistent warps pop chunk items with a single atomicAdd each
 template <typename F>
-__device__ __forceinline__ void forEachSample(const WorkItem* items, uint32_t numItems, uint32_t* head, F&& f) {
+__device__ __forceinline__ void forEachSample(const uint8_t* heapBase, const WorkItem* items, uint32_t numItems, uint32_t* head, F&& f) {
     const uint32_t lane = laneId();
     for (;;) {
         uint32_t it = 0;
@@ -225,9 +333,9 @@ __device__ __forceinline__ void forEachSample(const WorkItem* items, uint32_t nu
         if (it >= numItems) break;
         WorkItem w = items[it];
         if (w == ITEM_EMPTY || w == 0) continue;
-        const uint4* pts = itemChunk(w);
-        const uint32_t count = itemCount(w), level = itemLevel(w);
-        for (uint32_t i = lane; i < count; i += 32) f(pts[i], level);
+        const uint4* pts = itemChunk(heapBase, w);
+        const uint32_t count = itemCount(w), level = itemLevel(w), colorId = itemColorId(w);
+        for (uint32_t i = lane; i < count; i += 32) f(pts[i], level, colorId);
     }
 }
 
@@ -250,13 +358,14 @@ __device__ __forceinline__ Projected project(const Row* T, float width, float he
     return r;
 }
 
-__device__ __forceinline__ uint32_t sampleColor(const Uniforms& u, uint32_t pointColor, uint32_t level) {
-    if (u.colorByLOD && !u.colorByNode) {                                    // render.cu:49-59,76-78
+__device__ __forceinline__ uint32_t sampleColor(const Uniforms& u, uint32_t pointColor, uint32_t level, uint32_t colorId) {
+    if (u.colorByNode) return (uint32_t)((uint64_t)colorId * 123456789ull);  // (node->getID() % 127) * 123456789 (render.cu:74-76)
+    if (u.colorByLOD) {                                                      // render.cu:49-59,76-78
         int index = fpx::f2i(fpx::mul((float)(8 - (int)level), 1.8f));
         index = max(0, min(index, 7));
         return SPECTRAL[index];
     }
-    return pointColor;      // colorByNode (debug colouring by node id) is out of scope: see DESIGN.md
+    return pointColor;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -273,7 +382,6 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     uint8_t* base = reinterpret_cast<uint8_t*>(buffer);
     RCtl* ctl = reinterpret_cast<RCtl*>(base + rbuf::OFF_CTL);
     WorkItem* items = reinterpret_cast<WorkItem*>(base + rbuf::OFF_ITEMS);
-    uint32_t* visList = reinterpret_cast<uint32_t*>(base + rbuf::OFF_VISLIST);
     uint64_t* framebuffer = reinterpret_cast<uint64_t*>(base + rbuf::OFF_FB);
 
     const int width = fpx::f2i(uniforms.width), height = fpx::f2i(uniforms.height);
@@ -284,12 +392,36 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     uint32_t* fb_color = fb_depth + (((uint64_t)numPixels * 4 + 15) & ~15ull) / 4;
     const bool hqs = uniforms.useHighQualityShading != 0;
 
+    // chunk-list cache: whatever the 200 000 000-byte buffer has left behind the HQS targets
+    EmitCtx ec;
+    ec.ctl = ctl; ec.items = items; ec.nodes = nodes;
+    {
+        const uint64_t cacheOff = ((uint64_t)(reinterpret_cast<uint8_t*>(fb_color + 4ull * numPixels) - base) + 255ull) & ~255ull;
+        const uint64_t entriesBytes = rbuf::NODE_TAB * 2 * sizeof(ListEntry);
+        ec.cache = reinterpret_cast<CacheHeader*>(base + cacheOff);
+        ec.entries = reinterpret_cast<ListEntry*>(base + cacheOff + 256);
+        ec.pool = reinterpret_cast<uint64_t*>(base + cacheOff + 256 + entriesBytes);
+        const uint64_t poolOff = cacheOff + 256 + entriesBytes;
+        ec.poolCap = poolOff + (1ull << 20) <= rbuf::TOTAL_BYTES ? (uint32_t)min((rbuf::TOTAL_BYTES - poolOff) / 8, (uint64_t)0x7fffffffu) : 0u;
+    }
+    // the persistent heap: the root's grid is its first allocation, right behind the 16-byte header {buffer, offset}
+    // (reset.cu:40-43,69 of the reference and ours)
+    ec.heapBase = reinterpret_cast<const uint8_t*>(nodes[0].grid) - 16;
+    ec.heapUsed = nodes[0].grid ? *reinterpret_cast<const volatile uint64_t*>(ec.heapBase + 8) : 0ull;
+
     if (first) {
         *frameStartTimestamp = globaltimer();
         ctl->numItems = 0; ctl->head[0] = 0; ctl->head[1] = 0; ctl->head[2] = 0;
         ctl->numVisibleNodes = 0; ctl->numVisiblePoints = 0; ctl->numVisibleVoxels = 0;
         ctl->numVisibleInner = 0; ctl->numVisibleLeaves = 0; ctl->overflow = 0;
+        ctl->cacheHits = 0; ctl->cacheWalks = 0;
+        if (ec.poolCap != 0 && (ec.cache->magic != CACHE_MAGIC || ec.cache->poolCap != ec.poolCap || ec.cache->cursor >= ec.poolCap)) {
+            // first frame, another resolution, another kernel's scratch, or the pool ran full: start the pool over (stale
+            // entries are harmless: they fail verification)
+            ec.cache->magic = CACHE_MAGIC; ec.cache->cursor = 0; ec.cache->poolCap = ec.poolCap;
+        }
     }
+    // ---- phase 1: clear the targets | visibility flags of every node (independent) -------------------------------
     // clear: depth = +inf (0x7f800000), colour = 0x00332211 (render.cu:1126-1131)
     {
         const uint64_t clearValue = (0x7f800000ull << 32) | 0x00332211ull;
@@ -302,32 +434,29 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
             for (uint32_t i = gtid; i < numPixels; i += gstride) c4[i] = make_uint4(0, 0, 0, 0);
         }
     }
-    grid.sync();
-
     float bsx = fpx::sub(uniforms.boxMax[0], uniforms.boxMin[0]);
     float bsy = fpx::sub(uniforms.boxMax[1], uniforms.boxMin[1]);
     float bsz = fpx::sub(uniforms.boxMax[2], uniforms.boxMin[2]);
     float cubeSize = fmaxf(fmaxf(bsx, bsy), bsz);
-    const uint32_t numNodes = ldv(&stats->numNodes);
-
+    const uint32_t numNodes = min(ldv(&stats->numNodes), (uint32_t)rbuf::NODE_TAB);
     computeVisibilityFlags(uniforms, nodes, numNodes, cubeSize, uniforms.boxMin[0], uniforms.boxMin[1], uniforms.boxMin[2]);
     grid.sync();
-    lodCut(ctl, visList, nodes, numNodes);
-    grid.sync();
 
-    emitItems(ctl, items, visList, nodes, min(ldv(&ctl->numVisibleNodes), (uint32_t)rbuf::VIS_CAP));
+    // ---- phase 2: LOD cut + chunk items ------------------------------------------------------------------------------
+    if (nodes[0].grid != nullptr) lodCutAndEmit(ec, numNodes);
     grid.sync();
 
     const uint32_t numItems = min(ldv(&ctl->numItems), (uint32_t)rbuf::ITEM_CAP);
     const Row* T = uniforms.transform.rows;
     const int pointSize = uniforms.pointSize;
+    const uint8_t* heapBase = ec.heapBase;
 
     if (uniforms.showPoints && !hqs) {
         // single pass: depth|colour packed in 64 bits, atomicMin (render.cu:61-104,161-210)
-        forEachSample(items, numItems, &ctl->head[0], [&](uint4 p, uint32_t level) {
+        forEachSample(heapBase, items, numItems, &ctl->head[0], [&](uint4 p, uint32_t level, uint32_t colorId) {
             Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
             if (!pr.inside) return;
-            uint64_t encoded = ((uint64_t)__float_as_uint(pr.depth) << 32) | sampleColor(uniforms, p.w, level);
+            uint64_t encoded = ((uint64_t)__float_as_uint(pr.depth) << 32) | sampleColor(uniforms, p.w, level, colorId);
             for (int ox = 0; ox < pointSize; ox++)
             for (int oy = 0; oy < pointSize; oy++) {
                 uint32_t qx = (uint32_t)max(0, min(pr.x + ox, width));        // clamp bounds are inclusive (render.cu:91-92)
@@ -338,7 +467,7 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
         });
     } else if (uniforms.showPoints && hqs) {
         // pass 1: closest depth per pixel (render.cu:247-391)
-        forEachSample(items, numItems, &ctl->head[1], [&](uint4 p, uint32_t level) {
+        forEachSample(heapBase, items, numItems, &ctl->head[1], [&](uint4 p, uint32_t level, uint32_t colorId) {
             Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
             if (!pr.inside || !(pr.depth > 0.0f)) return;
             uint32_t udepth = __float_as_uint(pr.depth);
@@ -352,10 +481,10 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
         });
         grid.sync();
         // pass 2: accumulate colours of samples within 1 % of the closest depth (render.cu:406-602)
-        forEachSample(items, numItems, &ctl->head[2], [&](uint4 p, uint32_t level) {
+        forEachSample(heapBase, items, numItems, &ctl->head[2], [&](uint4 p, uint32_t level, uint32_t colorId) {
             Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
             if (!pr.inside || !(pr.depth > 0.0f)) return;
-            uint32_t color = sampleColor(uniforms, p.w, level);
+            uint32_t color = sampleColor(uniforms, p.w, level, colorId);
             for (int ox = 0; ox < pointSize; ox++)
             for (int oy = 0; oy < pointSize; oy++) {
                 uint32_t qx = (uint32_t)max(0, min(pr.x + ox, width));

@@ -7,7 +7,8 @@ with the reference's own NVRTC/nvJitLink recipe) through the headless launch sur
 For every case of tests/make_golden_cases.py it stores the canonical octree records, the
 deterministic Stats fields, MUFU.RCP(cube size) and the packed u64 framebuffer of one frame, all
 produced by the reference's kernel_construct / kernel / kernel_render. The CPU suite pins
-oracle/oracle.cpp to these; the GPU suite pins our kernels to them."""
+oracle/oracle.cpp (builder, canonicaliser and rasteriser) to these; the GPU suite does not read them:
+it runs the reference kernels live beside ours on the same buffers (tests/test_parity_gpu.py)."""
 import os
 import sys
 

@@ -88,3 +88,18 @@ def test_generators_are_counter_based():
     s, _, cube = data.shell(100_000)
     r = np.sqrt(((np.stack([s["x"], s["y"], s["z"]], 1).astype(np.float64) - cube[0] / 2) ** 2).sum(1))
     assert abs(r - 1800).max() < 0.3
+
+
+def test_abi_matches_the_reference_headers_field_by_field(tmp_path):
+    """tests/native/abi_pairwise.cu includes the reference's OWN HostDeviceInterface.h / structures.cuh next to
+    include/simlod_abi.h and static_asserts size and offset of every field pairwise (compile-only)."""
+    import shutil
+    import subprocess
+    ref = os.environ.get("SIMLOD_REFERENCE", "/root/reference")
+    po = os.path.join(ref, "modules", "progressive_octree")
+    if not os.path.isdir(po) or shutil.which("nvcc") is None:
+        pytest.skip("needs the reference tree and nvcc (build-time check; the GPU box has neither mounted)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["nvcc", "-std=c++17", "-c", "-o", str(tmp_path / "abi_pairwise.o"), "-I" + po, "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "tests", "native", "abi_pairwise.cu")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]

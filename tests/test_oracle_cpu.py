@@ -189,3 +189,13 @@ def test_oracle_matches_golden_digests_from_the_reference_kernels():
         s = o.stats()
         for f, v in zip(oracle.STATS_FIELDS, g["%s/stats" % name]):
             assert int(getattr(s, f)) == int(v), (name, f)
+        # the frame the reference's kernel_render drew of that octree (same Uniforms bytes): the LOD cut of the CPU
+        # rasteriser must be the reference's, and so must the depth of every pixel — except where a sample sits within
+        # an ulp of a pixel edge (1/w is MUFU.RCP on the device, a correctly rounded reciprocal here: DESIGN.md §6).
+        # Colours are not compared: which point donates a voxel's colour is a race in the reference.
+        H, W = g["%s/framebuffer" % name].shape
+        fb, rs, _flags = o.canon().render(g["%s/uniforms" % name].tobytes(), W, H)
+        want = g["%s/visible" % name]
+        assert [rs.numVisibleNodes, rs.numVisibleInner, rs.numVisibleLeaves, rs.numVisiblePoints, rs.numVisibleVoxels] == [int(v) for v in want], name
+        depth_mismatch = float(((fb >> np.uint64(32)) != (g["%s/framebuffer" % name] >> np.uint64(32))).mean())
+        assert depth_mismatch < 2e-3, (name, depth_mismatch)

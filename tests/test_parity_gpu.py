@@ -216,12 +216,88 @@ def test_framebuffer_point_size_2_and_lod_colours(sim):
     build_gpu(sim, list(data.batches(pts)), (mn, mx))
     view, proj = camera.autofocus(mx, sim.width, sim.height)
     sim.set_camera(view, proj)
-    for settings in (dict(pointSize=2), dict(pointSize=1, colorByLOD=1), dict(pointSize=3, useHighQualityShading=1)):
-        sim.set_settings(pointSize=1, colorByLOD=0, useHighQualityShading=0)
+    for settings in (dict(pointSize=2), dict(pointSize=1, colorByLOD=1), dict(pointSize=3, useHighQualityShading=1),
+                     dict(colorByNode=1), dict(colorByNode=1, colorByLOD=1), dict(colorByNode=1, useHighQualityShading=1)):     # render.cu:73-78
+        sim.set_settings(pointSize=1, colorByLOD=0, colorByNode=0, useHighQualityShading=0)
         sim.set_settings(**settings)
         r = render_both(sim)
         assert (r[False][0] == r[True][0]).all(), settings
+    sim.set_settings(pointSize=1, colorByLOD=0, colorByNode=0, useHighQualityShading=0)
+
+
+@needs_ref
+def test_framebuffer_with_frozen_visibility_transform(sim):
+    # settings.doUpdateVisibility off (main.cpp:300-306): the LOD cut keeps the bound transform of the previous view
+    # (transform_updateBound, render.cu:792-852) while the samples are splatted with the new one (transform, render.cu:62)
+    pts, mn, mx = data.terrain(2_000_000)
+    build_gpu(sim, list(data.batches(pts)), (mn, mx))
     sim.set_settings(pointSize=1, colorByLOD=0, useHighQualityShading=0)
+    r = float(np.linalg.norm(mx))
+    far = camera.orbit_camera(-2.0, -0.9, r * 6.0, (mx[0] * 0.5, mx[1] * 0.5, 0.0), sim.width, sim.height)
+    close = camera.orbit_camera(0.4, -0.3, r * 0.08, (mx[0] * 0.55, mx[1] * 0.45, mx[2] * 0.3), sim.width, sim.height)
+    for hqs in (0, 1):
+        sim.set_settings(useHighQualityShading=hqs)
+        sim.set_camera(*far)
+        sim.set_camera(*close, update_visibility=False)
+        frozen = render_both(sim)
+        assert (frozen[False][3].reshape(-1, 152)[:, [116, 119]] == frozen[True][3].reshape(-1, 152)[:, [116, 119]]).all()
+        assert (frozen[False][0] == frozen[True][0]).all(), "frozen visibility transform, hqs %d" % hqs
+        assert (frozen[False][1] == frozen[True][1]).all()
+        assert frozen[False][2].numVisibleVoxels > 0 and frozen[False][2].numVisiblePoints == 0      # the far cut, seen from close
+        sim.set_camera(*close)
+        moved = render_both(sim)
+        assert (moved[False][0] == moved[True][0]).all()
+        assert (frozen[False][0] != moved[False][0]).any()
+    sim.set_settings(useHighQualityShading=0)
+
+
+def cache_counters(sim):
+    """RCtl::cacheHits / cacheWalks of the last frame (render.cu: lists served from the chunk-list cache / walked)."""
+    c = sim.memcpy_dtoh(sim.buffers().renderbuffer + 40, 8).view(np.uint32)
+    return int(c[0]), int(c[1])
+
+
+@needs_ref
+def test_chunk_list_cache_is_only_a_hint(sim):
+    """The rasteriser keeps the chunk pointers of drawn nodes across frames and verifies them against the octree before
+    use. Frames must equal the reference kernel's whatever happens between them: growth of the lists, a reset followed by
+    a different octree at the same addresses, and another render kernel using the buffer as scratch."""
+    pts, mn, mx = data.terrain(5_000_000)
+    batches = list(data.batches(pts))
+    sim.set_settings(pointSize=1, colorByLOD=0, colorByNode=0, useHighQualityShading=0)
+    view, proj = camera.autofocus(mx, sim.width, sim.height)
+    sim.set_camera(view, proj)
+
+    def same_as_reference(label):
+        r = render_both(sim)                       # ours, then the reference kernel (which scribbles over the buffer)
+        assert (r[False][0] == r[True][0]).all(), label
+        return r[False][0]
+
+    build_gpu(sim, batches[:3], (mn, mx))
+    a = same_as_reference("first frame")
+    sim.render(); sim.render()
+    hits, walks = cache_counters(sim)
+    assert hits > 0 and walks == 0, (hits, walks)                        # second frame in a row: every list comes from the cache
+    assert (sim.framebuffer() == a).all()
+    same_as_reference("after the reference kernel used the buffer")     # its scratch overwrote ours: verified, rebuilt
+    # the lists grow: two more batches into the same octree
+    for b in batches[3:]:
+        sim.upload_batch(b)
+    while sim.stats().batchletIndex < len(batches):
+        sim.update_octree()
+    sim.render(); sim.render()
+    same_as_reference("after growth")
+    # a reset and a different octree (other points, same heap addresses)
+    other, _, _ = data.terrain(3_000_000, seed=11)
+    sim.render()
+    build_gpu(sim, list(data.batches(other)), (mn, mx))
+    b_ = same_as_reference("after a reset")
+    assert (a != b_).any()
+    # HQS reads the same items
+    sim.set_settings(useHighQualityShading=1)
+    sim.render()
+    same_as_reference("hqs")
+    sim.set_settings(useHighQualityShading=0)
 
 
 def test_framebuffer_vs_cpu_oracle_rasteriser():
