@@ -97,6 +97,12 @@ int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t co
 // slots (main.cpp:141-222) while the uploader publishes them IN FILE ORDER and update launches consume them.
 int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_threads, uint64_t* num_points,
                               float* kernel_ms, float* total_ms);
+// same with flags. SIMLOD_STREAM_DIRECT: unbuffered (O_DIRECT) reads of whole 4 KB blocks — the reference's Windows
+// loader reads unbuffered too (SimlodLoader.cpp:59-141, FILE_FLAG_NO_BUFFERING) — for files that are not in the page
+// cache; SIMLOD_ERR_INVALID when the file system cannot do it (tmpfs).
+enum { SIMLOD_STREAM_DIRECT = 1 };
+int simlod_insert_simlod_file_ex(SimlodContext* ctx, const char* path, int loader_threads, uint32_t flags, uint64_t* num_points,
+                                 float* kernel_ms, float* total_ms);
 
 // LAS front end. The reference decodes LAS point records on CPU threads
 // (loadLasNative, LasLoader.cpp:169-226) and uploads 16-byte points; here the raw records are uploaded

@@ -116,7 +116,7 @@ EXPORTS = [
     "simlod_memcpy_htod", "simlod_host_alloc", "simlod_host_free", "simlod_device_alloc", "simlod_device_free",
     "simlod_get_launch_info", "simlod_device_rcp", "simlod_synchronize", "simlod_flush_l2",
     "simlod_partition_count", "simlod_partition_scatter", "simlod_partition_wait",
-    "simlod_export_framebuffer", "simlod_peer_signal", "simlod_composite_framebuffers", "simlod_generate", "simlod_reset_with_grid",
+    "simlod_export_framebuffer", "simlod_peer_signal", "simlod_composite_framebuffers", "simlod_generate", "simlod_reset_with_grid", "simlod_insert_simlod_file_ex",
 ]
 
 _lib = None
@@ -145,6 +145,7 @@ def load_library():
         "simlod_upload_batch_las": [vp, vp, u32, C.POINTER(LasLayout)],
         "simlod_upload_batch_las_device": [vp, u64, u32, C.POINTER(LasLayout)],
         "simlod_insert_simlod_file": [vp, C.c_char_p, C.c_int, C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(C.c_float)],
+        "simlod_insert_simlod_file_ex": [vp, C.c_char_p, C.c_int, u32, C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(C.c_float)],
         "simlod_update_octree": [vp, C.POINTER(C.c_float)],
         "simlod_insert": [vp, vp, u64, C.POINTER(C.c_float), C.POINTER(C.c_float)],
         "simlod_insert_device": [vp, u64, u64, C.POINTER(C.c_float), C.POINTER(C.c_float)],
@@ -344,11 +345,12 @@ class SimLOD:
         self._check(self._lib.simlod_insert_device(self._ctx, int(device_ptr), int(count), C.byref(kms), C.byref(tms)))
         return kms.value, tms.value
 
-    def insert_simlod_file(self, path, loader_threads=16):
+    def insert_simlod_file(self, path, loader_threads=16, direct=False):
         """reload() of the reference for one .simlod file: reset, stream the file through pinned slots with
-        `loader_threads` reader threads, insert. Returns (num_points, summed kernel ms, total device ms)."""
+        `loader_threads` reader threads, insert. direct=True reads unbuffered (O_DIRECT), for files that are not in
+        the page cache. Returns (num_points, summed kernel ms, total device ms)."""
         n, kms, tms = C.c_uint64(), C.c_float(), C.c_float()
-        self._check(self._lib.simlod_insert_simlod_file(self._ctx, path.encode(), int(loader_threads), C.byref(n), C.byref(kms), C.byref(tms)))
+        self._check(self._lib.simlod_insert_simlod_file_ex(self._ctx, path.encode(), int(loader_threads), 1 if direct else 0, C.byref(n), C.byref(kms), C.byref(tms)))
         self._lib.simlod_get_uniforms(self._ctx, C.byref(self.uniforms))
         return n.value, kms.value, tms.value
 

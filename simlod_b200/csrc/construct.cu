@@ -127,11 +127,13 @@ struct Ctl {
     BatchCounters batch[3];        // @160
     uint32_t allocDone;            // @256 blocks that have finished their share of the in-phase allocations of this launch (monotonic)
     uint32_t _pad[3];
-    uint64_t subNanos[16];         // @272 block 0's own timeline inside the phases (developer aid): fused = 0 allocate, 1 count+sample, 2 wait for the
+    uint64_t launchClock[32][2];   // %globaltimer at the start / end of the last 32 launches (slot = launchCount % 32): launch gaps as the device sees them
+    uint32_t launchCount, _pad2[3];
+    uint64_t subNanos[16];         // @800 block 0's own timeline inside the phases (developer aid): fused = 0 allocate, 1 count+sample, 2 wait for the
                                    //      allocation, 3 flush, 4 insert, 5 barrier; split = 6 work, 7 barrier; re-walk = 8 items, 9 flush, 10 barrier; 11 top of the batch loop, 12 re-walk list
 };
 static_assert(offsetof(Ctl, spilledTotal) == 80, "bench.py reads Ctl::spilledTotal at byte 80");
-static_assert(offsetof(Ctl, phaseNanos) == 96 && offsetof(Ctl, batch) == 160 && offsetof(Ctl, allocDone) == 256 && offsetof(Ctl, subNanos) == 272, "tools read Ctl by offset");
+static_assert(offsetof(Ctl, phaseNanos) == 96 && offsetof(Ctl, batch) == 160 && offsetof(Ctl, allocDone) == 256 && offsetof(Ctl, launchClock) == 272 && offsetof(Ctl, launchCount) == 784 && offsetof(Ctl, subNanos) == 800, "tools read Ctl by offset");
 
 // what the lane that sees a leaf cross 50 000 records about it (everything the split round needs)
 struct SpillInfo {
@@ -1282,6 +1284,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             ctl->spilledTotal = 0; ctl->voxelsTotal = 0; ctl->voxelsByPass[0] = 0; ctl->voxelsByPass[1] = 0;
             for (int i = 0; i < 8; i++) ctl->phaseNanos[i] = 0;
             for (int i = 0; i < 16; i++) ctl->subNanos[i] = 0;
+            ctl->launchCount = 0;
             ctl->rowBump = 0; ctl->rowFreeCount = 0;
             c.firstChild()[0] = 0;
             c.parentOf()[0] = 0;
@@ -1458,5 +1461,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         stats->allocatedBytes_persistent = ldv(&c.heap()->offset);
         stats->frameID = (uint32_t)uniforms.frameCounter;
         stats->dbg = ldv(&ctl->errorFlags);
+        const uint32_t lc = ctl->launchCount++;
+        ctl->launchClock[lc & 31u][0] = tStart; ctl->launchClock[lc & 31u][1] = globaltimer();
     }
 }

@@ -124,6 +124,8 @@ struct SimlodContext {
     CUarray colorArray = nullptr;
     CUsurfObject surface = 0;
     SimlodStats* hStats = nullptr;     // pinned
+    SimlodStats* hStatsRing = nullptr; // pinned, one snapshot per launch in flight (8)
+    CUevent evStatsDone[8] = {};       // the snapshot behind launch slot k has landed
     Program programs[3];
     CUmodule utilModule = nullptr, lasModule = nullptr, partitionModule = nullptr, genModule = nullptr;
     CUfunction fnGenUniform = nullptr, fnGenTerrain = nullptr, fnGenShell = nullptr;
@@ -251,10 +253,12 @@ int readStats(SimlodContext* ctx) {
 }
 
 // Stats::dbg carries kernel_construct's sticky capacity flags (construct.cu: ERR_*); bit 7 (a point far outside the
-// box) is informational, the others mean samples were dropped or a split was postponed
+// box) is informational
 int checkOverflow(SimlodContext* ctx) {
-    const uint32_t flags = ctx->hStats->dbg & 0x7fu;
-    if (flags) return fail(SIMLOD_ERR_OVERFLOW, "kernel_construct exceeded a per-batch capacity (Stats::dbg = 0x%x: 1 spill, 2 voxels, 4 directory, 8 nodes, 16 chunk stack, 32 splits, 64 leaf rows); reset to clear", flags);
+    // bits 0, 3, 5 (spill buffer, nodes[], split list full) only POSTPONE a split — no sample is lost, the octree stays valid,
+    // the bit stays visible in Stats::dbg; bits 1, 2, 4, 6 mean voxels or points were dropped: that is an error
+    const uint32_t flags = ctx->hStats->dbg & 0x56u;
+    if (flags) return fail(SIMLOD_ERR_OVERFLOW, "kernel_construct dropped samples: a per-batch capacity was exceeded (Stats::dbg = 0x%x: 2 voxel backlog, 4 chunk directory, 16 chunk stack, 64 leaf rows); reset to clear", ctx->hStats->dbg);
     return SIMLOD_OK;
 }
 
@@ -362,6 +366,8 @@ static int createResources(SimlodContext* ctx, const SimlodConfig* config) {
     CU(D(cuMemAlloc)(&ctx->cudaprint, 1024 * 1000 + 16));                 // CudaPrint ring (CudaPrint.cuh:33-36); never written
     CU(D(cuMemAlloc)(&ctx->flushBuf, L2_FLUSH_BYTES));
     CU(D(cuMemHostAlloc)((void**)&ctx->hStats, sizeof(SimlodStats), 0));
+    CU(D(cuMemHostAlloc)((void**)&ctx->hStatsRing, 8 * sizeof(SimlodStats), 0));
+    for (int i = 0; i < 8; i++) CU(D(cuEventCreate)(&ctx->evStatsDone[i], CU_EVENT_DISABLE_TIMING));
     ALLOC(b.ring, b.ring_bytes);
     if (config->persistent_bytes) {
         b.persistent_bytes = config->persistent_bytes;
@@ -430,6 +436,8 @@ void simlod_destroy(SimlodContext* ctx) {
                               ctx->numBatchesUploaded, ctx->batchSizes, ctx->frameStart, ctx->scratch4, ctx->cudaprint, ctx->flushBuf};
         for (CUdeviceptr p : ptrs) if (p) D(cuMemFree)(p);
         if (ctx->hStats) D(cuMemFreeHost)(ctx->hStats);
+        if (ctx->hStatsRing) D(cuMemFreeHost)(ctx->hStatsRing);
+        for (int i = 0; i < 8; i++) if (ctx->evStatsDone[i]) D(cuEventDestroy)(ctx->evStatsDone[i]);
         for (int p = 0; p < 3; p++) if (ctx->programs[p].module) D(cuModuleUnload)(ctx->programs[p].module);
         if (ctx->utilModule) D(cuModuleUnload)(ctx->utilModule);
         if (ctx->partitionModule) D(cuModuleUnload)(ctx->partitionModule);
@@ -589,6 +597,11 @@ int simlod_update_octree(SimlodContext* ctx, float* kernel_ms) {
     return checkOverflow(ctx);
 }
 
+// The main loop's streaming behaviour (main.cpp:1176-1180 + the uploader thread, :963-1063) without a frame in between:
+// uploads run ahead as far as the 50-slot ring allows, update launches are enqueued back to back (each consumes at most
+// 20 batches or 10 ms, voxels.cu:22,883,940), and the host learns what the device has consumed from asynchronous Stats
+// snapshots (one per launch, as the reference copies Stats every frame, main.cpp:1201-1216) — it never drains the
+// launch stream to decide what to do next, so the GPU does not idle between launches.
 static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr dev, uint64_t count, float* kernel_ms, float* total_ms) {
     int rc = setCurrent(ctx); if (rc) return rc;
     const uint64_t numBatches = (count + SLOT_POINTS - 1) / SLOT_POINTS;
@@ -596,8 +609,42 @@ static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr
     const uint32_t target = ctx->uploaded + (uint32_t)numBatches;
     uint64_t next = 0;
     float total = 0.0f;
+    // A launch starts once the batches it is meant to consume are published (stream wait on the slot's event) instead of
+    // snapshotting a half-filled ring. Device-resident sources arrive far faster than they are consumed: full 20-batch
+    // launches. Host sources arrive at PCIe speed, slower than the builder: launch from 2 batches on, so that
+    // insertion trails the upload closely.
+    const uint32_t gate = host ? 2u : 20u;
+    int inFlight[8]; int numInFlight = 0, nextSlot = 0;      // FIFO of launch slots whose Stats snapshot is pending
+    uint32_t covered = ctx->processed;                       // batches the enqueued launches are expected to have consumed
+    uint32_t stalled = 0;
+    auto drainOne = [&](bool block) -> int {                 // 1: a snapshot was taken in, 0: none ready, < 0: error
+        if (numInFlight == 0) return 0;
+        const int k = inFlight[0];
+        if (!block) {
+            CUresult q = D(cuEventQuery)(ctx->evStatsDone[k]);
+            if (q == CUDA_ERROR_NOT_READY) return 0;
+            if (q != CUDA_SUCCESS) return fail(SIMLOD_ERR_CUDA, "event query failed (%d)", (int)q);
+        } else {
+            CUresult q = D(cuEventSynchronize)(ctx->evStatsDone[k]);
+            if (q != CUDA_SUCCESS) { const char* e = nullptr; D(cuGetErrorString)(q, &e); return fail(SIMLOD_ERR_CUDA, "kernel_construct failed: %s (%d)", e ? e : "?", (int)q); }
+        }
+        float ms = 0.0f;
+        D(cuEventElapsedTime)(&ms, ctx->evBurst[k][0], ctx->evBurst[k][1]);
+        total += ms;
+        const uint32_t before = ctx->processed;
+        *ctx->hStats = ctx->hStatsRing[k];
+        ctx->processed = ctx->hStats->batchletIndex;
+        for (int i = 1; i < numInFlight; i++) inFlight[i - 1] = inFlight[i];
+        numInFlight--;
+        if (ctx->hStats->memCapacityReached) return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed);
+        int orc = checkOverflow(ctx); if (orc) return orc;
+        stalled = ctx->processed == before ? stalled + 1 : 0;
+        if (numInFlight == 0 && covered > ctx->processed) covered = ctx->processed;     // a launch ran into its 10 ms budget: the rest is launched again
+        return 1;
+    };
     CU(D(cuEventRecord)(ctx->evTotalStart, ctx->streamMain));
     while (ctx->processed < target) {
+        bool progress = false;
         // uploader: keep the ring as full as back-pressure allows (main.cpp:1012,1033-1056)
         while (next < numBatches && ctx->uploaded - ctx->processed < RING_SLOTS) {
             uint64_t first = next * SLOT_POINTS;
@@ -605,33 +652,32 @@ static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr
             rc = uploadCommon(ctx, host ? host + first : nullptr, dev ? dev + first * sizeof(SimlodPoint) : 0, n);
             if (rc) return rc;
             next++;
+            progress = true;
         }
-        // The reference launches updateOctree once per frame while uploads stream in (main.cpp:1176-1180).
-        // Without a frame to draw in between, launches are enqueued back to back — each consumes at most
-        // 20 batches or 10 ms — and Stats is read once per burst.
-        const uint32_t pendingBatches = ctx->uploaded - ctx->processed;
-        // A launch starts once the batches it is meant to consume are published (stream wait on the slot's event)
-        // instead of snapshotting a half-filled ring. Device-resident sources arrive far faster than they are
-        // consumed: gate on full 20-batch launches. Host sources arrive at PCIe speed, slower than the builder:
-        // gate on 2 batches so that insertion trails the upload closely.
-        const uint32_t gate = host ? 2u : 20u;
-        int burst = (int)std::min<uint32_t>(8u, std::max<uint32_t>(1u, (pendingBatches + gate - 1u) / gate));
-        for (int k = 0; k < burst; k++) {
-            if (pendingBatches > 0) {
-                uint32_t lastWanted = std::min<uint32_t>(ctx->uploaded, ctx->processed + gate * (uint32_t)(k + 1)) - 1u;
-                CU(D(cuStreamWaitEvent)(ctx->streamMain, ctx->evSlot[lastWanted % RING_SLOTS], 0));
-            }
+        while (numInFlight < 8 && ctx->uploaded > covered && (ctx->uploaded - covered >= gate || next == numBatches)) {
+            const uint32_t take = std::min<uint32_t>(20u, ctx->uploaded - covered);
+            CU(D(cuStreamWaitEvent)(ctx->streamMain, ctx->evSlot[(covered + take - 1u) % RING_SLOTS], 0));
+            const int k = nextSlot; nextSlot = (nextSlot + 1) % 8;
             rc = enqueueConstruct(ctx, k); if (rc) return rc;
+            CU(D(cuMemcpyDtoHAsync)(&ctx->hStatsRing[k], ctx->buf.stats, sizeof(SimlodStats), ctx->streamMain));
+            CU(D(cuEventRecord)(ctx->evStatsDone[k], ctx->streamMain));
+            inFlight[numInFlight++] = k;
+            covered += take;
+            progress = true;
         }
-        rc = readStats(ctx); if (rc) return rc;
-        for (int k = 0; k < burst; k++) {
-            float ms = 0.0f;
-            CU(D(cuEventElapsedTime)(&ms, ctx->evBurst[k][0], ctx->evBurst[k][1]));
-            total += ms;
+        for (;;) {
+            int d = drainOne(false);
+            if (d < 0) return d;
+            if (d == 0) break;
+            progress = true;
         }
-        if (ctx->hStats->memCapacityReached) return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed);
-        rc = checkOverflow(ctx); if (rc) return rc;
+        if (!progress) {
+            if (numInFlight > 0) { int d = drainOne(true); if (d < 0) return d; }
+            else if (stalled > 4) return fail(SIMLOD_ERR_CUDA, "kernel_construct makes no progress (%u of %u batches consumed)", ctx->processed, target);
+            else covered = ctx->processed;
+        }
     }
+    while (numInFlight > 0) { int d = drainOne(true); if (d < 0) return d; }
     CU(D(cuEventRecord)(ctx->evTotalEnd, ctx->streamMain));
     CU(D(cuEventSynchronize)(ctx->evTotalEnd));
     if (kernel_ms) *kernel_ms = total;
@@ -651,8 +697,14 @@ int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t co
 // ---- streaming front end -------------------------------------------------------------
 int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_threads, uint64_t* num_points,
                               float* kernel_ms, float* total_ms) {
+    return simlod_insert_simlod_file_ex(ctx, path, loader_threads, 0, num_points, kernel_ms, total_ms);
+}
+
+int simlod_insert_simlod_file_ex(SimlodContext* ctx, const char* path, int loader_threads, uint32_t flags, uint64_t* num_points,
+                                 float* kernel_ms, float* total_ms) {
     int rc = setCurrent(ctx); if (rc) return rc;
     if (!path) return fail(SIMLOD_ERR_INVALID, "null path");
+    const bool direct = (flags & SIMLOD_STREAM_DIRECT) != 0;
     constexpr int POOL_SLOTS = 32;         // 512 MB page-locked (the reference: 200 x 16 MB, main.cpp:35)
     const uint64_t slotBytes = SLOT_POINTS * sizeof(SimlodPoint);
     FILE* f = fopen(path, "rb");
@@ -687,8 +739,11 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
     std::atomic<uint64_t> nextPiece{0};
     std::atomic<bool> abort{false};
     const int nThreads = std::max(1, std::min(loader_threads, 64));
-    const int fd = open(path, O_RDONLY);
-    if (fd < 0) return fail(SIMLOD_ERR_INVALID, "cannot open %s", path);
+    // SIMLOD_STREAM_DIRECT: unbuffered reads, as the reference's Windows loader does (SimlodLoader.cpp:59-141, FILE_FLAG_NO_BUFFERING):
+    // whole 4 KB blocks straight from the device into a per-thread block buffer — no page-cache copy, no cache pollution —
+    // for files that are not resident in the page cache (a cold 5.6 GB scan gains nothing from being cached on the way)
+    const int fd = open(path, direct ? (O_RDONLY | O_DIRECT) : O_RDONLY);
+    if (fd < 0) return fail(SIMLOD_ERR_INVALID, direct ? "cannot open %s with O_DIRECT (tmpfs and some overlay file systems do not support it)" : "cannot open %s", path);
     if (!ctx->loaderPool) ctx->loaderPool = new LoaderPool();
     LoaderPool* pool = ctx->loaderPool;
     pool->run(nThreads, [&, pool](int worker) {
@@ -703,6 +758,23 @@ int simlod_insert_simlod_file(SimlodContext* ctx, const char* path, int loader_t
                 uint64_t bytes = std::min<uint64_t>(PIECE_POINTS, inBatch - p0) * 16;
                 char* dst = (char*)ctx->pinnedPool + (k % POOL_SLOTS) * slotBytes + p0 * 16;
                 off_t at = (off_t)(24 + (k * SLOT_POINTS + p0) * 16);
+                if (direct) {
+                    // the piece is <= 1 MB of records at a file offset that is 8 (mod 16): read the 4 KB blocks that cover it
+                    char* blockBuf = pool->directBuffer(worker);
+                    const off_t a0 = at & ~(off_t)4095;
+                    const size_t want = (size_t)((((uint64_t)at + bytes + 4095ull) & ~4095ull) - (uint64_t)a0);
+                    size_t have = 0;
+                    while (have < want) {
+                        ssize_t r = pread(fd, blockBuf + have, want - have, a0 + (off_t)have);
+                        if (r < 0) { abort.store(true); break; }
+                        if (r == 0) break;                                        // end of file inside the last block
+                        have += (size_t)r;
+                        if (r % 4096) break;                                      // short read at the end of the file
+                    }
+                    if (have < (size_t)(at - a0) + bytes) abort.store(true);
+                    else copyStreamingU(dst, blockBuf + (at - a0), bytes);
+                    bytes = 0;
+                }
                 char* stage = pool->bounce[worker];
                 while (bytes) {
                     uint64_t want = std::min<uint64_t>(bytes, LoaderPool::BOUNCE_BYTES), have = 0;

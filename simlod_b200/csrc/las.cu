@@ -15,8 +15,30 @@
 constexpr uint32_t LAS_TILE = 256;          // records per block iteration
 constexpr uint32_t LAS_MAX_BPP = 96;        // largest supported record (LAS 1.4 format 10 = 67 bytes + extra bytes)
 
-__device__ __forceinline__ uint32_t smemU16(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
-__device__ __forceinline__ int32_t smemI32(const uint8_t* p) { return (int32_t)(smemU16(p) | (smemU16(p + 2) << 16)); }
+// Records are 2-byte aligned when bytesPerPoint and the RGB offset are even (formats 0-3, 6-8 without odd extra bytes):
+// 16-bit shared loads. Odd record sizes (format 5 = 63 bytes, formats 4 / 9 / 10, odd extra bytes) put every other
+// record on an odd address: fields are assembled from byte loads there (the reference memcpy's, LasLoader.cpp:206-217).
+template <bool EVEN> __device__ __forceinline__ uint32_t smemU16(const uint8_t* p) {
+    if (EVEN) return *reinterpret_cast<const uint16_t*>(p);
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+}
+template <bool EVEN> __device__ __forceinline__ int32_t smemI32(const uint8_t* p) { return (int32_t)(smemU16<EVEN>(p) | (smemU16<EVEN>(p + 2) << 16)); }
+
+template <bool EVEN>
+__device__ __forceinline__ uint4 decodeRecord(const uint8_t* r, uint32_t offsetRgb, double scaleX, double scaleY, double scaleZ, double offsetX, double offsetY, double offsetZ) {
+    // LasLoader.cpp:206-210: point.x = double(XYZ[0]) * scale_x + offset_x  (double mul, double add, then to float)
+    float x = __double2float_rn(__dadd_rn(__dmul_rn((double)smemI32<EVEN>(r + 0), scaleX), offsetX));
+    float y = __double2float_rn(__dadd_rn(__dmul_rn((double)smemI32<EVEN>(r + 4), scaleY), offsetY));
+    float z = __double2float_rn(__dadd_rn(__dmul_rn((double)smemI32<EVEN>(r + 8), scaleZ), offsetZ));
+    uint32_t color = 0xff000000u;          // the reference leaves alpha (and, without RGB, the colour) uninitialised
+    if (offsetRgb > 0) {
+        // LasLoader.cpp:212-217: 16-bit channels above 255 are scaled down by 256
+        uint32_t cr = smemU16<EVEN>(r + offsetRgb), cg = smemU16<EVEN>(r + offsetRgb + 2), cb = smemU16<EVEN>(r + offsetRgb + 4);
+        cr = cr > 255 ? cr / 256 : cr; cg = cg > 255 ? cg / 256 : cg; cb = cb > 255 ? cb / 256 : cb;
+        color |= cr | (cg << 8) | (cb << 16);
+    }
+    return make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(z), color);
+}
 
 extern "C" __global__ void __launch_bounds__(256)
 simlod_las_decode(const uint8_t* __restrict__ records, uint64_t numPoints, uint32_t bytesPerPoint, uint32_t offsetRgb,
@@ -57,18 +79,9 @@ simlod_las_decode(const uint8_t* __restrict__ records, uint64_t numPoints, uint3
         }
         if (threadIdx.x < n) {
             const uint8_t* r = sh_rec + threadIdx.x * bytesPerPoint;
-            // LasLoader.cpp:206-210: point.x = double(XYZ[0]) * scale_x + offset_x  (double mul, double add, then to float)
-            float x = __double2float_rn(__dadd_rn(__dmul_rn((double)smemI32(r + 0), scaleX), offsetX));
-            float y = __double2float_rn(__dadd_rn(__dmul_rn((double)smemI32(r + 4), scaleY), offsetY));
-            float z = __double2float_rn(__dadd_rn(__dmul_rn((double)smemI32(r + 8), scaleZ), offsetZ));
-            uint32_t color = 0xff000000u;          // the reference leaves alpha (and, without RGB, the colour) uninitialised
-            if (offsetRgb > 0) {
-                // LasLoader.cpp:212-217: 16-bit channels above 255 are scaled down by 256
-                uint32_t cr = smemU16(r + offsetRgb), cg = smemU16(r + offsetRgb + 2), cb = smemU16(r + offsetRgb + 4);
-                cr = cr > 255 ? cr / 256 : cr; cg = cg > 255 ? cg / 256 : cg; cb = cb > 255 ? cb / 256 : cb;
-                color |= cr | (cg << 8) | (cb << 16);
-            }
-            uint4 v = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(z), color);
+            const bool even = ((bytesPerPoint | offsetRgb) & 1u) == 0;
+            uint4 v = even ? decodeRecord<true>(r, offsetRgb, scaleX, scaleY, scaleZ, offsetX, offsetY, offsetZ)
+                           : decodeRecord<false>(r, offsetRgb, scaleX, scaleY, scaleZ, offsetX, offsetY, offsetZ);
             *reinterpret_cast<uint4*>(out + first + threadIdx.x) = v;
         }
         __syncthreads();                          // the stage is reused by the next tile

@@ -35,8 +35,10 @@ struct CudaPrint;
 // unused tail of the 200 000 000-byte buffer (main.cpp:556) a cache of the nodes' chunk lists.
 namespace rbuf {
 constexpr uint64_t OFF_CTL       = 0;
+constexpr uint64_t OFF_VISLIST   = 4096;                           // u32 node indices of the LOD cut
+constexpr uint64_t VIS_CAP       = 263168;
 constexpr uint64_t ITEM_CAP      = 2097152;                        // chunk items per frame = 2 G samples (the reference: 100 000 nodes)
-constexpr uint64_t OFF_ITEMS     = 4096;                           // u64 per item, see packItem()
+constexpr uint64_t OFF_ITEMS     = OFF_VISLIST + VIS_CAP * 4;      // u64 per item, see packItem()
 constexpr uint64_t OFF_FB        = 31200144;                       // 15 200 000 + 7*16 + 32 + 16 000 000
 constexpr uint64_t TOTAL_BYTES   = 200000000;                      // what the host allocates (main.cpp:556)
 constexpr uint64_t NODE_TAB      = 263168;                         // >= floor(40 000 000 / 152) nodes
@@ -62,7 +64,9 @@ struct RCtl {
     uint32_t numVisibleNodes, numVisiblePoints, numVisibleVoxels, numVisibleInner, numVisibleLeaves;
     uint32_t overflow;
     uint32_t cacheHits, cacheWalks;      // lists served from the chunk-list cache / walked (developer counters)
+    uint64_t phaseNanos[6];              // @48 last frame, by the grid's first thread: clear|visibility, cut, items, draw (all passes), stats+EDL
 };
+static_assert(offsetof(RCtl, cacheHits) == 40 && offsetof(RCtl, phaseNanos) == 48, "tools and tests read RCtl by offset");
 
 // ---- chunk-list cache ---------------------------------------------------------------------------------------
 // Chunk lists are singly linked, so the k-th chunk of a node is k dependent loads away; the reference makes every
@@ -158,9 +162,9 @@ __device__ void computeVisibilityFlags(const Uniforms& u, Node* nodes, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------
-// visibility, pass 2: LOD cut (render.cu:906-933) + chunk items, one phase. A warp takes 32 nodes; every node
-// that is drawn (a visible non-large child of a large node, or a large visible leaf) is then handled by the whole
-// warp: its two chunk lists are turned into work items through the cache above.
+// visibility, pass 2: LOD cut (render.cu:906-933), then the chunk items of every drawn node (a visible non-large
+// child of a large node, or a large visible leaf): a whole warp turns the node's two chunk lists into work items
+// through the cache above.
 // ------------------------------------------------------------------------------------------
 struct EmitCtx {
     RCtl* ctl;
@@ -274,8 +278,7 @@ __device__ void emitNode(const EmitCtx& e, const Node* node) {
     const uint32_t nP = (numPoints + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
     const uint32_t nV = (numVoxels + SIMLOD_POINTS_PER_CHUNK - 1) / SIMLOD_POINTS_PER_CHUNK;
     uint32_t base = 0;
-    if (lane == 0) {
-        atomicAdd(&e.ctl->numVisibleNodes, 1u);                                      // render.cu:918-932 bookkeeping
+    if (lane == 0) {                                                                 // render.cu:918-932 bookkeeping
         if (numPoints > 0) { atomicAdd(&e.ctl->numVisibleLeaves, 1u); atomicAdd(&e.ctl->numVisiblePoints, numPoints); }
         else if (numVoxels > 0) { atomicAdd(&e.ctl->numVisibleInner, 1u); atomicAdd(&e.ctl->numVisibleVoxels, numVoxels); }
         if (nP + nV) base = atomicAdd(&e.ctl->numItems, nP + nV);
@@ -289,37 +292,32 @@ __device__ void emitNode(const EmitCtx& e, const Node* node) {
     emitList(e, node->voxelChunks, nV, numVoxels, level, colorId, &e.entries[2 * index + 1], e.items + base + nP);
 }
 
-__device__ void lodCutAndEmit(const EmitCtx& e, uint32_t numNodes) {
-    const uint32_t FULL = 0xffffffffu;
-    const uint32_t lane = laneId();
-    const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t warp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;          // neighbouring nodes go to different SMs
-    for (uint32_t first = warp * 32u; first < numNodes; first += numWarps * 32u) {
-        const uint32_t n = first + lane;
-        const Node* node = &e.nodes[n];
-        const bool large = n < numNodes && node->isLarge;
-        const bool leaf = large && isLeaf(node);
-        // candidates of this lane: its children (render.cu:918-927), or the node itself when it is a large visible leaf
-#pragma unroll 1
-        for (int i = 0; i < 9; i++) {
-            const Node* cand = nullptr;
-            if (large) {
-                if (i < 8) {
-                    if (!leaf) {
-                        const Node* child = node->children[i];
-                        if (child != nullptr && !child->isLarge && child->visible) cand = child;
-                    }
-                } else if (leaf && node->visible) cand = node;
+// LOD cut (render.cu:906-933), one thread per node: the indices of the nodes to draw
+__device__ void lodCut(RCtl* ctl, uint32_t* visList, const Node* nodes, uint32_t numNodes) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < numNodes; n += stride) {
+        const Node* node = &nodes[n];
+        if (!node->isLarge) continue;
+        if (!isLeaf(node)) {
+            for (int i = 0; i < 8; i++) {
+                const Node* child = node->children[i];
+                if (child == nullptr || child->isLarge || !child->visible) continue;
+                uint32_t v = atomicAdd(&ctl->numVisibleNodes, 1u);
+                if (v < rbuf::VIS_CAP) visList[v] = (uint32_t)(child - nodes);
             }
-            uint32_t mask = __ballot_sync(FULL, cand != nullptr);
-            while (mask) {
-                const uint32_t src = __ffs(mask) - 1u;
-                mask &= mask - 1u;
-                const Node* drawn = reinterpret_cast<const Node*>(__shfl_sync(FULL, (uint64_t)cand, src));
-                emitNode(e, drawn);
-            }
+        } else if (node->visible) {
+            uint32_t v = atomicAdd(&ctl->numVisibleNodes, 1u);
+            if (v < rbuf::VIS_CAP) visList[v] = n;
         }
     }
+}
+
+// drawn nodes -> chunk items: one WARP per node, the nodes spread over all warps of the grid (drawn nodes cluster in
+// nodes[]: the 8 children of a node are neighbours)
+__device__ void emitVisible(const EmitCtx& e, const uint32_t* visList, uint32_t numVisible) {
+    const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    for (uint32_t v = warp; v < numVisible; v += numWarps) emitNode(e, &e.nodes[visList[v]]);
 }
 
 // one pass over the frame's items: persistent warps pop chunk items with a single atomicAdd each
@@ -409,8 +407,10 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     ec.heapBase = reinterpret_cast<const uint8_t*>(nodes[0].grid) - 16;
     ec.heapUsed = nodes[0].grid ? *reinterpret_cast<const volatile uint64_t*>(ec.heapBase + 8) : 0ull;
 
+    uint64_t tPhase = globaltimer();
+#define RPHASE(k) do { if (first) { uint64_t _t = globaltimer(); ctl->phaseNanos[k] = _t - tPhase; tPhase = _t; } } while (0)
     if (first) {
-        *frameStartTimestamp = globaltimer();
+        *frameStartTimestamp = tPhase;
         ctl->numItems = 0; ctl->head[0] = 0; ctl->head[1] = 0; ctl->head[2] = 0;
         ctl->numVisibleNodes = 0; ctl->numVisiblePoints = 0; ctl->numVisibleVoxels = 0;
         ctl->numVisibleInner = 0; ctl->numVisibleLeaves = 0; ctl->overflow = 0;
@@ -441,10 +441,16 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     const uint32_t numNodes = min(ldv(&stats->numNodes), (uint32_t)rbuf::NODE_TAB);
     computeVisibilityFlags(uniforms, nodes, numNodes, cubeSize, uniforms.boxMin[0], uniforms.boxMin[1], uniforms.boxMin[2]);
     grid.sync();
+    RPHASE(0);
 
-    // ---- phase 2: LOD cut + chunk items ------------------------------------------------------------------------------
-    if (nodes[0].grid != nullptr) lodCutAndEmit(ec, numNodes);
+    // ---- phase 2: LOD cut; phase 3: chunk items of the drawn nodes -----------------------------------------------
+    uint32_t* visList = reinterpret_cast<uint32_t*>(base + rbuf::OFF_VISLIST);
+    lodCut(ctl, visList, nodes, numNodes);
     grid.sync();
+    RPHASE(1);
+    if (nodes[0].grid != nullptr) emitVisible(ec, visList, min(ldv(&ctl->numVisibleNodes), (uint32_t)rbuf::VIS_CAP));
+    grid.sync();
+    RPHASE(2);
 
     const uint32_t numItems = min(ldv(&ctl->numItems), (uint32_t)rbuf::ITEM_CAP);
     const Row* T = uniforms.transform.rows;
@@ -509,6 +515,7 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
         }
     }
     grid.sync();
+    RPHASE(3);
 
     // the line/bounding-box overlay of the reference (render.cu:1197-1233) is empty unless
     // showBoundingBox is set; it is a debug overlay and not part of this path.
@@ -571,4 +578,5 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
             if (!covered) surf2Dwrite((uint32_t)(framebuffer[i] & 0xffffffffull), gl_colorbuffer, (int)x * 4, (int)y);
         }
     }
+    RPHASE(4);
 }

@@ -161,16 +161,18 @@ def batches(points, batch_size=1_000_000):
 
 
 # ---- LAS files (for the LAS front-end row) ------------------------------------------------------------
-LAS_RECORD_BYTES = {0: 20, 1: 28, 2: 26, 3: 34}
-LAS_RGB_OFFSET = {2: 20, 3: 28}
+LAS_RECORD_BYTES = {0: 20, 1: 28, 2: 26, 3: 34, 5: 63, 7: 36}      # 5: odd record size (waveform packet); 7: LAS 1.4
+LAS_RGB_OFFSET = {2: 20, 3: 28, 5: 28, 7: 30}
 
 
-def las_records(points, fmt=2, scale=(0.001, 0.001, 0.001), offset=(0.0, 0.0, 0.0), wide_colors=True):
+def las_records(points, fmt=2, scale=(0.001, 0.001, 0.001), offset=(0.0, 0.0, 0.0), wide_colors=True, extra_bytes=0):
     """Raw LAS point records (uint8, n x bytesPerPoint) for 16-byte points: int32 XYZ = round((p - offset) / scale),
     intensity/flags zero, RGB as 16-bit channels (x 257 when wide_colors, as most LAS writers do)."""
     n = points.shape[0]
-    bpp = LAS_RECORD_BYTES[fmt]
+    bpp = LAS_RECORD_BYTES[fmt] + extra_bytes
     rec = np.zeros((n, bpp), dtype=np.uint8)
+    if bpp > LAS_RECORD_BYTES[fmt]:
+        rec[:, LAS_RECORD_BYTES[fmt]:] = 0xA5                    # "extra bytes" of the record: anything
     for k, ax in enumerate("xyz"):
         q = np.rint((points[ax].astype(np.float64) - offset[k]) / scale[k]).astype("<i4")
         rec[:, 4 * k:4 * k + 4] = q.view(np.uint8).reshape(n, 4)
@@ -185,10 +187,10 @@ def las_records(points, fmt=2, scale=(0.001, 0.001, 0.001), offset=(0.0, 0.0, 0.
     return rec
 
 
-def write_las(path, points, fmt=2, scale=(0.001, 0.001, 0.001), offset=(0.0, 0.0, 0.0), wide_colors=True):
+def write_las(path, points, fmt=2, scale=(0.001, 0.001, 0.001), offset=(0.0, 0.0, 0.0), wide_colors=True, extra_bytes=0):
     """Minimal LAS 1.2 file with the header fields the reference reads (LasLoader.h:21-55)."""
     import struct
-    rec = las_records(points, fmt, scale, offset, wide_colors)
+    rec = las_records(points, fmt, scale, offset, wide_colors, extra_bytes)
     n, bpp = rec.shape
     hdr = bytearray(227)
     hdr[0:4] = b"LASF"

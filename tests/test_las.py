@@ -25,15 +25,16 @@ def same_points(a, b, with_color=True):
 
 
 @needs_ref_las
-@pytest.mark.parametrize("fmt,wide", [(2, True), (2, False), (3, True), (0, True), (1, True)])
-def test_oracle_decode_matches_reference_lasloader(tmp_path, fmt, wide):
+@pytest.mark.parametrize("fmt,wide,extra", [(2, True, 0), (2, False, 0), (3, True, 0), (0, True, 0), (1, True, 0),
+                                            (5, True, 0), (7, True, 0), (2, True, 1), (3, False, 3)])      # 5: 63-byte records; odd extra bytes
+def test_oracle_decode_matches_reference_lasloader(tmp_path, fmt, wide, extra):
     pts, _, _ = data.terrain(60_000)
     path = str(tmp_path / "t.las")
-    rec = data.write_las(path, pts, fmt=fmt, scale=SCALE, offset=OFFSET, wide_colors=wide)
+    rec = data.write_las(path, pts, fmt=fmt, scale=SCALE, offset=OFFSET, wide_colors=wide, extra_bytes=extra)
     for first, count in ((0, 60_000), (123, 4_567), (59_999, 1)):
         ref = oracle.ref_las_load(path, first, count, TRANSLATION)
         got = oracle.decode_las(rec[first:first + count], count, rec.shape[1], fmt, SCALE, OFFSET, TRANSLATION)
-        assert same_points(ref, got, with_color=fmt in (2, 3)), (fmt, first, count)
+        assert same_points(ref, got, with_color=fmt in (2, 3, 5, 7)), (fmt, first, count)
 
 
 def test_decode_roundtrip_properties():
@@ -50,12 +51,12 @@ def test_decode_roundtrip_properties():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fmt", [2, 3, 0])
-def test_device_decode_matches_oracle_and_reference(tmp_path, fmt):
+@pytest.mark.parametrize("fmt,extra", [(2, 0), (3, 0), (0, 0), (5, 0), (7, 0), (2, 1), (0, 3)])      # odd record sizes: every other record on an odd address
+def test_device_decode_matches_oracle_and_reference(tmp_path, fmt, extra):
     from simlod_b200 import SimLOD
     pts, mn, mx = data.terrain(700_001)
     path = str(tmp_path / "t.las")
-    rec = data.write_las(path, pts, fmt=fmt, scale=SCALE, offset=OFFSET)
+    rec = data.write_las(path, pts, fmt=fmt, scale=SCALE, offset=OFFSET, extra_bytes=extra)
     sim = SimLOD(320, 176, persistent_bytes=2 << 30)
     try:
         sim.set_box(mn, mx)
@@ -70,7 +71,7 @@ def test_device_decode_matches_oracle_and_reference(tmp_path, fmt):
             assert same_points(got, want, with_color=True), (fmt, slot)
             if HAVE_REF_LAS and n:
                 ref = oracle.ref_las_load(path, first, n, TRANSLATION)
-                assert same_points(got, ref, with_color=fmt in (2, 3)), (fmt, slot)
+                assert same_points(got, ref, with_color=fmt in (2, 3, 5, 7)), (fmt, slot)
             first += n
     finally:
         sim.close()

@@ -437,6 +437,27 @@ def test_shell_and_incoherent_streams_vs_oracle(sim):
     assert o.check_voxel_colors(cn) == 0
 
 
+def test_spill_buffer_overflow_postpones_splits_and_loses_nothing(sim):
+    """64 level-2 leaves of a uniform stream cross 50 000 points in the same 100 k-point batch: 64 x ~49.2 k stored points
+    exceed the 3 Mi-entry spill buffer (the reference re-inserts at most 3 000 001 spilled points per batch and silently
+    drops the rest, voxels.cu:628 — a regime where it is not defined). Here the splits that do not fit are refused as a
+    whole and requested again in the next batch: Stats::dbg bit 0 is raised, no point is lost, the octree stays valid."""
+    n = 3_600_000
+    pts, mn, mx = data.uniform_cube(n, size=1024.0, seed=123)
+    sim.set_box(mn, mx)
+    sim.reset()
+    sim.insert_batches(list(data.batches(pts, 100_000)))
+    st = sim.stats()
+    assert st.numPointsProcessed == n and st.numPoints == n, (st.numPoints, st.dbg)
+    assert st.dbg & 0x56 == 0                                   # nothing was dropped
+    cn = oracle.canon_from_image(*sim.download_octree())         # raises if the image is inconsistent
+    leaves = cn.records[cn.records["isLeaf"] == 1]
+    assert int(leaves["numPoints"].sum()) == n and (leaves["numPoints"] <= 64_000).all()
+    # with a stream that does not overflow, the same code path is the oracle's (regression guard for the refusal logic)
+    if st.dbg & 1:
+        assert (cn.records["level"] <= 4).all()
+
+
 @needs_ref
 def test_shell_stream_vs_reference_kernels(sim):
     pts, mn, mx = data.shell(2_400_000)

@@ -51,6 +51,40 @@ def test_file_streamer_builds_the_same_octree_as_in_memory_batches(tmp_path, thr
 
 
 @pytest.mark.gpu
+def test_file_streamer_unbuffered_reads_build_the_same_octree(tmp_path):
+    """SIMLOD_STREAM_DIRECT (O_DIRECT block reads, the cold-file path): same octree as the buffered path, for a file whose
+    pages were dropped from the page cache. Skipped where the file system cannot do O_DIRECT (tmpfs)."""
+    from simlod_b200 import SimLOD, SimlodError
+    n = 2_100_007                                  # ends in the middle of a 4 KB block
+    pts, mn, mx = data.terrain(n)
+    path = str(tmp_path / "cold.simlod")
+    data.write_simlod(path, pts, mn, mx)
+    fd = os.open(path, os.O_RDONLY)
+    try:
+        os.fsync(fd)
+        os.posix_fadvise(fd, 0, 0, os.POSIX_FADV_DONTNEED)       # evict the (clean) pages: the next read comes from the device
+    finally:
+        os.close(fd)
+    sim = SimLOD(320, 176, persistent_bytes=3 << 30)
+    try:
+        try:
+            got_n, kms, tms = sim.insert_simlod_file(path, loader_threads=5, direct=True)
+        except SimlodError as e:
+            if "O_DIRECT" in str(e):
+                pytest.skip("file system of %s does not support O_DIRECT" % tmp_path)
+            raise
+        st_a = sim.stats()
+        assert got_n == n and st_a.numPoints == n and st_a.dbg == 0
+        cn_a = oracle.canon_from_image(*sim.download_octree())
+        sim.insert_simlod_file(path, loader_threads=5)
+        st_b = sim.stats()
+        cn_b = oracle.canon_from_image(*sim.download_octree())
+        assert not oracle.compare_canon(cn_a, cn_b) and not oracle.compare_stats(st_a, st_b)
+    finally:
+        sim.close()
+
+
+@pytest.mark.gpu
 def test_file_streamer_rejects_bad_input(tmp_path):
     from simlod_b200 import SimLOD, SimlodError
     sim = SimLOD(320, 176, persistent_bytes=1 << 30)

@@ -129,7 +129,7 @@ for K in sizes:
             st = sim.stats()
             assert st.numPoints == n and st.dbg == 0, (st.numPoints, st.dbg)
             ph = sim.memcpy_dtoh(sim.buffers().momentary + 96, 64).view(np.uint64).astype(np.float64)
-            sub = sim.memcpy_dtoh(sim.buffers().momentary + 272, 128).view(np.uint64).astype(np.float64)
+            sub = sim.memcpy_dtoh(sim.buffers().momentary + 800, 128).view(np.uint64).astype(np.float64)
             if best is None or kms < best[0]:
                 best = (kms, tms, ph, sub)
         kms, tms, ph, sub = best

@@ -67,7 +67,7 @@ def full_build(module):
         kms, tms = sim.insert_device(dptr, n)
         if best is None or kms < best[0]:
             ph = sim.memcpy_dtoh(sim.buffers().momentary + 96, 64).view(np.uint64).astype(np.float64)
-            sub = sim.memcpy_dtoh(sim.buffers().momentary + 272, 96).view(np.uint64).astype(np.float64)
+            sub = sim.memcpy_dtoh(sim.buffers().momentary + 800, 96).view(np.uint64).astype(np.float64)
             best = (kms, tms, ph, sub)
     st = sim.stats()
     canon = oracle.canon_from_image(*sim.download_octree())
