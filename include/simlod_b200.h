@@ -87,7 +87,9 @@ int simlod_update_octree(SimlodContext* ctx, float* kernel_ms);
 // "points/sec update kernel" denominator, main.cpp:1484); *total_ms (optional) = device time from
 // the first upload to the end of the last launch, measured with an event pair on the launch stream.
 int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t count, float* kernel_ms, float* total_ms);
-// same with the whole point set resident in device memory (batches are copied device-to-device)
+// same with the whole point set resident in device memory: the kernel reads the 1 000 000-point batches where they are
+// (no copy into the ring; the `points` argument of each launch maps the ring slots of its 50-batch window onto the
+// caller's buffer, which must stay valid and unchanged until the call returns)
 int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms, float* total_ms);
 
 // Streaming front end for one `.simlod` file: reload() + spawnLoader + spawnUploader of

@@ -54,7 +54,8 @@ constexpr uint64_t ITEM_CAP       = MAX_BATCH + SPILL_CAP;
 constexpr uint64_t VOXEL_CAP      = 4ull << 20;        // voxels created per batch, per parity
 constexpr uint64_t VOXEL_SHARED   = 512ull << 10;      // tail of the voxel backlog shared by all blocks (overflow of a block's own segment)
 constexpr uint64_t DIR_CAP        = 512ull << 10;      // chunk directory entries per batch, per parity
-constexpr uint64_t QUEUE_CAP      = 2ull << 20;        // free-chunk stack (reference: 1 M)
+constexpr uint64_t QUEUE_CAP      = 3ull << 19;        // free-chunk stack, 1.5 Mi entries (reference: 1 M)
+constexpr uint64_t WL_CAP         = 2ull << 20;        // items a re-walk round can be told to visit by name (more: every affected run is scanned)
 constexpr uint64_t SPILLNODE_CAP  = 100000;            // voxels.cu:847
 constexpr uint64_t ROW_CAP        = 65536;             // leaves that hold points at the same time (x 64 chunk slots)
 constexpr uint64_t ROW_SLOTS      = 64;                // chunk pointers per leaf row (a leaf holds <= 50 chunks)
@@ -84,7 +85,8 @@ constexpr uint64_t OFF_SLOTOF     = align256(OFF_LEAFOF + 2 * ITEM_CAP * 4);    
 constexpr uint64_t OFF_SPILLED    = align256(OFF_SLOTOF + 2 * ITEM_CAP * 4);
 constexpr uint64_t OFF_VKEY       = align256(OFF_SPILLED + SPILL_CAP * 16);            // [2]
 constexpr uint64_t OFF_VCOLOR     = align256(OFF_VKEY + 2 * VOXEL_CAP * 8);            // [2]
-constexpr uint64_t TOTAL          = align256(OFF_VCOLOR + 2 * VOXEL_CAP * 4);
+constexpr uint64_t OFF_WORKLIST   = align256(OFF_VCOLOR + 2 * VOXEL_CAP * 4);
+constexpr uint64_t TOTAL          = align256(OFF_WORKLIST + WL_CAP * 4);
 static_assert(TOTAL <= 300000000ull, "scratch must fit the host's 300 MB momentary buffer (main.cpp:554)");
 }  // namespace scratch
 
@@ -129,7 +131,9 @@ struct Ctl {
     uint32_t _pad[3];
     uint64_t launchClock[32][2];   // %globaltimer at the start / end of the last 32 launches (slot = launchCount % 32): launch gaps as the device sees them
     uint32_t launchCount, _pad2[3];
-    uint64_t subNanos[16];         // @800 block 0's own timeline inside the phases (developer aid): fused = 0 allocate, 1 count+sample, 2 wait for the
+    uint64_t subNanos[16];         // @800
+    struct Worklist { uint32_t cursor[2]; uint32_t legacy; uint32_t pad; } wl[3];      // @928 per batch (index = batch % 3): entries of the list of
+                                   //      round r (cursor[r & 1]); legacy != 0: some block could not name its items, rounds scan the affected runs block 0's own timeline inside the phases (developer aid): fused = 0 allocate, 1 count+sample, 2 wait for the
                                    //      allocation, 3 flush, 4 insert, 5 barrier; split = 6 work, 7 barrier; re-walk = 8 items, 9 flush, 10 barrier; 11 top of the batch loop, 12 re-walk list
 };
 static_assert(offsetof(Ctl, spilledTotal) == 80, "bench.py reads Ctl::spilledTotal at byte 80");
@@ -184,6 +188,7 @@ struct Ctx {
     __device__ __forceinline__ Point*     spilled()     const { return at<Point>(scratch::OFF_SPILLED); }
     __device__ __forceinline__ uint64_t*  vkey(uint32_t p)   const { return at<uint64_t>(scratch::OFF_VKEY) + p * scratch::VOXEL_CAP; }     // cell | node << 21 | slot << 41
     __device__ __forceinline__ uint32_t*  vcolor(uint32_t p) const { return at<uint32_t>(scratch::OFF_VCOLOR) + p * scratch::VOXEL_CAP; }
+    __device__ __forceinline__ uint32_t*  worklist()    const { return at<uint32_t>(scratch::OFF_WORKLIST); }    // items (leafOf index) the coming re-walk pass visits
 };
 
 // the batch a pass works on
@@ -429,6 +434,21 @@ __device__ __forceinline__ uint32_t finalSlot(uint32_t sl) { return (sl & PROVIS
 // the first-visit pass keeps the slots of the block's own run in shared memory until they are final
 constexpr uint32_t RUNSLOT_CAP = 2048;
 __shared__ uint32_t sh_runSlot[RUNSLOT_CAP];
+// "My items": what the block counted in its last counting pass, with the table entry each went to (the slot word).
+// After the first-visit pass that is its run of the batch (sh_runSlot); after a re-walk pass the explicit list below
+// (kept in the TMA stages, which only first-visit passes use). A leaf can only cross its capacity in the pass that
+// adds to it, so the items that move in a round are exactly items of these lists whose table entry names a leaf that
+// was split: the split phase picks them out in shared memory and names them in a global worklist, and the re-walk
+// pass visits the worklist — nothing is scanned to find out that it did not move. A block that cannot name its
+// items (list or table full, run too long for sh_runSlot) raises Ctl::Worklist::legacy; the rounds of that batch then
+// scan the affected runs (markAffectedRun), for which the run filters are kept up to date in every case.
+constexpr uint32_t LIST_CAP = 2048;
+__shared__ uint32_t sh_listCount;         // entries of the explicit list (may run past LIST_CAP: overflow)
+__shared__ uint32_t sh_listMode;          // 0: the run (sh_runSlot), 1: the explicit list
+__shared__ uint32_t sh_blockLegacy;       // this block cannot name its items any more in this batch
+__shared__ uint8_t  sh_entrySplit[VOXTAB_SIZE];
+__shared__ uint32_t sh_splitNodes[64];
+__shared__ uint32_t sh_wlCount, sh_wlBase, sh_wlFill;
 // block-wide exclusive prefix sum of one value per thread (256 threads); returns the block total
 __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t& total) {
     __shared__ uint32_t sh_warpSum[8];
@@ -552,9 +572,105 @@ __device__ __noinline__ uint32_t countGlobal(const Ctx c, const Batch b, uint32_
 // ------------------------------------------------------------------------------------------
 struct LeafCache { uint32_t node, level, kx, ky, kz, parent; };      // node == VOXTAB_EMPTY: nothing cached
 
-template <bool SAMPLE, bool COUNT, bool UNCACHED_GRID, bool DEDUP>
+// the upward half of the walk: probe / set the point's cell from (sNode, sLevel) towards the root until a set bit is met
+// (or down to stopLevel), recording a voxel for every cell this thread wins
+template <bool UNCACHED_GRID, bool DEDUP>
+__device__ __forceinline__ void sampleUp(const Ctx& c, const Batch& b, const Coords& q, uint32_t color, uint32_t sNode, uint32_t sLevel, uint32_t stopLevel) {
+    const uint32_t lane = laneId();
+    const bool exhaustive = !nested(q);          // far outside the box: probe every level like the reference does
+    if (exhaustive) atomicOr(&c.ctl()->errorFlags, ERR_FAR_POINT);
+    // atomicOr results are not needed to continue upwards (a speculative probe of the level above is always
+    // correct: every cell has exactly one winner), so up to 3 stay in flight per lane
+    uint32_t pending = 0;
+    uint32_t old0 = 0, old1 = 0, old2 = 0, key0 = 0, key1 = 0, key2 = 0, cel0 = 0, cel1 = 0, cel2 = 0;
+    auto settle = [&]() {
+        if (pending > 0 && (old0 & (1u << (cel0 & 31u))) == 0) recordVoxel(c, b, key0, cel0, color);
+        if (pending > 1 && (old1 & (1u << (cel1 & 31u))) == 0) recordVoxel(c, b, key1, cel1, color);
+        if (pending > 2 && (old2 & (1u << (cel2 & 31u))) == 0) recordVoxel(c, b, key2, cel2, color);
+        pending = 0;
+    };
+    const uint64_t* gridPtr = c.gridPtr();
+    for (;;) {
+        uint64_t g = gridPtr[sNode];
+        bool goUp = exhaustive;
+        if (g != 0) {
+            uint32_t cell = cellAt(q, sLevel);
+            uint32_t* word = reinterpret_cast<uint32_t*>(g) + (cell >> 5);
+            uint32_t bit = 1u << (cell & 31u);
+            // non-atomic pre-test (voxels.cu:93-94): bits are only ever set while a grid is live, so a set bit seen
+            // through the (non-coherent) L1 is final. The root's grid is cleared in place when the root splits
+            // (voxels.cu:370-382): the one pass that follows such a clear reads through L2 instead.
+            uint32_t seen = UNCACHED_GRID ? ldcg(word) : *word;
+            if ((seen & bit) == 0) {
+                // first-visit passes: neighbouring points of a scan hit the same cell, so one atomic per distinct cell
+                // among the converged lanes. Re-walk passes fill freshly cleared grids, where the cells of a warp's
+                // items are mostly distinct and the match would cost more than the few atomics it saves.
+                bool mine = true;
+                if (DEDUP) {
+                    uint32_t active = __activemask();
+                    uint32_t peers = __match_any_sync(active, (uint64_t)(uintptr_t)word * 32ull + (cell & 31u));
+                    mine = lane == (uint32_t)__ffs(peers) - 1u;
+                }
+                if (mine) {
+                    if (pending == 3) settle();
+                    uint32_t old = atomicOr(word, bit);
+                    if (pending == 0) { old0 = old; key0 = sNode; cel0 = cell; }
+                    else if (pending == 1) { old1 = old; key1 = sNode; cel1 = cell; }
+                    else { old2 = old; key2 = sNode; cel2 = cell; }
+                    pending++;
+                    goUp = true;
+                }
+            }
+        }
+        if (!goUp || sLevel <= stopLevel) break;
+        sNode = c.parentOf()[sNode];
+        sLevel--;
+    }
+    settle();
+}
+
+// voxel stage of a first-visit pass: per warp, a queue of (item, deepest grid node | level << 24) of the run's points whose
+// cell was still clear when they were walked
+constexpr uint32_t VQ_CAP = 64;
+__shared__ uint2 sh_vq[8][VQ_CAP];
+__shared__ uint32_t sh_vqCount[8];
+
+template <bool UNCACHED_GRID>
+__device__ __forceinline__ void voxelStageDrain(const Ctx& c, const Batch& b) {           // warp-collective
+    const uint32_t warp = threadIdx.x >> 5, lane = laneId();
+    const uint32_t n = sh_vqCount[warp];
+    for (uint32_t e0 = 0; e0 < n; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        if (e < n) {
+            const uint2 entry = sh_vq[warp][e];
+            const uint4 pt = ldPoint(b.points + entry.x);
+            const Coords q = quantize(c, pt);
+            sampleUp<UNCACHED_GRID, true>(c, b, q, pt.w, entry.y & 0xffffffu, entry.y >> 24, 0u);
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    if (lane == 0) sh_vqCount[warp] = 0;
+    __syncwarp();
+}
+// queue this lane's point if `deferred` != ~0 (warp-collective; drains first when the queue would overflow)
+template <bool UNCACHED_GRID>
+__device__ __forceinline__ void voxelStagePush(const Ctx& c, const Batch& b, uint32_t item, uint32_t deferred) {
+    const uint32_t warp = threadIdx.x >> 5, lane = laneId();
+    const uint32_t mask = __ballot_sync(0xffffffffu, deferred != 0xffffffffu);
+    if (mask == 0) return;
+    if (sh_vqCount[warp] + __popc(mask) > VQ_CAP) voxelStageDrain<UNCACHED_GRID>(c, b);
+    const uint32_t base = sh_vqCount[warp];
+    if (deferred != 0xffffffffu) sh_vq[warp][base + __popc(mask & lanemaskLt())] = make_uint2(item, deferred);
+    __syncwarp();
+    if (lane == 0) sh_vqCount[warp] = base + __popc(mask);
+    __syncwarp();
+}
+
+template <bool SAMPLE, bool COUNT, bool UNCACHED_GRID, bool DEDUP, bool DEFER = false>
 __device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& cache, bool valid, uint4 pt, uint32_t node, uint32_t level,
-                                     uint32_t stopLevel, uint32_t* bloom, uint32_t& leafPacked, uint32_t& slot) {
+                                     uint32_t stopLevel, uint32_t* bloom, bool forceGlobal, uint32_t& leafPacked, uint32_t& slot, uint32_t& deferred) {
+    deferred = 0xffffffffu;
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = laneId();
     const uint32_t ltmask = lanemaskLt();
@@ -582,58 +698,26 @@ __device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& ca
         }
         if (SAMPLE) {
             // nodes with a grid on the path: the inner nodes, and the root even while it is a leaf (reset.cu:69)
-            uint32_t sNode = level == 0 ? node : parent;
-            uint32_t sLevel = level == 0 ? 0u : level - 1;
-            const bool exhaustive = !nested(q);          // far outside the box: probe every level like the reference does
-            if (exhaustive) atomicOr(&c.ctl()->errorFlags, ERR_FAR_POINT);
-            // atomicOr results are not needed to continue upwards (a speculative probe of the level above is always
-            // correct: every cell has exactly one winner), so up to 3 stay in flight per lane
-            uint32_t pending = 0;
-            uint32_t old0 = 0, old1 = 0, old2 = 0, key0 = 0, key1 = 0, key2 = 0, cel0 = 0, cel1 = 0, cel2 = 0;
-            auto settle = [&]() {
-                if (pending > 0 && (old0 & (1u << (cel0 & 31u))) == 0) recordVoxel(c, b, key0, cel0, pt.w);
-                if (pending > 1 && (old1 & (1u << (cel1 & 31u))) == 0) recordVoxel(c, b, key1, cel1, pt.w);
-                if (pending > 2 && (old2 & (1u << (cel2 & 31u))) == 0) recordVoxel(c, b, key2, cel2, pt.w);
-                pending = 0;
-            };
-            const uint64_t* gridPtr = c.gridPtr();
-            for (;;) {
-                uint64_t g = gridPtr[sNode];
-                bool goUp = exhaustive;
-                if (g != 0) {
-                    uint32_t cell = cellAt(q, sLevel);
-                    uint32_t* word = reinterpret_cast<uint32_t*>(g) + (cell >> 5);
-                    uint32_t bit = 1u << (cell & 31u);
-                    // non-atomic pre-test (voxels.cu:93-94): bits are only ever set while a grid is live, so a set bit seen
-                    // through the (non-coherent) L1 is final. The root's grid is cleared in place when the root splits
-                    // (voxels.cu:370-382): the one pass that follows such a clear reads through L2 instead.
-                    uint32_t seen = UNCACHED_GRID ? ldcg(word) : *word;
-                    if ((seen & bit) == 0) {
-                        // first-visit passes: neighbouring points of a scan hit the same cell, so one atomic per distinct cell
-                        // among the converged lanes. Re-walk passes fill freshly cleared grids, where the cells of a warp's
-                        // items are mostly distinct and the match would cost more than the few atomics it saves.
-                        bool mine = true;
-                        if (DEDUP) {
-                            uint32_t active = __activemask();
-                            uint32_t peers = __match_any_sync(active, (uint64_t)(uintptr_t)word * 32ull + (cell & 31u));
-                            mine = lane == (uint32_t)__ffs(peers) - 1u;
-                        }
-                        if (mine) {
-                            if (pending == 3) settle();
-                            uint32_t old = atomicOr(word, bit);
-                            if (pending == 0) { old0 = old; key0 = sNode; cel0 = cell; }
-                            else if (pending == 1) { old1 = old; key1 = sNode; cel1 = cell; }
-                            else { old2 = old; key2 = sNode; cel2 = cell; }
-                            pending++;
-                            goUp = true;
-                        }
+            const uint32_t sNode = level == 0 ? node : parent;
+            const uint32_t sLevel = level == 0 ? 0u : level - 1;
+            if (DEFER) {
+                // first-visit pass over the block's run: ONE probe of the deepest grid here; whatever needs more (a clear bit: an
+                // atomic, a voxel record, the levels above) is queued for the warp's voxel stage, where the few such points of a
+                // run are handled with all lanes busy instead of one or two lanes holding up the other thirty every time
+                bool need = !nested(q);
+                if (!need) {
+                    const uint64_t g = c.gridPtr()[sNode];
+                    if (g != 0) {
+                        const uint32_t cell = cellAt(q, sLevel);
+                        const uint32_t* word = reinterpret_cast<const uint32_t*>(g) + (cell >> 5);
+                        const uint32_t seen = UNCACHED_GRID ? ldcg(word) : *word;
+                        need = (seen & (1u << (cell & 31u))) == 0;
                     }
                 }
-                if (!goUp || sLevel <= stopLevel) break;
-                sNode = c.parentOf()[sNode];
-                sLevel--;
+                deferred = need ? (sNode | (sLevel << 24)) : 0xffffffffu;
+            } else {
+                sampleUp<UNCACHED_GRID, DEDUP>(c, b, q, pt.w, sNode, sLevel, stopLevel);
             }
-            settle();
         }
     }
     __syncwarp();
@@ -647,9 +731,9 @@ __device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& ca
             uint32_t cnt = __popc(peers);
             uint32_t r = 0;
             if (lane == leader) {
-                uint32_t t = tabInsert(sh_leafKey, node);
+                uint32_t t = forceGlobal ? VOXTAB_EMPTY : tabInsert(sh_leafKey, node);
                 if (t != VOXTAB_EMPTY) { r = atomicAdd(&sh_leafCount[t], cnt) | PROVISIONAL | (t << 24); sh_leafLevel[t] = (uint8_t)level; }   // block-local rank
-                else                   r = countGlobal(c, b, node, level, cnt);                // table full: final slot at once
+                else                 { r = countGlobal(c, b, node, level, cnt); sh_blockLegacy = 1; }   // table (or list) full: final slot at once
                 if (bloom) bloomAdd(bloom, node);
             }
             r = __shfl_sync(peers, r, leader);
@@ -726,6 +810,63 @@ __device__ __forceinline__ void markAffectedRun(const Ctx& c, const Batch& b, ui
     if (threadIdx.x == 0) c.runFlag()[blockIdx.x] = flag;
 }
 
+// the explicit list lives in the two TMA stages (16 KB): item index and slot word of up to LIST_CAP items
+__device__ __forceinline__ uint32_t* listItem() { return reinterpret_cast<uint32_t*>(&sh_tile[0][0]); }
+__device__ __forceinline__ uint32_t* listSlot() { return reinterpret_cast<uint32_t*>(&sh_tile[0][0]) + LIST_CAP; }
+static_assert(sizeof(sh_tile) >= LIST_CAP * 8, "the explicit item list must fit the TMA stages");
+
+// Split phase, every block: name the items that move in this round (see sh_listCount above) in the global worklist.
+__device__ void buildWorklist(const Ctx& c, const Batch& b, uint32_t spillBegin, uint32_t spillEnd, uint32_t round) {
+    Ctl::Worklist* w = &c.ctl()->wl[b.index % 3u];
+    const uint32_t numSplit = spillEnd - spillBegin;
+    if (numSplit > 64u || sh_blockLegacy != 0) {                       // block-uniform
+        if (threadIdx.x == 0) atomicExch(&w->legacy, 1u);
+        return;
+    }
+    uint32_t blockFirst, blockEnd;
+    blockRun(b.size, blockFirst, blockEnd);
+    const uint32_t mode = sh_listMode;
+    const uint32_t total = mode == 0 ? blockEnd - blockFirst : min(sh_listCount, LIST_CAP);
+    if (threadIdx.x < numSplit) sh_splitNodes[threadIdx.x] = c.spill()[spillBegin + threadIdx.x].node;
+    if (threadIdx.x == 0) { sh_wlCount = 0; sh_wlFill = 0; }
+    __syncthreads();
+    if (threadIdx.x < VOXTAB_SIZE) {
+        const uint32_t key = sh_leafKey[threadIdx.x];
+        uint32_t f = 0;
+        if (key != VOXTAB_EMPTY) for (uint32_t j = 0; j < numSplit; j++) f |= key == sh_splitNodes[j] ? 1u : 0u;
+        sh_entrySplit[threadIdx.x] = (uint8_t)f;
+    }
+    __syncthreads();
+    const uint32_t* words = mode == 0 ? sh_runSlot : listSlot();
+    auto movedAt = [&](uint32_t k) { const uint32_t word = words[k]; return (word & PROVISIONAL) != 0 && sh_entrySplit[(word >> 24) & (VOXTAB_SIZE - 1)] != 0; };
+    uint32_t cnt = 0;
+    for (uint32_t k = threadIdx.x; k < total; k += blockDim.x) cnt += movedAt(k) ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (laneId() == 0 && cnt) atomicAdd(&sh_wlCount, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t n = sh_wlCount;
+        uint32_t base = n ? atomicAdd(&w->cursor[round & 1u], n) : 0u;
+        if ((uint64_t)base + n > scratch::WL_CAP) { atomicExch(&w->legacy, 1u); base = 0xffffffffu; }
+        sh_wlBase = base;
+    }
+    __syncthreads();
+    const uint32_t base = sh_wlBase;
+    if (base == 0xffffffffu || sh_wlCount == 0) return;
+    uint32_t* wl = c.worklist();
+    const uint32_t* items = listItem();
+    for (uint32_t k0 = 0; k0 < total; k0 += blockDim.x) {                // block-uniform trip count
+        const uint32_t k = k0 + threadIdx.x;
+        const bool m = k < total && movedAt(k);
+        const uint32_t mask = __ballot_sync(0xffffffffu, m);
+        if (mask == 0) continue;
+        uint32_t off = 0;
+        if (laneId() == 0) off = atomicAdd(&sh_wlFill, (uint32_t)__popc(mask));
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (m) wl[base + off + __popc(mask & lanemaskLt())] = mode == 0 ? blockFirst + k : items[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // one pass over the batch points (ring slot) followed by the spilled points of this batch
 //   FRESH  : items start at the root (first visit); otherwise only items whose cached leaf has
@@ -733,7 +874,7 @@ __device__ __forceinline__ void markAffectedRun(const Ctx& c, const Batch& b, ui
 //   the table flush (leaf counters, voxel counters) is left to the caller: passFlush()
 // ------------------------------------------------------------------------------------------
 template <bool SAMPLE, bool COUNT, bool FRESH, bool UNCACHED_GRID>
-__device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t numSpilled, uint32_t spilledBefore, uint32_t spillBegin, uint32_t spillEnd) {
+__device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t numSpilled, uint32_t spilledBefore, uint32_t round) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t* leafOf = c.leafOf(b.parity);
@@ -745,6 +886,7 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
 
     if (COUNT && threadIdx.x < VOXTAB_SIZE) { sh_leafKey[threadIdx.x] = VOXTAB_EMPTY; sh_leafCount[threadIdx.x] = 0; }
     if (FRESH && COUNT && threadIdx.x < BLOOM_WORDS) sh_runBloom[threadIdx.x] = 0;
+    if (FRESH && COUNT && threadIdx.x == 0) { sh_listMode = 0; sh_listCount = 0; sh_blockLegacy = (blockEnd - blockFirst) > RUNSLOT_CAP ? 1u : 0u; }
     if (SAMPLE) voxelPassBegin(c, b, FRESH);
     __syncthreads();
 
@@ -753,6 +895,8 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
         const uint32_t numTiles = (runLen + TILE_POINTS - 1) / TILE_POINTS;
         uint32_t ph0 = sh_tilePhase[0], ph1 = sh_tilePhase[1];
         __syncthreads();
+        // (the stages held the explicit item list of the previous batch's rounds: order those generic-proxy writes before the bulk copies)
+        if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (threadIdx.x == 0 && numTiles > 0) tileLoad(0, b.points + blockFirst, min(TILE_POINTS, runLen));
         for (uint32_t t = 0; t < numTiles; t++) {
             const uint32_t tileFirst = blockFirst + t * TILE_POINTS;
@@ -766,7 +910,9 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
                 const bool valid = i < blockEnd;
                 uint4 pt = valid ? sh_tile[t & 1][idx] : make_uint4(0, 0, 0, 0);
                 uint32_t lp = 0, slot = 0;
-                walk<SAMPLE, COUNT, UNCACHED_GRID, true>(c, b, cache, valid, pt, 0, 0, 0, COUNT ? sh_runBloom : nullptr, lp, slot);
+                uint32_t deferred;
+                walk<SAMPLE, COUNT, UNCACHED_GRID, true, true>(c, b, cache, valid, pt, 0, 0, 0, COUNT ? sh_runBloom : nullptr, false, lp, slot, deferred);
+                if (SAMPLE) voxelStagePush<UNCACHED_GRID>(c, b, i, deferred);
                 if (valid && COUNT) {
                     leafOf[i] = lp;
                     if (runLen <= RUNSLOT_CAP) sh_runSlot[i - blockFirst] = slot; else slotOf[i] = slot;
@@ -774,54 +920,103 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
             }
             __syncthreads();
         }
+        if (SAMPLE) voxelStageDrain<UNCACHED_GRID>(c, b);
         if (threadIdx.x == 0) { sh_tilePhase[0] = ph0; sh_tilePhase[1] = ph1; }
         if (COUNT && threadIdx.x < BLOOM_WORDS) c.runBloom()[blockIdx.x * BLOOM_WORDS + threadIdx.x] = sh_runBloom[threadIdx.x];
     } else {
-        // ---- the runs that can hold an item whose leaf was split in the round that just ended: every block published
-        // its own run's verdict before the barrier (markAffectedRun), so all blocks build the same list
-        if (gridDim.x <= AFFECTED_CAP) {
-            const uint32_t* flags = c.runFlag();
-            uint32_t numAffected = 0;
-            for (uint32_t g0 = 0; g0 < gridDim.x; g0 += blockDim.x) {          // block-uniform trip count
-                const uint32_t g = g0 + threadIdx.x;
-                const uint32_t flag = g < gridDim.x ? ldcg(&flags[g]) : 0u;
-                uint32_t total = 0;
-                const uint32_t off = blockExclusiveScan(flag, total);
-                if (flag) sh_affected[numAffected + off] = g;
-                numAffected += total;
-            }
-            if (threadIdx.x == 0) sh_numAffected = numAffected;
+        Ctl::Worklist* w = &c.ctl()->wl[b.index % 3u];
+        if (ldcg(&w->legacy) == 0) {
+            // ---- the items the split phase named (buildWorklist), then the points spilled in this round ---------------------
+            const uint32_t numListed = min(ldcg(&w->cursor[round & 1u]), (uint32_t)scratch::WL_CAP);
+            const uint32_t total = numListed + (numSpilled - spilledBefore);
+            const uint32_t perRun = ((b.size + gridDim.x - 1) / gridDim.x + 31u) & ~31u;
+            const uint32_t* wl = c.worklist();
+            if (threadIdx.x == 0) { sh_listCount = 0; sh_listMode = 1; }          // the list of the previous round has been read (split phase)
             __syncthreads();
-        }
-        // ---- the affected runs and the spilled points as one item space --------------------------------------------
-        const Rewalk rw = rewalkSlice(b.size, numSpilled, spilledBefore);
-#if SIMLOD_TIMERS >= 2
-        uint64_t tList = 0;
-        if (blockIdx.x == 0 && threadIdx.x == 0) { tList = globaltimer(); c.ctl()->subNanos[14] += rw.total; c.ctl()->subNanos[15] += rw.runItems; }
-#endif
-        for (uint32_t base = rewalkFirstGranule(); base < rw.total; base += rewalkGranuleStride()) {
-            const uint32_t u = base + laneId();
-            uint32_t run = 0xffffffffu, i = 0xffffffffu, node = 0, level = 0;
-            bool valid = u < rw.total;
-            const bool spilledItem = valid && u >= rw.runItems;
-            if (valid) { i = rewalkItem(rw, u, run); valid = spilledItem || i < b.size; }      // (the last run is padded)
-            uint4 pt = make_uint4(0, 0, 0, 0);
-            if (spilledItem) pt = *reinterpret_cast<const uint4*>(c.spilled() + (i - scratch::MAX_BATCH));     // independent of the leaf look-up
-            if (valid) {
-                uint32_t lp = leafOf[i];
-                node = lp & 0xffffffu; level = lp >> 24;
-                // points spilled in the round that just ended sit in a leaf that was split in it: no need to look
-                if (!(spilledItem && i - scratch::MAX_BATCH >= rw.spilledBefore)) valid = c.firstChild()[node] != 0 && level < SIMLOD_MAX_DEPTH;
+            for (uint32_t base = rewalkFirstGranule(); base < total; base += rewalkGranuleStride()) {
+                const uint32_t u = base + laneId();
+                bool valid = u < total;
+                const uint32_t i = !valid ? 0u : (u < numListed ? wl[u] : (uint32_t)scratch::MAX_BATCH + spilledBefore + (u - numListed));
+                const bool spilledItem = valid && i >= scratch::MAX_BATCH;
+                uint4 pt = make_uint4(0, 0, 0, 0);
+                uint32_t node = 0, level = 0;
+                if (valid) {
+                    pt = spilledItem ? *reinterpret_cast<const uint4*>(c.spilled() + (i - scratch::MAX_BATCH)) : ldPoint(b.points + i);
+                    const uint32_t lp = leafOf[i];
+                    node = lp & 0xffffffu; level = lp >> 24;
+                    valid = level < SIMLOD_MAX_DEPTH;                    // a level-20 node is the leaf even after it "split" (voxels.cu:169)
+                }
+                // room in the block's item list for the warp's items; without it they are counted globally (final slots at once)
+                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                if (vmask == 0) continue;
+                uint32_t k0 = 0;
+                if (laneId() == 0) k0 = atomicAdd(&sh_listCount, (uint32_t)__popc(vmask));
+                k0 = __shfl_sync(0xffffffffu, k0, 0);
+                const bool forceGlobal = k0 + __popc(vmask) > LIST_CAP;
+                const uint32_t myk = k0 + __popc(vmask & lanemaskLt());
+                uint32_t lp = 0, slot = 0;
+                uint32_t deferredUnused;
+                walk<SAMPLE, COUNT, UNCACHED_GRID, false>(c, b, cache, valid, pt, node, level, level,
+                                                         valid && !spilledItem ? c.runBloom() + (i / perRun) * BLOOM_WORDS : nullptr, forceGlobal, lp, slot, deferredUnused);
+                if (valid && COUNT) {
+                    leafOf[i] = lp;
+                    if (!forceGlobal) { listItem()[myk] = i; listSlot()[myk] = slot; }           // the final slot is written by passFlush
+                    else {
+                        slotOf[i] = slot;
+                        if (myk < LIST_CAP) { listItem()[myk] = 0xffffffffu; listSlot()[myk] = 0; }       // reserved but unused: the warp's items straddled the end of the list
+                    }
+                }
             }
-            if (!__any_sync(0xffffffffu, valid)) continue;
-            if (valid && !spilledItem) pt = ldPoint(b.points + i);
-            uint32_t lp = 0, slot = 0;
-            walk<SAMPLE, COUNT, UNCACHED_GRID, false>(c, b, cache, valid, pt, node, level, level, run != 0xffffffffu ? c.runBloom() + run * BLOOM_WORDS : nullptr, lp, slot);
-            if (valid && COUNT) { leafOf[i] = lp; slotOf[i] = slot; }
+        } else {
+            if (threadIdx.x == 0) sh_blockLegacy = 1;
+            // ---- the runs that can hold an item whose leaf was split in the round that just ended: every block published
+            // its own run's verdict before the barrier (markAffectedRun), so all blocks build the same list
+            if (gridDim.x <= AFFECTED_CAP) {
+                const uint32_t* flags = c.runFlag();
+                uint32_t numAffected = 0;
+                for (uint32_t g0 = 0; g0 < gridDim.x; g0 += blockDim.x) {          // block-uniform trip count
+                    const uint32_t g = g0 + threadIdx.x;
+                    const uint32_t flag = g < gridDim.x ? ldcg(&flags[g]) : 0u;
+                    uint32_t total = 0;
+                    const uint32_t off = blockExclusiveScan(flag, total);
+                    if (flag) sh_affected[numAffected + off] = g;
+                    numAffected += total;
+                }
+                if (threadIdx.x == 0) sh_numAffected = numAffected;
+                __syncthreads();
+            }
+            // ---- the affected runs and the spilled points as one item space --------------------------------------------
+            const Rewalk rw = rewalkSlice(b.size, numSpilled, spilledBefore);
+    #if SIMLOD_TIMERS >= 2
+            uint64_t tList = 0;
+            if (blockIdx.x == 0 && threadIdx.x == 0) { tList = globaltimer(); c.ctl()->subNanos[14] += rw.total; c.ctl()->subNanos[15] += rw.runItems; }
+    #endif
+            for (uint32_t base = rewalkFirstGranule(); base < rw.total; base += rewalkGranuleStride()) {
+                const uint32_t u = base + laneId();
+                uint32_t run = 0xffffffffu, i = 0xffffffffu, node = 0, level = 0;
+                bool valid = u < rw.total;
+                const bool spilledItem = valid && u >= rw.runItems;
+                if (valid) { i = rewalkItem(rw, u, run); valid = spilledItem || i < b.size; }      // (the last run is padded)
+                uint4 pt = make_uint4(0, 0, 0, 0);
+                if (spilledItem) pt = *reinterpret_cast<const uint4*>(c.spilled() + (i - scratch::MAX_BATCH));     // independent of the leaf look-up
+                if (valid) {
+                    uint32_t lp = leafOf[i];
+                    node = lp & 0xffffffu; level = lp >> 24;
+                    // points spilled in the round that just ended sit in a leaf that was split in it: no need to look
+                    if (!(spilledItem && i - scratch::MAX_BATCH >= rw.spilledBefore)) valid = c.firstChild()[node] != 0 && level < SIMLOD_MAX_DEPTH;
+                }
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                if (valid && !spilledItem) pt = ldPoint(b.points + i);
+                uint32_t lp = 0, slot = 0;
+                uint32_t deferredUnused;
+                walk<SAMPLE, COUNT, UNCACHED_GRID, false>(c, b, cache, valid, pt, node, level, level, run != 0xffffffffu ? c.runBloom() + run * BLOOM_WORDS : nullptr, false, lp, slot, deferredUnused);
+                if (valid && COUNT) { leafOf[i] = lp; slotOf[i] = slot; }
+            }
+    #if SIMLOD_TIMERS >= 2
+            if (blockIdx.x == 0 && threadIdx.x == 0) c.ctl()->subNanos[13] += globaltimer() - tList;      // warp 0's loop alone
+    #endif
+
         }
-#if SIMLOD_TIMERS >= 2
-        if (blockIdx.x == 0 && threadIdx.x == 0) c.ctl()->subNanos[13] += globaltimer() - tList;      // warp 0's loop alone
-#endif
     }
     if (FRESH) {
         // spilled points of this batch, from the root (sampling-only pass after a root split)
@@ -831,7 +1026,8 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
             uint4 pt = make_uint4(0, 0, 0, 0);
             if (valid) pt = *reinterpret_cast<const uint4*>(c.spilled() + j);
             uint32_t lp = 0, slot = 0;
-            walk<SAMPLE, COUNT, UNCACHED_GRID, true>(c, b, cache, valid, pt, 0, 0, 0, nullptr, lp, slot);
+            uint32_t deferredUnused;
+            walk<SAMPLE, COUNT, UNCACHED_GRID, true>(c, b, cache, valid, pt, 0, 0, 0, nullptr, false, lp, slot, deferredUnused);
         }
     }
     __syncthreads();
@@ -841,6 +1037,7 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
 // side), then block-local ranks -> slots. Must run after waitAllocBlock() when an allocation is in flight.
 template <bool SAMPLE, bool COUNT, bool FRESH>
 __device__ __forceinline__ void passFlush(const Ctx& c, const Batch& b, uint32_t numSpilled, uint32_t spilledBefore) {
+    // (non-FRESH passes: sh_listMode == 1 and no legacy flag means passItems visited the worklist and kept its items in the list)
     if (COUNT && threadIdx.x < VOXTAB_SIZE) {
         uint32_t leaf = sh_leafKey[threadIdx.x], cnt = sh_leafCount[threadIdx.x];
         if (leaf != VOXTAB_EMPTY && cnt > 0) sh_leafBase[threadIdx.x] = countGlobal(c, b, leaf, sh_leafLevel[threadIdx.x], cnt);
@@ -859,7 +1056,12 @@ __device__ __forceinline__ void passFlush(const Ctx& c, const Batch& b, uint32_t
             } else {
                 for (uint32_t i = blockFirst + threadIdx.x; i < blockEnd; i += blockDim.x) { uint32_t sl = slotOf[i]; if (sl & PROVISIONAL) slotOf[i] = finalSlot(sl); }
             }
-        } else {                                                          // the items this block visited in passItems
+        } else if (ldcg(&c.ctl()->wl[b.index % 3u].legacy) == 0) {        // the items this block visited in passItems: its list
+            const uint32_t n = min(sh_listCount, LIST_CAP);
+            const uint32_t* li = listItem();
+            const uint32_t* ls = listSlot();
+            for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) if (li[k] != 0xffffffffu) slotOf[li[k]] = finalSlot(ls[k]);
+        } else {                                                          // ... in the affected runs (legacy rounds)
             const Rewalk rw = rewalkSlice(b.size, numSpilled, spilledBefore);
             for (uint32_t base = rewalkFirstGranule(); base < rw.total; base += rewalkGranuleStride()) {
                 const uint32_t u = base + laneId();
@@ -1216,6 +1418,7 @@ __device__ __noinline__ void insertAll(const Ctx c, const Batch b, uint32_t numS
     __syncthreads();
 }
 
+__device__ __forceinline__ void clearWorklist(Ctl::Worklist* w) { w->cursor[0] = 0; w->cursor[1] = 0; w->legacy = 0; }
 __device__ __forceinline__ void clearBatchCounters(BatchCounters* b) {
     b->numSpillTotal = 0; b->numSpilled = 0; b->numBacklog = 0; b->numDirtyLeaves = 0; b->numDirtyVox = 0; b->dirCursor = 0; b->voxelsCreated = 0; b->insertCursor = 0;
 }
@@ -1277,7 +1480,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         ctl->elapsedNanos = 0;
         ctl->memUsed = c.heap()->offset;
         ctl->allocDone = 0;
-        for (int i = 0; i < 3; i++) clearBatchCounters(&ctl->batch[i]);
+        for (int i = 0; i < 3; i++) { clearBatchCounters(&ctl->batch[i]); clearWorklist(&ctl->wl[i]); }
         for (int i = 0; i < 8; i++) ctl->statCounters[i] = 0;
         if (stats->batchletIndex == 0) {       // fresh after the reset kernel: the tree is the root alone
             ctl->errorFlags = 0;
@@ -1294,6 +1497,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         }
     }
     if (threadIdx.x == 0) { sh_allocTarget = 0; sh_allocSeen = 0; sh_numAffected = 0; }
+    if (threadIdx.x < 8) sh_vqCount[threadIdx.x] = 0;
     tileBarInit();
     grid.sync();
     uint64_t tPhase = tStart;
@@ -1350,9 +1554,9 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             if (threadIdx.x == 0) { __threadfence(); atomicAdd(&ctl->allocDone, 1u); }
         }
         SUB_DONE(0);
-        if (first) clearBatchCounters(&ctl->batch[(batchIndex + 1) % 3u]);      // idle set: last used by batch b-2, next by b+1
-        if (deferSampling) passItems<false, true, true, false>(c, b, 0, 0, 0, 0);
-        else               passItems<true, true, true, false>(c, b, 0, 0, 0, 0);
+        if (first) { clearBatchCounters(&ctl->batch[(batchIndex + 1) % 3u]); clearWorklist(&ctl->wl[(batchIndex + 1) % 3u]); }      // idle set: last used by batch b-2, next by b+1
+        if (deferSampling) passItems<false, true, true, false>(c, b, 0, 0, 0);
+        else               passItems<true, true, true, false>(c, b, 0, 0, 0);
         SUB_DONE(1);
         waitAllocBlock(c);
         SUB_DONE(2);
@@ -1377,6 +1581,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             const uint32_t spillEnd = min(ldv(&b.bc->numSpillTotal), (uint32_t)scratch::SPILLNODE_CAP);
             if (spillEnd == spillBegin) break;
             markAffectedRun(c, b, spillBegin, spillEnd);
+            buildWorklist(c, b, spillBegin, spillEnd, (uint32_t)round);
             splitRound(c, b, spillBegin, spillEnd);
             SUB_DONE(6);
             grid.sync();
@@ -1386,8 +1591,9 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             if (first) ctl->phaseNanos[6] += 1;
 #endif
             const uint32_t numSpilled = min(ldv(&b.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
-            if (deferSampling) passItems<false, true, false, false>(c, b, numSpilled, spilledBefore, spillBegin, spillEnd);
-            else               passItems<true, true, false, false>(c, b, numSpilled, spilledBefore, spillBegin, spillEnd);
+            if (first) ctl->wl[b.index % 3u].cursor[(round + 1) & 1] = 0;       // the list of the previous round has been consumed
+            if (deferSampling) passItems<false, true, false, false>(c, b, numSpilled, spilledBefore, (uint32_t)round);
+            else               passItems<true, true, false, false>(c, b, numSpilled, spilledBefore, (uint32_t)round);
             SUB_DONE(8);
             if (deferSampling) passFlush<false, true, false>(c, b, numSpilled, spilledBefore);
             else               passFlush<true, true, false>(c, b, numSpilled, spilledBefore);
@@ -1402,7 +1608,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         if (deferSampling) {
             // the root was a leaf when the batch started: sample along the final paths, as the reference does after
             // expand() (voxels.cu:738-742). The root's grid may just have been cleared in place: probe it through L2.
-            passItems<true, false, true, true>(c, b, numSpilled, 0, 0, 0);
+            passItems<true, false, true, true>(c, b, numSpilled, 0, 0);
             passFlush<true, false, true>(c, b, numSpilled, 0);
             grid.sync();
             PHASE_DONE(3);

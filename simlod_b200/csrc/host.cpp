@@ -125,6 +125,12 @@ struct SimlodContext {
     CUsurfObject surface = 0;
     SimlodStats* hStats = nullptr;     // pinned
     SimlodStats* hStatsRing = nullptr; // pinned, one snapshot per launch in flight (8)
+    struct PublishMirror { uint32_t sizes[RING_SLOTS]; uint32_t count; uint32_t pad[13]; };   // 256 B
+    PublishMirror* hPublish = nullptr; // pinned, 16 snapshots of {batchSizes[50], numBatchesUploaded} for grouped publication
+    CUevent evPublish[16] = {};        // the copies out of mirror i have completed
+    uint32_t hostSizes[RING_SLOTS] = {};   // what batchSizes[] holds on the device once everything enqueued has run
+    uint32_t unpublished = 0;          // batches copied into the ring but not yet published (sizes + counter)
+    uint32_t publishIndex = 0;
     CUevent evStatsDone[8] = {};       // the snapshot behind launch slot k has landed
     Program programs[3];
     CUmodule utilModule = nullptr, lasModule = nullptr, partitionModule = nullptr, genModule = nullptr;
@@ -262,8 +268,29 @@ int checkOverflow(SimlodContext* ctx) {
     return SIMLOD_OK;
 }
 
+// Publication of a GROUP of batches whose points have been copied into their ring slots (uploadCommon with publish =
+// false): ONE copy of the 50 slot sizes and ONE of the counter, out of a pinned snapshot, instead of two small
+// operations per batch. With a device-resident source the 40 memsets behind 20 batch copies were what the next launch
+// waited for: 0.3 ms of idle GPU between launches (tools/launch_gaps.py), 10 % of the whole insertion.
+int publishPending(SimlodContext* ctx) {
+    if (ctx->unpublished == 0) return SIMLOD_OK;
+    const uint32_t m = ctx->publishIndex++ % 16u;
+    if (ctx->publishIndex > 16u) CU(D(cuEventSynchronize)(ctx->evPublish[m]));       // the snapshot's previous copies have left it
+    SimlodContext::PublishMirror* pm = &ctx->hPublish[m];
+    memcpy(pm->sizes, ctx->hostSizes, sizeof(pm->sizes));
+    pm->count = ctx->uploaded;
+    CU(D(cuMemcpyHtoDAsync)(ctx->batchSizes, pm->sizes, sizeof(pm->sizes), ctx->streamUpload));        // main.cpp:1047-1050: sizes first,
+    CU(D(cuMemcpyHtoDAsync)(ctx->numBatchesUploaded, &pm->count, 4, ctx->streamUpload));                // then the global counter
+    CU(D(cuEventRecord)(ctx->evPublish[m], ctx->streamUpload));
+    for (uint32_t k = ctx->unpublished; k > 0; k--) CU(D(cuEventRecord)(ctx->evSlot[(ctx->uploaded - k) % RING_SLOTS], ctx->streamUpload));
+    ctx->unpublished = 0;
+    return SIMLOD_OK;
+}
+
 int publishBatch(SimlodContext* ctx, uint32_t slot, uint32_t count) {
     // main.cpp:1047-1050: the size of the slot first, then the global counter, in stream order after the copy
+    int prc = publishPending(ctx); if (prc) return prc;
+    ctx->hostSizes[slot] = count;
     CU(D(cuMemsetD32Async)(ctx->batchSizes + 4ull * slot, count, 1, ctx->streamUpload));
     ctx->uploaded++;
     CU(D(cuMemsetD32Async)(ctx->numBatchesUploaded, ctx->uploaded, 1, ctx->streamUpload));
@@ -272,10 +299,10 @@ int publishBatch(SimlodContext* ctx, uint32_t slot, uint32_t count) {
 }
 
 // enqueue one kernel_construct launch between the event pair `slot` without waiting for it
-int enqueueConstruct(SimlodContext* ctx, int slot) {
+int enqueueConstruct(SimlodContext* ctx, int slot, CUdeviceptr pointsBase = 0) {
     SimlodUniforms u = ctx->uniforms;
     u.frameCounter = ctx->frameCounter;
-    CUdeviceptr ring = ctx->buf.ring, momentary = ctx->buf.momentary, persistent = ctx->buf.persistent, nodes = ctx->buf.nodes,
+    CUdeviceptr ring = pointsBase ? pointsBase : ctx->buf.ring, momentary = ctx->buf.momentary, persistent = ctx->buf.persistent, nodes = ctx->buf.nodes,
                 stats = ctx->buf.stats, frameStart = ctx->frameStart, cudaprint = ctx->cudaprint,
                 nbu = ctx->numBatchesUploaded, bs = ctx->batchSizes;
     void* args[] = {&u, &ring, &momentary, &persistent, &nodes, &stats, &frameStart, &cudaprint, &nbu, &bs};   // main.cpp:374-382
@@ -367,6 +394,8 @@ static int createResources(SimlodContext* ctx, const SimlodConfig* config) {
     CU(D(cuMemAlloc)(&ctx->flushBuf, L2_FLUSH_BYTES));
     CU(D(cuMemHostAlloc)((void**)&ctx->hStats, sizeof(SimlodStats), 0));
     CU(D(cuMemHostAlloc)((void**)&ctx->hStatsRing, 8 * sizeof(SimlodStats), 0));
+    CU(D(cuMemHostAlloc)((void**)&ctx->hPublish, 16 * sizeof(SimlodContext::PublishMirror), 0));
+    for (int i = 0; i < 16; i++) CU(D(cuEventCreate)(&ctx->evPublish[i], CU_EVENT_DISABLE_TIMING));
     for (int i = 0; i < 8; i++) CU(D(cuEventCreate)(&ctx->evStatsDone[i], CU_EVENT_DISABLE_TIMING));
     ALLOC(b.ring, b.ring_bytes);
     if (config->persistent_bytes) {
@@ -437,6 +466,8 @@ void simlod_destroy(SimlodContext* ctx) {
         for (CUdeviceptr p : ptrs) if (p) D(cuMemFree)(p);
         if (ctx->hStats) D(cuMemFreeHost)(ctx->hStats);
         if (ctx->hStatsRing) D(cuMemFreeHost)(ctx->hStatsRing);
+        if (ctx->hPublish) D(cuMemFreeHost)(ctx->hPublish);
+        for (int i = 0; i < 16; i++) if (ctx->evPublish[i]) D(cuEventDestroy)(ctx->evPublish[i]);
         for (int i = 0; i < 8; i++) if (ctx->evStatsDone[i]) D(cuEventDestroy)(ctx->evStatsDone[i]);
         for (int p = 0; p < 3; p++) if (ctx->programs[p].module) D(cuModuleUnload)(ctx->programs[p].module);
         if (ctx->utilModule) D(cuModuleUnload)(ctx->utilModule);
@@ -518,10 +549,12 @@ int simlod_reset_with_grid(SimlodContext* ctx, uint32_t blocks, uint32_t threads
     CU(D(cuStreamSynchronize)(ctx->streamMain));
     ctx->uploaded = 0;
     ctx->processed = 0;
+    ctx->unpublished = 0;
+    memset(ctx->hostSizes, 0, sizeof(ctx->hostSizes));
     return SIMLOD_OK;
 }
 
-static int uploadCommon(SimlodContext* ctx, const void* host, CUdeviceptr dev, uint32_t count) {
+static int uploadCommon(SimlodContext* ctx, const void* host, CUdeviceptr dev, uint32_t count, bool publish = true) {
     int rc = setCurrent(ctx); if (rc) return rc;
     if (count > SLOT_POINTS) return fail(SIMLOD_ERR_INVALID, "batch of %u points exceeds the ring slot size of %llu", count, (unsigned long long)SLOT_POINTS);
     if (ctx->uploaded - ctx->processed >= RING_SLOTS) {
@@ -534,7 +567,11 @@ static int uploadCommon(SimlodContext* ctx, const void* host, CUdeviceptr dev, u
         if (host) CU(D(cuMemcpyHtoDAsync)(dst, host, (size_t)count * sizeof(SimlodPoint), ctx->streamUpload));   // main.cpp:1040
         else      CU(D(cuMemcpyDtoDAsync)(dst, dev, (size_t)count * sizeof(SimlodPoint), ctx->streamUpload));
     }
-    return publishBatch(ctx, slot, count);
+    if (publish) return publishBatch(ctx, slot, count);
+    ctx->hostSizes[slot] = count;           // published with its group: publishPending()
+    ctx->uploaded++;
+    ctx->unpublished++;
+    return SIMLOD_OK;
 }
 
 int simlod_upload_batch(SimlodContext* ctx, const SimlodPoint* host_points, uint32_t count) {
@@ -649,11 +686,13 @@ static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr
         while (next < numBatches && ctx->uploaded - ctx->processed < RING_SLOTS) {
             uint64_t first = next * SLOT_POINTS;
             uint32_t n = (uint32_t)std::min<uint64_t>(SLOT_POINTS, count - first);
-            rc = uploadCommon(ctx, host ? host + first : nullptr, dev ? dev + first * sizeof(SimlodPoint) : 0, n);
+            rc = uploadCommon(ctx, host ? host + first : nullptr, dev ? dev + first * sizeof(SimlodPoint) : 0, n, false);
             if (rc) return rc;
             next++;
             progress = true;
+            if (host && ctx->unpublished >= gate) { rc = publishPending(ctx); if (rc) return rc; }      // a host source trickles in at PCIe speed: publish as it goes
         }
+        rc = publishPending(ctx); if (rc) return rc;
         while (numInFlight < 8 && ctx->uploaded > covered && (ctx->uploaded - covered >= gate || next == numBatches)) {
             const uint32_t take = std::min<uint32_t>(20u, ctx->uploaded - covered);
             CU(D(cuStreamWaitEvent)(ctx->streamMain, ctx->evSlot[(covered + take - 1u) % RING_SLOTS], 0));
@@ -685,13 +724,88 @@ static int insertCommon(SimlodContext* ctx, const SimlodPoint* host, CUdeviceptr
     return SIMLOD_OK;
 }
 
+// Device-resident source: the point set already IS a sequence of 1 000 000-point batches in HBM, so copying it into the
+// ring would only move 16 B/point a second time — and those device-to-device copies cannot run under the persistent
+// cooperative kernel (measured: every launch waited 0.24 ms for the 20 copies behind it, tools/launch_gaps.py).
+// kernel_construct addresses batch g as points + (g % 50) * 1 000 000 (voxels.cu:886-889); within one window of 50
+// consecutive batches that is a linear map of g, so the launches of a window get a `points` argument that makes slot
+// g % 50 land on batch g of the caller's buffer. The ring protocol is unchanged from the kernel's side (sizes and counter are
+// published per window, the next window only after the device has consumed the current one); only the bytes do not move.
+static int insertDeviceDirect(SimlodContext* ctx, CUdeviceptr dev, uint64_t count, float* kernel_ms, float* total_ms) {
+    int rc = setCurrent(ctx); if (rc) return rc;
+    const uint64_t numBatches = (count + SLOT_POINTS - 1) / SLOT_POINTS;
+    rc = readStats(ctx); if (rc) return rc;
+    while (ctx->processed < ctx->uploaded) {               // batches uploaded earlier sit in the real ring: consume them first
+        rc = launchConstruct(ctx, nullptr); if (rc) return rc;
+        rc = readStats(ctx); if (rc) return rc;
+        if (ctx->hStats->memCapacityReached) return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed);
+    }
+    const uint32_t g0 = ctx->uploaded;                     // global index of this call's first batch
+    const uint32_t target = g0 + (uint32_t)numBatches;
+    float total = 0.0f;
+    int inFlight[8]; int numInFlight = 0, nextSlot = 0;
+    uint32_t covered = ctx->processed, stalled = 0;
+    CUdeviceptr base = 0;
+    CU(D(cuEventRecord)(ctx->evTotalStart, ctx->streamMain));
+    while (ctx->processed < target) {
+        if (numInFlight == 0) {
+            covered = ctx->processed;
+            if (ctx->uploaded == ctx->processed) {         // the window is consumed: publish the next one (sizes + counter only)
+                const uint32_t window = ctx->processed / (uint32_t)RING_SLOTS;
+                const uint32_t windowEnd = std::min<uint32_t>(target, (window + 1u) * (uint32_t)RING_SLOTS);
+                while (ctx->uploaded < windowEnd) {
+                    const uint64_t first = (uint64_t)(ctx->uploaded - g0) * SLOT_POINTS;
+                    ctx->hostSizes[ctx->uploaded % RING_SLOTS] = (uint32_t)std::min<uint64_t>(SLOT_POINTS, count - first);
+                    ctx->uploaded++;
+                    ctx->unpublished++;
+                }
+                rc = publishPending(ctx); if (rc) return rc;
+                // slot s of this window = batch window * 50 + s = the caller's batch (window * 50 + s - g0)
+                base = dev + (uint64_t)((int64_t)window * (int64_t)RING_SLOTS - (int64_t)g0) * (SLOT_POINTS * sizeof(SimlodPoint));
+            }
+            if (stalled > 4) return fail(SIMLOD_ERR_CUDA, "kernel_construct makes no progress (%u of %u batches consumed)", ctx->processed, target);
+            while (numInFlight < 8 && ctx->uploaded > covered) {
+                const uint32_t take = std::min<uint32_t>(20u, ctx->uploaded - covered);
+                CU(D(cuStreamWaitEvent)(ctx->streamMain, ctx->evSlot[(covered + take - 1u) % RING_SLOTS], 0));
+                const int k = nextSlot; nextSlot = (nextSlot + 1) % 8;
+                rc = enqueueConstruct(ctx, k, base); if (rc) return rc;
+                CU(D(cuMemcpyDtoHAsync)(&ctx->hStatsRing[k], ctx->buf.stats, sizeof(SimlodStats), ctx->streamMain));
+                CU(D(cuEventRecord)(ctx->evStatsDone[k], ctx->streamMain));
+                inFlight[numInFlight++] = k;
+                covered += take;
+            }
+        }
+        const int k = inFlight[0];
+        CUresult q = D(cuEventSynchronize)(ctx->evStatsDone[k]);
+        if (q != CUDA_SUCCESS) { const char* e = nullptr; D(cuGetErrorString)(q, &e); return fail(SIMLOD_ERR_CUDA, "kernel_construct failed: %s (%d)", e ? e : "?", (int)q); }
+        float ms = 0.0f;
+        D(cuEventElapsedTime)(&ms, ctx->evBurst[k][0], ctx->evBurst[k][1]);
+        total += ms;
+        const uint32_t before = ctx->processed;
+        *ctx->hStats = ctx->hStatsRing[k];
+        ctx->processed = ctx->hStats->batchletIndex;
+        for (int i = 1; i < numInFlight; i++) inFlight[i - 1] = inFlight[i];
+        numInFlight--;
+        stalled = ctx->processed == before ? stalled + 1 : 0;
+        if (ctx->hStats->memCapacityReached) return fail(SIMLOD_ERR_CAPACITY, "persistent heap almost full after %llu points", (unsigned long long)ctx->hStats->numPointsProcessed);
+        rc = checkOverflow(ctx); if (rc) return rc;
+    }
+    CU(D(cuEventRecord)(ctx->evTotalEnd, ctx->streamMain));
+    CU(D(cuEventSynchronize)(ctx->evTotalEnd));
+    if (kernel_ms) *kernel_ms = total;
+    if (total_ms) CU(D(cuEventElapsedTime)(total_ms, ctx->evTotalStart, ctx->evTotalEnd));
+    return SIMLOD_OK;
+}
+
 int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t count, float* kernel_ms, float* total_ms) {
     if (!host_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
     return insertCommon(ctx, host_points, 0, count, kernel_ms, total_ms);
 }
 int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms, float* total_ms) {
     if (!device_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
-    return insertCommon(ctx, nullptr, (CUdeviceptr)device_points, count, kernel_ms, total_ms);
+    if (!ctx) return fail(SIMLOD_ERR_INVALID, "null context");
+    if ((device_points & 15ull) != 0) return insertCommon(ctx, nullptr, (CUdeviceptr)device_points, count, kernel_ms, total_ms);    // unaligned source: through the ring
+    return insertDeviceDirect(ctx, (CUdeviceptr)device_points, count, kernel_ms, total_ms);
 }
 
 // ---- streaming front end -------------------------------------------------------------
