@@ -482,6 +482,7 @@ def main():
         dptr = sim.device_alloc(npts * 16)
         sim.generate(sim.GEN_TERRAIN, dptr, npts, 0, npts, TERRAIN_SEED + rank)
         host_ptr = sim.host_alloc(npts * 16)
+        numa_node = sim.numa_node()
         sim._check(sim._lib.simlod_memcpy_dtoh(sim._ctx, host_ptr, dptr, npts * 16))
         t_gen = time.time() - t_gen
 
@@ -637,7 +638,7 @@ def main():
                          "note": "latency/atomic bound, not bandwidth bound: see DESIGN.md §7"},
             "e2e": {"value": round(all_pts / t_e2e / 1e3, 2), "unit": "Mpoints/s", "h2d_bytes_per_step": BATCH * 16,
                     "d2h_bytes_per_step": round(112.0 * (e_launches + 1) / NB, 1), "wall_clock_value": round(all_pts / t_e2e_wall / 1e3, 2),
-                    "launches": e_launches, "passes": e_passes},
+                    "launches": e_launches, "passes": e_passes, "pinned_on_numa_node": numa_node},
             "gpu_launches": launches_per_pass * passes,
             "clocks": sampler.summary(windows),
         }

@@ -151,6 +151,9 @@ int simlod_host_free(SimlodContext* ctx, void* ptr);
 int simlod_device_alloc(SimlodContext* ctx, uint64_t bytes, uint64_t* out);
 int simlod_device_free(SimlodContext* ctx, uint64_t ptr);
 
+// host NUMA node the context's page-locked buffers (simlod_host_alloc, the streamer's pool) were placed on: the node
+// closest to the device (CU_DEVICE_ATTRIBUTE_HOST_NUMA_ID, else sysfs); -1 when unknown or before the first allocation
+int simlod_get_numa_node(SimlodContext* ctx, int* node);
 // launch bookkeeping: kernels launched by this context so far, and the grid sizes in use
 int simlod_get_launch_info(SimlodContext* ctx, uint64_t* launches, uint32_t* construct_blocks, uint32_t* render_blocks, uint32_t* num_sms);
 // MUFU.RCP(x) as the device computes it (the one float a CPU restatement cannot derive when the

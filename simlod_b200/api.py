@@ -116,7 +116,7 @@ EXPORTS = [
     "simlod_memcpy_htod", "simlod_host_alloc", "simlod_host_free", "simlod_device_alloc", "simlod_device_free",
     "simlod_get_launch_info", "simlod_device_rcp", "simlod_synchronize", "simlod_flush_l2",
     "simlod_partition_count", "simlod_partition_scatter", "simlod_partition_wait",
-    "simlod_export_framebuffer", "simlod_peer_signal", "simlod_composite_framebuffers", "simlod_generate", "simlod_reset_with_grid", "simlod_insert_simlod_file_ex",
+    "simlod_export_framebuffer", "simlod_peer_signal", "simlod_composite_framebuffers", "simlod_generate", "simlod_reset_with_grid", "simlod_insert_simlod_file_ex", "simlod_get_numa_node",
 ]
 
 _lib = None
@@ -163,6 +163,7 @@ def load_library():
         "simlod_get_launch_info": [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)],
         "simlod_device_rcp": [vp, C.c_float, C.POINTER(C.c_float)],
         "simlod_flush_l2": [vp],
+        "simlod_get_numa_node": [vp, C.POINTER(C.c_int)],
         "simlod_generate": [vp, C.c_int, u64, u64, u64, u64, C.c_float, u64],
         "simlod_synchronize": [vp],
         "simlod_partition_count": [vp, u64, u32, C.POINTER(PartitionPlan), C.POINTER(u64), C.POINTER(u64)],
@@ -434,6 +435,11 @@ class SimLOD:
         n, cb, rb, sms = C.c_uint64(), C.c_uint32(), C.c_uint32(), C.c_uint32()
         self._check(self._lib.simlod_get_launch_info(self._ctx, C.byref(n), C.byref(cb), C.byref(rb), C.byref(sms)))
         return {"launches": n.value, "construct_blocks": cb.value, "render_blocks": rb.value, "num_sms": sms.value}
+
+    def numa_node(self):
+        n = C.c_int(-1)
+        self._check(self._lib.simlod_get_numa_node(self._ctx, C.byref(n)))
+        return n.value
 
     def device_rcp(self, x):
         out = C.c_float()

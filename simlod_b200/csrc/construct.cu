@@ -203,8 +203,10 @@ struct Batch {
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ldv(const uint32_t* p) { return *(volatile const uint32_t*)p; }
-__device__ __forceinline__ uint64_t ldv(const uint64_t* p) { return *(volatile const uint64_t*)p; }
+// values other blocks wrote in an earlier phase (or that the host's copies wrote): read at the L2, never from a stale L1 line.
+// (ld.relaxed.gpu rather than a volatile load: the latter is a system-scope access, several times the latency)
+__device__ __forceinline__ uint32_t ldv(const uint32_t* p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ uint64_t ldv(const uint64_t* p) { uint64_t v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ uint32_t ldcg(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 __device__ __forceinline__ uint32_t ldAcquire(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31; }
@@ -448,6 +450,8 @@ __shared__ uint32_t sh_listMode;          // 0: the run (sh_runSlot), 1: the exp
 __shared__ uint32_t sh_blockLegacy;       // this block cannot name its items any more in this batch
 __shared__ uint8_t  sh_entrySplit[VOXTAB_SIZE];
 __shared__ uint32_t sh_splitNodes[64];
+__shared__ SpillInfo sh_splitInfo[64];       // the leaves split in the current round (worklist rounds: at most 64) ...
+__shared__ uint32_t sh_splitGranule[65];     // ... and the running number of 32-point granules of their spilled points
 __shared__ uint32_t sh_wlCount, sh_wlBase, sh_wlFill;
 // block-wide exclusive prefix sum of one value per thread (256 threads); returns the block total
 __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t& total) {
@@ -572,6 +576,30 @@ __device__ __noinline__ uint32_t countGlobal(const Ctx c, const Batch b, uint32_
 // ------------------------------------------------------------------------------------------
 struct LeafCache { uint32_t node, level, kx, ky, kz, parent; };      // node == VOXTAB_EMPTY: nothing cached
 
+// count (voxels.cu:203-218, doCounting::countPoint): the lanes of a warp that reached the same leaf take consecutive ranks
+// from the block's table (or, when the table or the block's item list is full, final slots from the global counter).
+// Warp-collective; returns the lane's slot word.
+__device__ __forceinline__ uint32_t countInto(const Ctx& c, const Batch& b, bool valid, uint32_t node, uint32_t level, uint32_t* bloom, bool forceGlobal) {
+    const uint32_t lane = laneId();
+    uint32_t slot = 0;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+        uint32_t peers = __match_any_sync(vmask, node);
+        uint32_t leader = __ffs(peers) - 1;
+        uint32_t cnt = __popc(peers);
+        uint32_t r = 0;
+        if (lane == leader) {
+            uint32_t t = forceGlobal ? VOXTAB_EMPTY : tabInsert(sh_leafKey, node);
+            if (t != VOXTAB_EMPTY) { r = atomicAdd(&sh_leafCount[t], cnt) | PROVISIONAL | (t << 24); sh_leafLevel[t] = (uint8_t)level; }   // block-local rank
+            else                 { r = countGlobal(c, b, node, level, cnt); sh_blockLegacy = 1; }   // table (or list) full: final slot at once
+            if (bloom) bloomAdd(bloom, node);
+        }
+        r = __shfl_sync(peers, r, leader);
+        slot = r + __popc(peers & lanemaskLt());
+    }
+    return slot;
+}
+
 // the upward half of the walk: probe / set the point's cell from (sNode, sLevel) towards the root until a set bit is met
 // (or down to stopLevel), recording a voxel for every cell this thread wins
 template <bool UNCACHED_GRID, bool DEDUP>
@@ -629,51 +657,9 @@ __device__ __forceinline__ void sampleUp(const Ctx& c, const Batch& b, const Coo
     settle();
 }
 
-// voxel stage of a first-visit pass: per warp, a queue of (item, deepest grid node | level << 24) of the run's points whose
-// cell was still clear when they were walked
-constexpr uint32_t VQ_CAP = 64;
-__shared__ uint2 sh_vq[8][VQ_CAP];
-__shared__ uint32_t sh_vqCount[8];
-
-template <bool UNCACHED_GRID>
-__device__ __forceinline__ void voxelStageDrain(const Ctx& c, const Batch& b) {           // warp-collective
-    const uint32_t warp = threadIdx.x >> 5, lane = laneId();
-    const uint32_t n = sh_vqCount[warp];
-    for (uint32_t e0 = 0; e0 < n; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        if (e < n) {
-            const uint2 entry = sh_vq[warp][e];
-            const uint4 pt = ldPoint(b.points + entry.x);
-            const Coords q = quantize(c, pt);
-            sampleUp<UNCACHED_GRID, true>(c, b, q, pt.w, entry.y & 0xffffffu, entry.y >> 24, 0u);
-        }
-        __syncwarp();
-    }
-    __syncwarp();
-    if (lane == 0) sh_vqCount[warp] = 0;
-    __syncwarp();
-}
-// queue this lane's point if `deferred` != ~0 (warp-collective; drains first when the queue would overflow)
-template <bool UNCACHED_GRID>
-__device__ __forceinline__ void voxelStagePush(const Ctx& c, const Batch& b, uint32_t item, uint32_t deferred) {
-    const uint32_t warp = threadIdx.x >> 5, lane = laneId();
-    const uint32_t mask = __ballot_sync(0xffffffffu, deferred != 0xffffffffu);
-    if (mask == 0) return;
-    if (sh_vqCount[warp] + __popc(mask) > VQ_CAP) voxelStageDrain<UNCACHED_GRID>(c, b);
-    const uint32_t base = sh_vqCount[warp];
-    if (deferred != 0xffffffffu) sh_vq[warp][base + __popc(mask & lanemaskLt())] = make_uint2(item, deferred);
-    __syncwarp();
-    if (lane == 0) sh_vqCount[warp] = base + __popc(mask);
-    __syncwarp();
-}
-
-template <bool SAMPLE, bool COUNT, bool UNCACHED_GRID, bool DEDUP, bool DEFER = false>
+template <bool SAMPLE, bool COUNT, bool UNCACHED_GRID, bool DEDUP>
 __device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& cache, bool valid, uint4 pt, uint32_t node, uint32_t level,
-                                     uint32_t stopLevel, uint32_t* bloom, bool forceGlobal, uint32_t& leafPacked, uint32_t& slot, uint32_t& deferred) {
-    deferred = 0xffffffffu;
-    const uint32_t FULL = 0xffffffffu;
-    const uint32_t lane = laneId();
-    const uint32_t ltmask = lanemaskLt();
+                                     uint32_t stopLevel, uint32_t* bloom, bool forceGlobal, uint32_t& leafPacked, uint32_t& slot) {
     Coords q = quantize(c, pt);
     uint32_t parent = VOXTAB_EMPTY;
     if (valid) {
@@ -700,46 +686,13 @@ __device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& ca
             // nodes with a grid on the path: the inner nodes, and the root even while it is a leaf (reset.cu:69)
             const uint32_t sNode = level == 0 ? node : parent;
             const uint32_t sLevel = level == 0 ? 0u : level - 1;
-            if (DEFER) {
-                // first-visit pass over the block's run: ONE probe of the deepest grid here; whatever needs more (a clear bit: an
-                // atomic, a voxel record, the levels above) is queued for the warp's voxel stage, where the few such points of a
-                // run are handled with all lanes busy instead of one or two lanes holding up the other thirty every time
-                bool need = !nested(q);
-                if (!need) {
-                    const uint64_t g = c.gridPtr()[sNode];
-                    if (g != 0) {
-                        const uint32_t cell = cellAt(q, sLevel);
-                        const uint32_t* word = reinterpret_cast<const uint32_t*>(g) + (cell >> 5);
-                        const uint32_t seen = UNCACHED_GRID ? ldcg(word) : *word;
-                        need = (seen & (1u << (cell & 31u))) == 0;
-                    }
-                }
-                deferred = need ? (sNode | (sLevel << 24)) : 0xffffffffu;
-            } else {
-                sampleUp<UNCACHED_GRID, DEDUP>(c, b, q, pt.w, sNode, sLevel, stopLevel);
-            }
+            sampleUp<UNCACHED_GRID, DEDUP>(c, b, q, pt.w, sNode, sLevel, stopLevel);
         }
     }
     __syncwarp();
 
     leafPacked = node | (level << 24);
-    if (COUNT) {
-        uint32_t vmask = __ballot_sync(FULL, valid);
-        if (valid) {
-            uint32_t peers = __match_any_sync(vmask, node);
-            uint32_t leader = __ffs(peers) - 1;
-            uint32_t cnt = __popc(peers);
-            uint32_t r = 0;
-            if (lane == leader) {
-                uint32_t t = forceGlobal ? VOXTAB_EMPTY : tabInsert(sh_leafKey, node);
-                if (t != VOXTAB_EMPTY) { r = atomicAdd(&sh_leafCount[t], cnt) | PROVISIONAL | (t << 24); sh_leafLevel[t] = (uint8_t)level; }   // block-local rank
-                else                 { r = countGlobal(c, b, node, level, cnt); sh_blockLegacy = 1; }   // table (or list) full: final slot at once
-                if (bloom) bloomAdd(bloom, node);
-            }
-            r = __shfl_sync(peers, r, leader);
-            slot = r + __popc(peers & ltmask);
-        }
-    }
+    if (COUNT) slot = countInto(c, b, valid, node, level, bloom, forceGlobal);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -874,7 +827,7 @@ __device__ void buildWorklist(const Ctx& c, const Batch& b, uint32_t spillBegin,
 //   the table flush (leaf counters, voxel counters) is left to the caller: passFlush()
 // ------------------------------------------------------------------------------------------
 template <bool SAMPLE, bool COUNT, bool FRESH, bool UNCACHED_GRID>
-__device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t numSpilled, uint32_t spilledBefore, uint32_t round) {
+__device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t numSpilled, uint32_t spilledBefore, uint32_t round, uint32_t spillBegin = 0, uint32_t spillEnd = 0) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t* leafOf = c.leafOf(b.parity);
@@ -910,9 +863,7 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
                 const bool valid = i < blockEnd;
                 uint4 pt = valid ? sh_tile[t & 1][idx] : make_uint4(0, 0, 0, 0);
                 uint32_t lp = 0, slot = 0;
-                uint32_t deferred;
-                walk<SAMPLE, COUNT, UNCACHED_GRID, true, true>(c, b, cache, valid, pt, 0, 0, 0, COUNT ? sh_runBloom : nullptr, false, lp, slot, deferred);
-                if (SAMPLE) voxelStagePush<UNCACHED_GRID>(c, b, i, deferred);
+                walk<SAMPLE, COUNT, UNCACHED_GRID, true>(c, b, cache, valid, pt, 0, 0, 0, COUNT ? sh_runBloom : nullptr, false, lp, slot);
                 if (valid && COUNT) {
                     leafOf[i] = lp;
                     if (runLen <= RUNSLOT_CAP) sh_runSlot[i - blockFirst] = slot; else slotOf[i] = slot;
@@ -920,7 +871,6 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
             }
             __syncthreads();
         }
-        if (SAMPLE) voxelStageDrain<UNCACHED_GRID>(c, b);
         if (threadIdx.x == 0) { sh_tilePhase[0] = ph0; sh_tilePhase[1] = ph1; }
         if (COUNT && threadIdx.x < BLOOM_WORDS) c.runBloom()[blockIdx.x * BLOOM_WORDS + threadIdx.x] = sh_runBloom[threadIdx.x];
     } else {
@@ -928,15 +878,47 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
         if (ldcg(&w->legacy) == 0) {
             // ---- the items the split phase named (buildWorklist), then the points spilled in this round ---------------------
             const uint32_t numListed = min(ldcg(&w->cursor[round & 1u]), (uint32_t)scratch::WL_CAP);
-            const uint32_t total = numListed + (numSpilled - spilledBefore);
             const uint32_t perRun = ((b.size + gridDim.x - 1) / gridDim.x + 31u) & ~31u;
             const uint32_t* wl = c.worklist();
+            const uint32_t numSplit = spillEnd - spillBegin;                      // <= 64 in worklist rounds
+            if (threadIdx.x < numSplit) sh_splitInfo[threadIdx.x] = c.spill()[spillBegin + threadIdx.x];
             if (threadIdx.x == 0) { sh_listCount = 0; sh_listMode = 1; }          // the list of the previous round has been read (split phase)
             __syncthreads();
-            for (uint32_t base = rewalkFirstGranule(); base < total; base += rewalkGranuleStride()) {
+            if (threadIdx.x == 0) {
+                uint32_t run = 0;
+                for (uint32_t k = 0; k < numSplit; k++) { sh_splitGranule[k] = run; run += (sh_splitInfo[k].stored + 31u) / 32u; }
+                sh_splitGranule[numSplit] = run;
+            }
+            __syncthreads();
+#if SIMLOD_TIMERS >= 2
+            uint64_t tRw = globaltimer();
+#define RW_DONE(k) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { uint64_t _t = globaltimer(); c.ctl()->subNanos[k] += _t - tRw; tRw = _t; } } while (0)
+#else
+#define RW_DONE(k) do { } while (0)
+#endif
+            // room in the block's item list for a warp's items; without it they are counted globally (final slots at once)
+            auto reserve = [&](bool valid, bool& forceGlobal) {
+                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                uint32_t k0 = 0;
+                if (laneId() == 0) k0 = atomicAdd(&sh_listCount, (uint32_t)__popc(vmask));
+                k0 = __shfl_sync(0xffffffffu, k0, 0);
+                forceGlobal = k0 + __popc(vmask) > LIST_CAP;
+                return k0 + __popc(vmask & lanemaskLt());
+            };
+            auto remember = [&](uint32_t i, uint32_t lp, uint32_t slot, uint32_t myk, bool forceGlobal) {
+                leafOf[i] = lp;
+                if (!forceGlobal) { listItem()[myk] = i; listSlot()[myk] = slot; }       // the final slot is written by passFlush
+                else {
+                    slotOf[i] = slot;
+                    if (myk < LIST_CAP) { listItem()[myk] = 0xffffffffu; listSlot()[myk] = 0; }   // reserved but unused: the warp's items straddled the end of the list
+                }
+            };
+            RW_DONE(12);
+            // ---- (1) the items the split phase named (buildWorklist): batch points, and points spilled in earlier rounds ------
+            for (uint32_t base = rewalkFirstGranule(); base < numListed; base += rewalkGranuleStride()) {
                 const uint32_t u = base + laneId();
-                bool valid = u < total;
-                const uint32_t i = !valid ? 0u : (u < numListed ? wl[u] : (uint32_t)scratch::MAX_BATCH + spilledBefore + (u - numListed));
+                bool valid = u < numListed;
+                const uint32_t i = valid ? wl[u] : 0u;
                 const bool spilledItem = valid && i >= scratch::MAX_BATCH;
                 uint4 pt = make_uint4(0, 0, 0, 0);
                 uint32_t node = 0, level = 0;
@@ -946,27 +928,41 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
                     node = lp & 0xffffffu; level = lp >> 24;
                     valid = level < SIMLOD_MAX_DEPTH;                    // a level-20 node is the leaf even after it "split" (voxels.cu:169)
                 }
-                // room in the block's item list for the warp's items; without it they are counted globally (final slots at once)
-                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-                if (vmask == 0) continue;
-                uint32_t k0 = 0;
-                if (laneId() == 0) k0 = atomicAdd(&sh_listCount, (uint32_t)__popc(vmask));
-                k0 = __shfl_sync(0xffffffffu, k0, 0);
-                const bool forceGlobal = k0 + __popc(vmask) > LIST_CAP;
-                const uint32_t myk = k0 + __popc(vmask & lanemaskLt());
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                bool forceGlobal;
+                const uint32_t myk = reserve(valid, forceGlobal);
                 uint32_t lp = 0, slot = 0;
-                uint32_t deferredUnused;
                 walk<SAMPLE, COUNT, UNCACHED_GRID, false>(c, b, cache, valid, pt, node, level, level,
-                                                         valid && !spilledItem ? c.runBloom() + (i / perRun) * BLOOM_WORDS : nullptr, forceGlobal, lp, slot, deferredUnused);
-                if (valid && COUNT) {
-                    leafOf[i] = lp;
-                    if (!forceGlobal) { listItem()[myk] = i; listSlot()[myk] = slot; }           // the final slot is written by passFlush
-                    else {
-                        slotOf[i] = slot;
-                        if (myk < LIST_CAP) { listItem()[myk] = 0xffffffffu; listSlot()[myk] = 0; }       // reserved but unused: the warp's items straddled the end of the list
-                    }
-                }
+                                                         valid && !spilledItem ? c.runBloom() + (i / perRun) * BLOOM_WORDS : nullptr, forceGlobal, lp, slot);
+                if (valid && COUNT) remember(i, lp, slot, myk, forceGlobal);
             }
+            RW_DONE(13);
+            // ---- (2) the points spilled in this round, leaf by leaf: a warp's 32 points come out of ONE split leaf, whose
+            // record (children, grid, level) is in shared memory — no leaf look-up, no descent: the child is one step down,
+            // the only grid on the way is the leaf's own fresh one
+            const uint32_t numGranules = sh_splitGranule[numSplit];
+            for (uint32_t g = rewalkFirstGranule() / 32u; g < numGranules; g += rewalkGranuleStride() / 32u) {
+                uint32_t lo = 0, hi = numSplit;                          // last split with first granule <= g
+                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh_splitGranule[mid] <= g) lo = mid; else hi = mid; }
+                const uint32_t node = sh_splitInfo[lo].node, level = sh_splitInfo[lo].level, childBase = sh_splitInfo[lo].childBase;
+                const uint32_t within = (g - sh_splitGranule[lo]) * 32u + laneId();
+                bool valid = within < sh_splitInfo[lo].stored && level < SIMLOD_MAX_DEPTH;
+                const uint32_t j = sh_splitInfo[lo].base + within;
+                const uint32_t i = (uint32_t)scratch::MAX_BATCH + j;
+                uint4 pt = make_uint4(0, 0, 0, 0);
+                if (valid) pt = *reinterpret_cast<const uint4*>(c.spilled() + j);
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                bool forceGlobal;
+                const uint32_t myk = reserve(valid, forceGlobal);
+                const Coords q = quantize(c, pt);
+                const uint32_t child = childBase + childIndexAt(q, level);
+                if (SAMPLE && valid) sampleUp<UNCACHED_GRID, false>(c, b, q, pt.w, node, level, level);
+                __syncwarp();
+                uint32_t slot = 0;
+                if (COUNT) slot = countInto(c, b, valid, child, level + 1, nullptr, forceGlobal);
+                if (valid && COUNT) remember(i, child | ((level + 1) << 24), slot, myk, forceGlobal);
+            }
+            RW_DONE(14);
         } else {
             if (threadIdx.x == 0) sh_blockLegacy = 1;
             // ---- the runs that can hold an item whose leaf was split in the round that just ended: every block published
@@ -987,10 +983,6 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
             }
             // ---- the affected runs and the spilled points as one item space --------------------------------------------
             const Rewalk rw = rewalkSlice(b.size, numSpilled, spilledBefore);
-    #if SIMLOD_TIMERS >= 2
-            uint64_t tList = 0;
-            if (blockIdx.x == 0 && threadIdx.x == 0) { tList = globaltimer(); c.ctl()->subNanos[14] += rw.total; c.ctl()->subNanos[15] += rw.runItems; }
-    #endif
             for (uint32_t base = rewalkFirstGranule(); base < rw.total; base += rewalkGranuleStride()) {
                 const uint32_t u = base + laneId();
                 uint32_t run = 0xffffffffu, i = 0xffffffffu, node = 0, level = 0;
@@ -1008,13 +1000,9 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
                 if (!__any_sync(0xffffffffu, valid)) continue;
                 if (valid && !spilledItem) pt = ldPoint(b.points + i);
                 uint32_t lp = 0, slot = 0;
-                uint32_t deferredUnused;
-                walk<SAMPLE, COUNT, UNCACHED_GRID, false>(c, b, cache, valid, pt, node, level, level, run != 0xffffffffu ? c.runBloom() + run * BLOOM_WORDS : nullptr, false, lp, slot, deferredUnused);
+                walk<SAMPLE, COUNT, UNCACHED_GRID, false>(c, b, cache, valid, pt, node, level, level, run != 0xffffffffu ? c.runBloom() + run * BLOOM_WORDS : nullptr, false, lp, slot);
                 if (valid && COUNT) { leafOf[i] = lp; slotOf[i] = slot; }
             }
-    #if SIMLOD_TIMERS >= 2
-            if (blockIdx.x == 0 && threadIdx.x == 0) c.ctl()->subNanos[13] += globaltimer() - tList;      // warp 0's loop alone
-    #endif
 
         }
     }
@@ -1026,8 +1014,7 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
             uint4 pt = make_uint4(0, 0, 0, 0);
             if (valid) pt = *reinterpret_cast<const uint4*>(c.spilled() + j);
             uint32_t lp = 0, slot = 0;
-            uint32_t deferredUnused;
-            walk<SAMPLE, COUNT, UNCACHED_GRID, true>(c, b, cache, valid, pt, 0, 0, 0, nullptr, false, lp, slot, deferredUnused);
+            walk<SAMPLE, COUNT, UNCACHED_GRID, true>(c, b, cache, valid, pt, 0, 0, 0, nullptr, false, lp, slot);
         }
     }
     __syncthreads();
@@ -1497,7 +1484,6 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         }
     }
     if (threadIdx.x == 0) { sh_allocTarget = 0; sh_allocSeen = 0; sh_numAffected = 0; }
-    if (threadIdx.x < 8) sh_vqCount[threadIdx.x] = 0;
     tileBarInit();
     grid.sync();
     uint64_t tPhase = tStart;
@@ -1592,8 +1578,8 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
 #endif
             const uint32_t numSpilled = min(ldv(&b.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
             if (first) ctl->wl[b.index % 3u].cursor[(round + 1) & 1] = 0;       // the list of the previous round has been consumed
-            if (deferSampling) passItems<false, true, false, false>(c, b, numSpilled, spilledBefore, (uint32_t)round);
-            else               passItems<true, true, false, false>(c, b, numSpilled, spilledBefore, (uint32_t)round);
+            if (deferSampling) passItems<false, true, false, false>(c, b, numSpilled, spilledBefore, (uint32_t)round, spillBegin, spillEnd);
+            else               passItems<true, true, false, false>(c, b, numSpilled, spilledBefore, (uint32_t)round, spillBegin, spillEnd);
             SUB_DONE(8);
             if (deferSampling) passFlush<false, true, false>(c, b, numSpilled, spilledBefore);
             else               passFlush<true, true, false>(c, b, numSpilled, spilledBefore);

@@ -18,6 +18,7 @@
 #include <emmintrin.h>
 #endif
 #include <unistd.h>
+#include <sys/syscall.h>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -150,6 +151,7 @@ struct SimlodContext {
     uint32_t processed = 0;            // Stats::batchletIndex as last read
     uint64_t launches = 0;
     uint32_t constructBlocks = 0, renderBlocks = 0;
+    int numaNode = -1;                 // host NUMA node the page-locked buffers were placed on (-1: unknown)
     uint64_t frameCounter = 0;
 };
 
@@ -168,16 +170,30 @@ int devAlloc(uint64_t* out, uint64_t bytes) {
 // allocates on the node of the calling thread, so the thread is parked on that node's CPUs for the call.
 struct NumaLocal {
     cpu_set_t old;
-    bool active = false;
+    bool active = false, policy = false;
+    int node = -1;
     explicit NumaLocal(SimlodContext* ctx) {
-        char bus[32] = {0};
-        if (D(cuDeviceGetPCIBusId)(bus, (int)sizeof(bus), ctx->device) != CUDA_SUCCESS) return;
-        for (char* c = bus; *c; c++) *c = (char)tolower(*c);
-        char path[128];
-        snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
-        int node = -1;
-        if (FILE* f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+        // the host NUMA node closest to the device: the driver's own answer first, sysfs second
+        int attr = -1;
+        if (D(cuDeviceGetAttribute)(&attr, (CUdevice_attribute)134 /* CU_DEVICE_ATTRIBUTE_HOST_NUMA_ID */, ctx->device) == CUDA_SUCCESS && attr >= 0) node = attr;
+        if (node < 0) {
+            char bus[32] = {0};
+            if (D(cuDeviceGetPCIBusId)(bus, (int)sizeof(bus), ctx->device) != CUDA_SUCCESS) return;
+            for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+            char path[128];
+            snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+            if (FILE* f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+        }
         if (node < 0) return;
+        ctx->numaNode = node;
+        // page placement follows the allocating thread: prefer the node for its allocations (works where the container lets
+        // set_mempolicy through) and park the thread on the node's CPUs (first touch) for the duration of the call
+        unsigned long mask[16] = {0};
+        if (node < (int)(sizeof(mask) * 8)) {
+            mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+            policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof(mask) * 8) == 0;
+        }
+        char path[128];
         snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
         char list[4096] = {0};
         if (FILE* f = fopen(path, "r")) { if (!fgets(list, sizeof(list), f)) list[0] = 0; fclose(f); }
@@ -194,7 +210,10 @@ struct NumaLocal {
         if (CPU_COUNT(&want) == 0) return;
         active = sched_setaffinity(0, sizeof(want), &want) == 0;
     }
-    ~NumaLocal() { if (active) sched_setaffinity(0, sizeof(old), &old); }
+    ~NumaLocal() {
+        if (active) sched_setaffinity(0, sizeof(old), &old);
+        if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+    }
 };
 
 const char* kernelName(int program) {
@@ -1076,6 +1095,12 @@ int simlod_get_launch_info(SimlodContext* ctx, uint64_t* launches, uint32_t* con
     if (construct_blocks) *construct_blocks = ctx->constructBlocks;
     if (render_blocks) *render_blocks = ctx->renderBlocks;
     if (num_sms) *num_sms = (uint32_t)ctx->numSMs;
+    return SIMLOD_OK;
+}
+
+int simlod_get_numa_node(SimlodContext* ctx, int* node) {
+    if (!ctx || !node) return fail(SIMLOD_ERR_INVALID, "null argument");
+    *node = ctx->numaNode;
     return SIMLOD_OK;
 }
 

@@ -37,7 +37,7 @@ namespace rbuf {
 constexpr uint64_t OFF_CTL       = 0;
 constexpr uint64_t OFF_VISLIST   = 4096;                           // u32 node indices of the LOD cut
 constexpr uint64_t VIS_CAP       = 263168;
-constexpr uint64_t ITEM_CAP      = 2097152;                        // quarter-chunk items per frame = 0.5 G samples (the reference: 100 000 nodes)
+constexpr uint64_t ITEM_CAP      = 2097152;                        // chunk items per frame = 2 G samples (the reference: 100 000 nodes)
 constexpr uint64_t OFF_ITEMS     = OFF_VISLIST + VIS_CAP * 4;      // u64 per item, see packItem()
 constexpr uint64_t OFF_FB        = 31200144;                       // 15 200 000 + 7*16 + 32 + 16 000 000
 constexpr uint64_t TOTAL_BYTES   = 200000000;                      // what the host allocates (main.cpp:556)
@@ -45,27 +45,15 @@ constexpr uint64_t NODE_TAB      = 263168;                         // >= floor(4
 static_assert(OFF_ITEMS + ITEM_CAP * 8 <= OFF_FB, "render scratch overlaps the framebuffer");
 }
 
-// One work item = a quarter of a chunk (<= 250 contiguous samples = 4 KB), packed into a single 64-bit word:
-//   [63:26] (chunk address - heap base) >> 4   [25:16] sample count (1..250)   [15:11] node level   [10:4] node colour id
-//   [2:1] quarter of the chunk (samples from 250 * q)   [0] valid
-// A frame of a few million samples is only a few thousand chunks — fewer than the grid has warps — so whole chunks as
-// items leave warps idle while others splat 1000 samples in a row. ITEM_EMPTY = nothing to draw.
-constexpr uint32_t ITEM_SAMPLES = 250, ITEMS_PER_CHUNK = 4;
+// One work item = one chunk of <= 1000 samples, packed into a single 64-bit word:
+//   [63:26] (chunk address - heap base) >> 4   [25:16] sample count (1..1000)   [15:11] node level   [10:4] node colour id   [0] valid
+// ITEM_EMPTY = nothing to draw (list shorter than the counters say).
 typedef uint64_t WorkItem;
 constexpr WorkItem ITEM_EMPTY = ~0ull;
-__device__ __forceinline__ WorkItem packItem(const uint8_t* heapBase, const void* chunk, uint32_t quarter, uint32_t count, uint32_t level, uint32_t colorId) {
-    return ((uint64_t)((const uint8_t*)chunk - heapBase) >> 4 << 26) | ((uint64_t)count << 16) | ((uint64_t)(level & 31u) << 11) | ((uint64_t)(colorId & 127u) << 4) |
-           ((uint64_t)(quarter & 3u) << 1) | 1ull;
+__device__ __forceinline__ WorkItem packItem(const uint8_t* heapBase, const void* chunk, uint32_t count, uint32_t level, uint32_t colorId) {
+    return ((uint64_t)((const uint8_t*)chunk - heapBase) >> 4 << 26) | ((uint64_t)count << 16) | ((uint64_t)(level & 31u) << 11) | ((uint64_t)(colorId & 127u) << 4) | 1ull;
 }
-// the items of one chunk holding `samples` samples
-__device__ __forceinline__ void emitChunkItems(WorkItem* items, const uint8_t* heapBase, const void* chunk, uint32_t samples, uint32_t level, uint32_t colorId) {
-#pragma unroll
-    for (uint32_t q = 0; q < ITEMS_PER_CHUNK; q++) {
-        const uint32_t first = q * ITEM_SAMPLES;
-        items[q] = samples > first ? packItem(heapBase, chunk, q, min(ITEM_SAMPLES, samples - first), level, colorId) : ITEM_EMPTY;
-    }
-}
-__device__ __forceinline__ const uint4* itemSamples(const uint8_t* heapBase, WorkItem w) { return reinterpret_cast<const uint4*>(heapBase + ((w >> 26) << 4)) + ((w >> 1) & 3u) * ITEM_SAMPLES; }
+__device__ __forceinline__ const uint4* itemSamples(const uint8_t* heapBase, WorkItem w) { return reinterpret_cast<const uint4*>(heapBase + ((w >> 26) << 4)); }
 __device__ __forceinline__ uint32_t itemCount(WorkItem w) { return (uint32_t)(w >> 16) & 1023u; }
 __device__ __forceinline__ uint32_t itemLevel(WorkItem w) { return (uint32_t)(w >> 11) & 31u; }
 __device__ __forceinline__ uint32_t itemColorId(WorkItem w) { return (uint32_t)(w >> 4) & 127u; }
@@ -246,7 +234,7 @@ __device__ void emitList(const EmitCtx& e, const Chunk* head, uint32_t n, uint32
         if (!__all_sync(FULL, good)) { ok = false; break; }
         const uint32_t lastLane = min(31u, m - 1 - k0);
         carriedNext = __shfl_sync(FULL, nx, lastLane);
-        if (have) emitChunkItems(items + ITEMS_PER_CHUNK * k, e.heapBase, reinterpret_cast<const void*>(p), samplesOf(k), level, colorId);
+        if (have) items[k] = packItem(e.heapBase, reinterpret_cast<const void*>(p), samplesOf(k), level, colorId);
     }
     if (!ok) m = 0;
     if (m == n) { if (lane == 0) atomicAdd(&e.ctl->cacheHits, 1u); return; }
@@ -274,11 +262,11 @@ __device__ void emitList(const EmitCtx& e, const Chunk* head, uint32_t n, uint32
         for (; k < n; k++) {
             if (cur == nullptr || !validChunkPointer(e, (uint64_t)cur)) break;
             if (caching) e.pool[off + k] = (uint64_t)cur;
-            emitChunkItems(items + ITEMS_PER_CHUNK * k, e.heapBase, cur, samplesOf(k), level, colorId);
+            items[k] = packItem(e.heapBase, cur, samplesOf(k), level, colorId);
             cur = cur->next;
         }
         const uint32_t known = k;
-        for (; k < n; k++) for (uint32_t q = 0; q < ITEMS_PER_CHUNK; q++) items[ITEMS_PER_CHUNK * k + q] = ITEM_EMPTY;
+        for (; k < n; k++) items[k] = ITEM_EMPTY;
         if (caching) *entry = ListEntry{off, known, cap, 0};
     }
     __syncwarp();
@@ -293,15 +281,15 @@ __device__ void emitNode(const EmitCtx& e, const Node* node) {
     if (lane == 0) {                                                                 // render.cu:918-932 bookkeeping
         if (numPoints > 0) { atomicAdd(&e.ctl->numVisibleLeaves, 1u); atomicAdd(&e.ctl->numVisiblePoints, numPoints); }
         else if (numVoxels > 0) { atomicAdd(&e.ctl->numVisibleInner, 1u); atomicAdd(&e.ctl->numVisibleVoxels, numVoxels); }
-        if (nP + nV) base = atomicAdd(&e.ctl->numItems, ITEMS_PER_CHUNK * (nP + nV));
+        if (nP + nV) base = atomicAdd(&e.ctl->numItems, nP + nV);
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     if (nP + nV == 0) return;
-    if ((uint64_t)base + ITEMS_PER_CHUNK * (nP + nV) > rbuf::ITEM_CAP) { if (lane == 0) atomicOr(&e.ctl->overflow, 1u); return; }
+    if ((uint64_t)base + nP + nV > rbuf::ITEM_CAP) { if (lane == 0) atomicOr(&e.ctl->overflow, 1u); return; }
     const uint32_t colorId = nodeColorId(node);
     const uint32_t index = (uint32_t)(node - e.nodes);
     emitList(e, node->points, nP, numPoints, level, colorId, &e.entries[2 * index + 0], e.items + base);
-    emitList(e, node->voxelChunks, nV, numVoxels, level, colorId, &e.entries[2 * index + 1], e.items + base + ITEMS_PER_CHUNK * nP);
+    emitList(e, node->voxelChunks, nV, numVoxels, level, colorId, &e.entries[2 * index + 1], e.items + base + nP);
 }
 
 // LOD cut (render.cu:906-933), one thread per node: the indices of the nodes to draw
@@ -332,7 +320,9 @@ __device__ void emitVisible(const EmitCtx& e, const uint32_t* visList, uint32_t 
     for (uint32_t v = warp; v < numVisible; v += numWarps) emitNode(e, &e.nodes[visList[v]]);
 }
 
-// one pass over the frame's items: persistent warps pop chunk items with a single atomicAdd each
+// one pass over the frame's items: persistent warps pop chunk items with a single atomicAdd each.
+// (Measured and rejected, profiles/r02/render_notes.md: quarter-chunk items, 2 / 4 warps per item on small frames, the next
+// pop prefetched under the current item, four sample loads in flight per lane — each within 3 % of this loop or slower.)
 template <typename F>
 __device__ __forceinline__ void forEachSample(const uint8_t* heapBase, const WorkItem* items, uint32_t numItems, uint32_t* head, F&& f) {
     const uint32_t lane = laneId();
@@ -345,14 +335,7 @@ __device__ __forceinline__ void forEachSample(const uint8_t* heapBase, const Wor
         if (w == ITEM_EMPTY || w == 0) continue;
         const uint4* pts = itemSamples(heapBase, w);
         const uint32_t count = itemCount(w), level = itemLevel(w), colorId = itemColorId(w);
-        // <= 250 samples: 8 per lane, loaded four at a time so that the loads (and the framebuffer probes behind them) overlap
-        for (uint32_t i0 = lane; i0 < count; i0 += 128) {
-            uint4 p[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) if (i0 + 32u * u < count) p[u] = pts[i0 + 32u * u];
-#pragma unroll
-            for (int u = 0; u < 4; u++) if (i0 + 32u * u < count) f(p[u], level, colorId);
-        }
+        for (uint32_t i = lane; i < count; i += 32) f(pts[i], level, colorId);
     }
 }
 

@@ -112,7 +112,7 @@ r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3",
                     os.path.join(ROOT, "simlod_b200", "csrc", "construct.cu")], capture_output=True, text=True)
 if r.returncode != 0:
     print("timers build failed:", r.stderr[-300:]); timed = None
-SUBS = ["f.alloc", "f.count", "f.wait", "f.flush", "f.insert", "f.barrier", "s.work", "s.barrier", "r.items", "r.flush", "r.barrier", "f.top", "-", "r.loop(warp0)"]
+SUBS = ["f.alloc", "f.count", "f.wait", "f.flush", "f.insert", "f.barrier", "s.work", "s.barrier", "r.items", "r.flush", "r.barrier", "f.top", "r.setup", "r.listed", "r.spilled"]
 for K in sizes:
     n = K * BATCH
     dptr = sim.device_alloc(n * 16)
@@ -139,7 +139,6 @@ for K in sizes:
         if ph.sum() > 0:
             print("   us/batch %s | rounds/batch %.2f" % ({k: round(float(v) / 1e3 / K, 1) for k, v in zip(PHASES, ph) if k != "rounds(count)"}, ph[6] / K), flush=True)
             print("   block 0 timeline, us/batch:", {k: round(float(v) / 1e3 / K, 1) for k, v in zip(SUBS, sub)}, flush=True)
-            print("   re-walk item space per batch: %.0f items, of which %.0f in affected runs" % (sub[14] / K, sub[15] / K), flush=True)
         if timed is None:
             break
     sim.use_module(0, None)
