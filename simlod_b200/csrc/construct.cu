@@ -99,6 +99,7 @@ enum : uint32_t {   // Ctl::errorFlags, mirrored into Stats::dbg. Sticky: cleare
     ERR_SPILLNODE_OVERFLOW = 1u << 5,
     ERR_ROW_OVERFLOW    = 1u << 6,   // more than ROW_CAP non-empty leaves, or a leaf with more than 64 chunks: points were dropped
     ERR_FAR_POINT       = 1u << 7,   // a point further than 16 cube edges outside the box (its 2^28 and 2^20 quantisations disagree)
+    ERR_INTERNAL        = 1u << 8,   // an invariant of the builder itself was violated (never seen; reported rather than ignored)
 };
 
 struct BatchCounters {              // one set per batch, index = batch % 3; the idle set is cleared during the phase before its use
@@ -132,10 +133,15 @@ struct Ctl {
     uint64_t launchClock[32][2];   // %globaltimer at the start / end of the last 32 launches (slot = launchCount % 32): launch gaps as the device sees them
     uint32_t launchCount, _pad2[3];
     uint64_t subNanos[16];         // @800
+                                   //      block 0's own timeline inside the phases (developer aid): fused = 0 allocate, 1 count+sample, 2 wait for the
+                                   //      allocation, 3 flush, 4 insert, 5 barrier; split = 6 work, 7 barrier; re-walk = 8 items, 9 flush, 10 barrier;
+                                   //      11 top of the batch loop, 12-14 re-walk set-up / listed items / spilled points
     struct Worklist { uint32_t cursor[2]; uint32_t legacy; uint32_t pad; } wl[3];      // @928 per batch (index = batch % 3): entries of the list of
-                                   //      round r (cursor[r & 1]); legacy != 0: some block could not name its items, rounds scan the affected runs block 0's own timeline inside the phases (developer aid): fused = 0 allocate, 1 count+sample, 2 wait for the
-                                   //      allocation, 3 flush, 4 insert, 5 barrier; split = 6 work, 7 barrier; re-walk = 8 items, 9 flush, 10 barrier; 11 top of the batch loop, 12 re-walk list
+                                   //      round r (cursor[r & 1]); legacy != 0: some block could not name its items, rounds scan the affected runs
+    uint32_t events[4];            // @976 since the last reset: re-walk rounds run in legacy mode, warps that counted globally for lack of list room,
+                                   //      table-full global counts, splits refused
 };
+static_assert(offsetof(Ctl, events) == 976, "tools read Ctl by offset");
 static_assert(offsetof(Ctl, spilledTotal) == 80, "bench.py reads Ctl::spilledTotal at byte 80");
 static_assert(offsetof(Ctl, phaseNanos) == 96 && offsetof(Ctl, batch) == 160 && offsetof(Ctl, allocDone) == 256 && offsetof(Ctl, launchClock) == 272 && offsetof(Ctl, launchCount) == 784 && offsetof(Ctl, subNanos) == 800, "tools read Ctl by offset");
 
@@ -210,6 +216,7 @@ __device__ __forceinline__ uint64_t ldv(const uint64_t* p) { uint64_t v; asm vol
 __device__ __forceinline__ uint32_t ldcg(const uint32_t* p) { uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 __device__ __forceinline__ uint32_t ldAcquire(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31; }
+__device__ __forceinline__ bool first_in_grid() { return blockIdx.x == 0 && threadIdx.x == 0; }
 __device__ __forceinline__ uint32_t lanemaskLt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 __device__ __forceinline__ uint64_t globaltimer() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
@@ -545,6 +552,7 @@ __device__ __noinline__ uint32_t countGlobal(const Ctx c, const Batch b, uint32_
         }
         if (err) {
             atomicOr(&c.ctl()->errorFlags, err);
+            atomicAdd(&c.ctl()->events[3], 1u);
             atomicExch(&c.splitState()[node], 0u);
         } else {
             SpillInfo info;
@@ -578,7 +586,10 @@ struct LeafCache { uint32_t node, level, kx, ky, kz, parent; };      // node == 
 
 // count (voxels.cu:203-218, doCounting::countPoint): the lanes of a warp that reached the same leaf take consecutive ranks
 // from the block's table (or, when the table or the block's item list is full, final slots from the global counter).
-// Warp-collective; returns the lane's slot word.
+// Warp-collective; returns the lane's slot word. `bloom`: the filter of the run the lane's item belongs to (none for
+// spilled points). MIXED_RUNS: the lanes' items may come from different runs (the worklist concatenates the blocks'
+// segments, so a warp's granule can straddle two of them) — every run gets the leaf, not only the leader's.
+template <bool MIXED_RUNS = false>
 __device__ __forceinline__ uint32_t countInto(const Ctx& c, const Batch& b, bool valid, uint32_t node, uint32_t level, uint32_t* bloom, bool forceGlobal) {
     const uint32_t lane = laneId();
     uint32_t slot = 0;
@@ -591,11 +602,15 @@ __device__ __forceinline__ uint32_t countInto(const Ctx& c, const Batch& b, bool
         if (lane == leader) {
             uint32_t t = forceGlobal ? VOXTAB_EMPTY : tabInsert(sh_leafKey, node);
             if (t != VOXTAB_EMPTY) { r = atomicAdd(&sh_leafCount[t], cnt) | PROVISIONAL | (t << 24); sh_leafLevel[t] = (uint8_t)level; }   // block-local rank
-            else                 { r = countGlobal(c, b, node, level, cnt); sh_blockLegacy = 1; }   // table (or list) full: final slot at once
+            else                 { r = countGlobal(c, b, node, level, cnt); sh_blockLegacy = 1; if (!forceGlobal) atomicAdd(&c.ctl()->events[2], 1u); }   // table (or list) full: final slot at once
             if (bloom) bloomAdd(bloom, node);
         }
         r = __shfl_sync(peers, r, leader);
         slot = r + __popc(peers & lanemaskLt());
+        if (MIXED_RUNS) {
+            const uint64_t leaderBloom = __shfl_sync(peers, (uint64_t)(uintptr_t)bloom, leader);
+            if (bloom && (uint64_t)(uintptr_t)bloom != leaderBloom) bloomAdd(bloom, node);
+        }
     }
     return slot;
 }
@@ -772,7 +787,11 @@ static_assert(sizeof(sh_tile) >= LIST_CAP * 8, "the explicit item list must fit 
 __device__ void buildWorklist(const Ctx& c, const Batch& b, uint32_t spillBegin, uint32_t spillEnd, uint32_t round) {
     Ctl::Worklist* w = &c.ctl()->wl[b.index % 3u];
     const uint32_t numSplit = spillEnd - spillBegin;
+#ifdef SIMLOD_NO_WORKLIST
+    if (true) {                                                         // developer knob: every round scans the affected runs
+#else
     if (numSplit > 64u || sh_blockLegacy != 0) {                       // block-uniform
+#endif
         if (threadIdx.x == 0) atomicExch(&w->legacy, 1u);
         return;
     }
@@ -903,6 +922,7 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
                 if (laneId() == 0) k0 = atomicAdd(&sh_listCount, (uint32_t)__popc(vmask));
                 k0 = __shfl_sync(0xffffffffu, k0, 0);
                 forceGlobal = k0 + __popc(vmask) > LIST_CAP;
+                if (forceGlobal && laneId() == 0) atomicAdd(&c.ctl()->events[1], 1u);
                 return k0 + __popc(vmask & lanemaskLt());
             };
             auto remember = [&](uint32_t i, uint32_t lp, uint32_t slot, uint32_t myk, bool forceGlobal) {
@@ -914,27 +934,36 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
                 }
             };
             RW_DONE(12);
-            // ---- (1) the items the split phase named (buildWorklist): batch points, and points spilled in earlier rounds ------
+            // ---- (1) the items the split phase named (buildWorklist): batch points, and points spilled in earlier rounds. Each sits
+            // in a leaf that was split in THIS round (that is how it got on the list), so the step down is the same as in (2):
+            // the leaf's record gives the children and the only grid to sample
             for (uint32_t base = rewalkFirstGranule(); base < numListed; base += rewalkGranuleStride()) {
                 const uint32_t u = base + laneId();
                 bool valid = u < numListed;
                 const uint32_t i = valid ? wl[u] : 0u;
                 const bool spilledItem = valid && i >= scratch::MAX_BATCH;
                 uint4 pt = make_uint4(0, 0, 0, 0);
-                uint32_t node = 0, level = 0;
+                uint32_t node = 0, level = 0, childBase = 0;
                 if (valid) {
                     pt = spilledItem ? *reinterpret_cast<const uint4*>(c.spilled() + (i - scratch::MAX_BATCH)) : ldPoint(b.points + i);
                     const uint32_t lp = leafOf[i];
                     node = lp & 0xffffffu; level = lp >> 24;
-                    valid = level < SIMLOD_MAX_DEPTH;                    // a level-20 node is the leaf even after it "split" (voxels.cu:169)
+                    uint32_t k = 0;
+                    while (k < numSplit && sh_splitInfo[k].node != node) k++;
+                    if (k < numSplit) childBase = sh_splitInfo[k].childBase;
+                    else { valid = false; atomicOr(&c.ctl()->errorFlags, ERR_INTERNAL); }      // cannot happen: listed items sit in split leaves
+                    valid = valid && level < SIMLOD_MAX_DEPTH;               // a level-20 node is the leaf even after it "split" (voxels.cu:169)
                 }
                 if (!__any_sync(0xffffffffu, valid)) continue;
                 bool forceGlobal;
                 const uint32_t myk = reserve(valid, forceGlobal);
-                uint32_t lp = 0, slot = 0;
-                walk<SAMPLE, COUNT, UNCACHED_GRID, false>(c, b, cache, valid, pt, node, level, level,
-                                                         valid && !spilledItem ? c.runBloom() + (i / perRun) * BLOOM_WORDS : nullptr, forceGlobal, lp, slot);
-                if (valid && COUNT) remember(i, lp, slot, myk, forceGlobal);
+                const Coords q = quantize(c, pt);
+                const uint32_t child = childBase + childIndexAt(q, level);
+                if (SAMPLE && valid) sampleUp<UNCACHED_GRID, false>(c, b, q, pt.w, node, level, level);
+                __syncwarp();
+                uint32_t slot = 0;
+                if (COUNT) slot = countInto<true>(c, b, valid, child, level + 1, valid && !spilledItem ? c.runBloom() + (i / perRun) * BLOOM_WORDS : nullptr, forceGlobal);
+                if (valid && COUNT) remember(i, child | ((level + 1) << 24), slot, myk, forceGlobal);
             }
             RW_DONE(13);
             // ---- (2) the points spilled in this round, leaf by leaf: a warp's 32 points come out of ONE split leaf, whose
@@ -965,6 +994,7 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
             RW_DONE(14);
         } else {
             if (threadIdx.x == 0) sh_blockLegacy = 1;
+            if (first_in_grid()) atomicAdd(&c.ctl()->events[0], 1u);
             // ---- the runs that can hold an item whose leaf was split in the round that just ended: every block published
             // its own run's verdict before the barrier (markAffectedRun), so all blocks build the same list
             if (gridDim.x <= AFFECTED_CAP) {
@@ -1475,6 +1505,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             for (int i = 0; i < 8; i++) ctl->phaseNanos[i] = 0;
             for (int i = 0; i < 16; i++) ctl->subNanos[i] = 0;
             ctl->launchCount = 0;
+            for (int i = 0; i < 4; i++) ctl->events[i] = 0;
             ctl->rowBump = 0; ctl->rowFreeCount = 0;
             c.firstChild()[0] = 0;
             c.parentOf()[0] = 0;

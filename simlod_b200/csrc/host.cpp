@@ -282,7 +282,7 @@ int readStats(SimlodContext* ctx) {
 int checkOverflow(SimlodContext* ctx) {
     // bits 0, 3, 5 (spill buffer, nodes[], split list full) only POSTPONE a split — no sample is lost, the octree stays valid,
     // the bit stays visible in Stats::dbg; bits 1, 2, 4, 6 mean voxels or points were dropped: that is an error
-    const uint32_t flags = ctx->hStats->dbg & 0x56u;
+    const uint32_t flags = ctx->hStats->dbg & 0x156u;    // (bit 8: an internal invariant of the builder failed)
     if (flags) return fail(SIMLOD_ERR_OVERFLOW, "kernel_construct dropped samples: a per-batch capacity was exceeded (Stats::dbg = 0x%x: 2 voxel backlog, 4 chunk directory, 16 chunk stack, 64 leaf rows); reset to clear", ctx->hStats->dbg);
     return SIMLOD_OK;
 }
@@ -823,7 +823,7 @@ int simlod_insert(SimlodContext* ctx, const SimlodPoint* host_points, uint64_t c
 int simlod_insert_device(SimlodContext* ctx, uint64_t device_points, uint64_t count, float* kernel_ms, float* total_ms) {
     if (!device_points && count) return fail(SIMLOD_ERR_INVALID, "null points");
     if (!ctx) return fail(SIMLOD_ERR_INVALID, "null context");
-    if ((device_points & 15ull) != 0) return insertCommon(ctx, nullptr, (CUdeviceptr)device_points, count, kernel_ms, total_ms);    // unaligned source: through the ring
+    if ((device_points & 15ull) != 0 || getenv("SIMLOD_NO_DIRECT") != nullptr) return insertCommon(ctx, nullptr, (CUdeviceptr)device_points, count, kernel_ms, total_ms);    // unaligned source: through the ring
     return insertDeviceDirect(ctx, (CUdeviceptr)device_points, count, kernel_ms, total_ms);
 }
 
