@@ -438,6 +438,76 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bench_merged_octree(sim, dptr, nb_avail, rank, world, dev, barrier):
+    """SURVEY.md §8f-3 beside the batch-sharded headline: ONE octree over the N GPUs. Every rank sends the points of its
+    first 16 batches to the owners of their level-2 cells (fused partition + push kernel over NVLink peer memory,
+    DESIGN.md §9.3), the exchange of group g+1 enqueued before the insertion of group g, and inserts what it receives.
+    Every local step is followed by an agreement (all ranks ok?) before the next collective, so a rank that cannot run it
+    makes all ranks skip the leg instead of hanging the others."""
+    import torch
+    import torch.distributed as dist
+    from simlod_b200 import dist as sdist
+    K, LEVEL, DEPTH = min(16, nb_avail), 2, 8
+
+    def agree(ok):
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
+    err = None
+    try:
+        plan0 = sim.partition_plan(LEVEL, np.zeros(8 ** LEVEL, np.uint8), world)
+        hist = np.zeros(8 ** LEVEL, np.int64)
+        for i in range(K):
+            hist += sim.partition_count(dptr + i * BATCH * 16, BATCH, plan0)[1].astype(np.int64)
+    except Exception as e:
+        err = repr(e)
+    if not agree(err is None):
+        return {"error": err or "another rank failed while planning"}
+    t = torch.tensor(hist, device=dev)
+    dist.all_reduce(t)
+    owners = sdist.plan_owners(t.cpu().numpy(), world)
+    ex = None
+    try:
+        ex = sdist.SpatialExchange(sim, LEVEL, owners, capacity_points=BATCH, depth=DEPTH, mode="p2p", device=torch.device(dev), timeout_ms=5000)
+    except Exception as e:
+        err = repr(e)
+    if not agree(err is None):
+        return {"error": err or "another rank could not set up peer memory"}
+    groups = [[(dptr + i * BATCH * 16, BATCH) for i in range(g0, min(K, g0 + DEPTH))] for g0 in range(0, K, DEPTH)]
+    best, received = None, 0
+    for rep in range(3):
+        try:
+            sim.reset()
+            barrier()
+            t0 = time.perf_counter()
+            ex.prepare([bt for g in groups for bt in g])
+            ex.send_group(groups[0])
+            received = 0
+            for gi in range(len(groups)):
+                ptr, n = ex.wait_group()
+                if gi + 1 < len(groups):
+                    ex.send_group(groups[gi + 1])
+                if n:
+                    sim.insert_device(ptr, n)
+                received += n
+            sim.synchronize()
+        except Exception as e:
+            err = repr(e)
+        if not agree(err is None):
+            return {"error": err or "another rank failed during the exchange"}
+        barrier()
+        dt = sdist.max_over_ranks(time.perf_counter() - t0, dev)
+        best = dt if best is None else min(best, dt)
+    st = sim.stats()
+    tot = sdist.reduce_stats(st, dev)
+    return {"value": round(world * K * BATCH / best / 1e6, 2), "unit": "Mpoints/s",
+            "what": "ONE octree over %d GPUs: %d x 1M-point batches per GPU exchanged by owner of the level-%d cell (fused partition + push over NVLink peer memory, groups of %d batches, "
+                    "exchange of group g+1 under the insertion of group g) and inserted; host clock around barriers, best of 3, planning window included" % (world, K, LEVEL, DEPTH),
+            "points_total": world * K * BATCH, "numPoints_all_ranks": tot["numPoints"], "all_points_arrived": tot["numPoints"] == world * K * BATCH,
+            "received_this_rank": int(received), "bit_exactness": "tests/test_merged_octree.py, tools/bench_merged.py (every rank's octree vs a local rebuild)"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -550,6 +620,16 @@ def main():
             nb_s = min(16, NB)
             raw = sim.memcpy_dtoh(dptr, nb_s * BATCH * 16).view(data.POINT_DTYPE)
             sample_batches = [raw[i * BATCH:(i + 1) * BATCH] for i in range(nb_s)]
+        # ---- one octree over the N GPUs, N > 1 only ----------------------------------------
+        merged = None
+        if world > 1 and not args.no_extras:
+            t0 = time.time()
+            try:
+                sim.set_box(mn, mx)
+                merged = bench_merged_octree(sim, dptr, NB, rank, world, dev, barrier)
+            except Exception as e:
+                merged = {"error": repr(e)}
+            windows.append((t0, time.time()))
         sim.device_free(dptr)
         sim.host_free(host_ptr)
 
@@ -650,6 +730,8 @@ def main():
             line["render"] = render
         if config4:
             line["config4"] = config4
+        if merged:
+            line["merged_octree"] = merged
         if las:
             line["las_decode"] = las
         if stream:

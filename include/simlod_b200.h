@@ -30,6 +30,19 @@ enum {
     SIMLOD_ERR_OVERFLOW      = -6,   // kernel_construct exceeded one of its per-batch capacities (Stats::dbg, sticky until the next reset)
 };
 
+enum {  // Stats::dbg after kernel_construct (the reference leaves the field at 0): sticky until the next reset
+    SIMLOD_DBG_SPLIT_POSTPONED_SPILL = 1 << 0,   // > 3 Mi spilled points in one batch: a split waits for the next batch (octree exact, a leaf holds > 50 000 points for now)
+    SIMLOD_DBG_VOXELS_DROPPED        = 1 << 1,   // > 4 Mi voxels created in one batch
+    SIMLOD_DBG_DIRECTORY_FULL        = 1 << 2,   // chunk directory of one batch exhausted: voxels dropped
+    SIMLOD_DBG_SPLIT_POSTPONED_NODES = 1 << 3,   // nodes[] (40 MB = 263 157 nodes) full: a split was refused
+    SIMLOD_DBG_CHUNK_STACK_FULL      = 1 << 4,   // free-chunk stack full: freed chunks leaked
+    SIMLOD_DBG_SPLIT_POSTPONED_COUNT = 1 << 5,   // > 100 000 splits in one batch
+    SIMLOD_DBG_ROWS_FULL             = 1 << 6,   // > 65 536 non-empty leaves at once (or a leaf beyond 64 chunks): points dropped
+    SIMLOD_DBG_FAR_POINT             = 1 << 7,   // informational: a point > 16 cube edges outside the box took the exhaustive sampling path
+    SIMLOD_DBG_INTERNAL              = 1 << 8,   // an invariant of the builder failed
+    SIMLOD_DBG_FATAL_MASK            = 0x156,    // the bits for which simlod_update_octree / simlod_insert* return SIMLOD_ERR_OVERFLOW
+};
+
 enum {  // the three CUDA programs of main_progressive_octree.cpp:603-626
     SIMLOD_PROGRAM_CONSTRUCT = 0,    // exports kernel_construct
     SIMLOD_PROGRAM_RENDER    = 1,    // exports kernel_render

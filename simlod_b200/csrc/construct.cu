@@ -140,7 +140,11 @@ struct Ctl {
                                    //      round r (cursor[r & 1]); legacy != 0: some block could not name its items, rounds scan the affected runs
     uint32_t events[4];            // @976 since the last reset: re-walk rounds run in legacy mode, warps that counted globally for lack of list room,
                                    //      table-full global counts, splits refused
+    uint64_t elapsedByParity[2];   // @992 launch time at the end of the fused phase of the last even / odd batch (read by the snapshots of that batch)
+    uint64_t roundHist[12][4];     // @1008 timers build: re-walk rounds by size class (class = bit length of listed + spilled items, / 2, capped):
+                                   //       rounds, nanoseconds (split + re-walk), listed items, spilled items of the round
 };
+static_assert(offsetof(Ctl, roundHist) == 1008 && sizeof(Ctl) <= 4096, "tools read Ctl by offset; the control block is 4 KB");
 static_assert(offsetof(Ctl, events) == 976, "tools read Ctl by offset");
 static_assert(offsetof(Ctl, spilledTotal) == 80, "bench.py reads Ctl::spilledTotal at byte 80");
 static_assert(offsetof(Ctl, phaseNanos) == 96 && offsetof(Ctl, batch) == 160 && offsetof(Ctl, allocDone) == 256 && offsetof(Ctl, launchClock) == 272 && offsetof(Ctl, launchCount) == 784 && offsetof(Ctl, subNanos) == 800, "tools read Ctl by offset");
@@ -460,6 +464,7 @@ __shared__ uint32_t sh_splitNodes[64];
 __shared__ SpillInfo sh_splitInfo[64];       // the leaves split in the current round (worklist rounds: at most 64) ...
 __shared__ uint32_t sh_splitGranule[65];     // ... and the running number of 32-point granules of their spilled points
 __shared__ uint32_t sh_wlCount, sh_wlBase, sh_wlFill;
+__shared__ uint32_t sh_roundLegacy, sh_roundListed;     // the round's worklist state, loaded once per block after the split barrier
 // block-wide exclusive prefix sum of one value per thread (256 threads); returns the block total
 __device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t& total) {
     __shared__ uint32_t sh_warpSum[8];
@@ -717,6 +722,12 @@ __device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& ca
 // walks the current one, so the HBM latency of the batch read leaves the critical path and no
 // registers or LSU slots are spent on it. Threads then read their point with one LDS.128.
 // ------------------------------------------------------------------------------------------
+#ifndef SIMLOD_REWALK_DEDUP
+#define SIMLOD_REWALK_DEDUP 0          // tuning knobs (tools/exp_variants.py): one atomicOr per distinct cell among a warp's re-walked items;
+#endif
+#ifndef SIMLOD_REWALK_L2TEST
+#define SIMLOD_REWALK_L2TEST 0         // pre-test the freshly cleared grids of a re-walk through L2 instead of L1
+#endif
 #ifndef SIMLOD_TILE_POINTS
 #define SIMLOD_TILE_POINTS 512         // tuning knob: a multiple of 256
 #endif
@@ -893,10 +904,9 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
         if (threadIdx.x == 0) { sh_tilePhase[0] = ph0; sh_tilePhase[1] = ph1; }
         if (COUNT && threadIdx.x < BLOOM_WORDS) c.runBloom()[blockIdx.x * BLOOM_WORDS + threadIdx.x] = sh_runBloom[threadIdx.x];
     } else {
-        Ctl::Worklist* w = &c.ctl()->wl[b.index % 3u];
-        if (ldcg(&w->legacy) == 0) {
+        if (sh_roundLegacy == 0) {
             // ---- the items the split phase named (buildWorklist), then the points spilled in this round ---------------------
-            const uint32_t numListed = min(ldcg(&w->cursor[round & 1u]), (uint32_t)scratch::WL_CAP);
+            const uint32_t numListed = min(sh_roundListed, (uint32_t)scratch::WL_CAP);
             const uint32_t perRun = ((b.size + gridDim.x - 1) / gridDim.x + 31u) & ~31u;
             const uint32_t* wl = c.worklist();
             const uint32_t numSplit = spillEnd - spillBegin;                      // <= 64 in worklist rounds
@@ -959,7 +969,7 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
                 const uint32_t myk = reserve(valid, forceGlobal);
                 const Coords q = quantize(c, pt);
                 const uint32_t child = childBase + childIndexAt(q, level);
-                if (SAMPLE && valid) sampleUp<UNCACHED_GRID, false>(c, b, q, pt.w, node, level, level);
+                if (SAMPLE && valid) sampleUp<UNCACHED_GRID || SIMLOD_REWALK_L2TEST, SIMLOD_REWALK_DEDUP>(c, b, q, pt.w, node, level, level);
                 __syncwarp();
                 uint32_t slot = 0;
                 if (COUNT) slot = countInto<true>(c, b, valid, child, level + 1, valid && !spilledItem ? c.runBloom() + (i / perRun) * BLOOM_WORDS : nullptr, forceGlobal);
@@ -985,7 +995,7 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
                 const uint32_t myk = reserve(valid, forceGlobal);
                 const Coords q = quantize(c, pt);
                 const uint32_t child = childBase + childIndexAt(q, level);
-                if (SAMPLE && valid) sampleUp<UNCACHED_GRID, false>(c, b, q, pt.w, node, level, level);
+                if (SAMPLE && valid) sampleUp<UNCACHED_GRID || SIMLOD_REWALK_L2TEST, SIMLOD_REWALK_DEDUP>(c, b, q, pt.w, node, level, level);
                 __syncwarp();
                 uint32_t slot = 0;
                 if (COUNT) slot = countInto(c, b, valid, child, level + 1, nullptr, forceGlobal);
@@ -1073,7 +1083,7 @@ __device__ __forceinline__ void passFlush(const Ctx& c, const Batch& b, uint32_t
             } else {
                 for (uint32_t i = blockFirst + threadIdx.x; i < blockEnd; i += blockDim.x) { uint32_t sl = slotOf[i]; if (sl & PROVISIONAL) slotOf[i] = finalSlot(sl); }
             }
-        } else if (ldcg(&c.ctl()->wl[b.index % 3u].legacy) == 0) {        // the items this block visited in passItems: its list
+        } else if (sh_roundLegacy == 0) {                                 // the items this block visited in passItems: its list
             const uint32_t n = min(sh_listCount, LIST_CAP);
             const uint32_t* li = listItem();
             const uint32_t* ls = listSlot();
@@ -1435,6 +1445,34 @@ __device__ __noinline__ void insertAll(const Ctx c, const Batch b, uint32_t numS
     __syncthreads();
 }
 
+// The control words every thread needs right after a grid barrier (this batch's counters, the clock, the heap mark, the
+// next batch's size). 4 736 warps loading the same few L2 lines one dependent load after the other cost several µs per
+// batch; instead one thread per block loads all of them at once (independent loads, two of them 16 bytes wide) and the
+// block reads them from shared memory.
+struct Snapshot {
+    uint32_t numSpillTotal, numSpilled, numBacklog, numDirtyLeaves, numDirtyVox, dirCursor, voxelsCreated, insertCursor;
+    uint32_t rootFirstChild, nextBatchSize;
+    uint64_t elapsedNanos, memUsed;
+};
+__shared__ Snapshot sh_snap;
+__device__ __forceinline__ void takeSnapshot(const Ctx& c, const BatchCounters* bc, uint32_t parity, const uint32_t* nextBatchSize) {
+    if (threadIdx.x == 0) {
+        uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "l"(bc) : "memory");
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "l"(reinterpret_cast<const uint8_t*>(bc) + 16) : "memory");
+        const uint64_t el = ldv(&c.ctl()->elapsedByParity[parity]), mu = ldv(&c.ctl()->memUsed);
+        const uint32_t fc = ldv(&c.firstChild()[0]);
+        const uint32_t nb = nextBatchSize ? ldv(nextBatchSize) : 0u;
+        Snapshot sn;
+        sn.numSpillTotal = a0; sn.numSpilled = a1; sn.numBacklog = a2; sn.numDirtyLeaves = a3; sn.numDirtyVox = b0; sn.dirCursor = b1; sn.voxelsCreated = b2; sn.insertCursor = b3;
+        sn.rootFirstChild = fc; sn.nextBatchSize = nb; sn.elapsedNanos = el; sn.memUsed = mu;
+        sh_snap = sn;
+    }
+    __syncthreads();
+}
+static_assert(offsetof(BatchCounters, numSpilled) == 4 && offsetof(BatchCounters, numBacklog) == 8 && offsetof(BatchCounters, numDirtyLeaves) == 12 &&
+              offsetof(BatchCounters, numDirtyVox) == 16 && offsetof(BatchCounters, voxelsCreated) == 24 && sizeof(BatchCounters) == 32, "takeSnapshot reads BatchCounters as two 16-byte quads");
+
 __device__ __forceinline__ void clearWorklist(Ctl::Worklist* w) { w->cursor[0] = 0; w->cursor[1] = 0; w->legacy = 0; }
 __device__ __forceinline__ void clearBatchCounters(BatchCounters* b) {
     b->numSpillTotal = 0; b->numSpilled = 0; b->numBacklog = 0; b->numDirtyLeaves = 0; b->numDirtyVox = 0; b->dirCursor = 0; b->voxelsCreated = 0; b->insertCursor = 0;
@@ -1494,7 +1532,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
     if (first) {
         *frameStartTimestamp = tStart;
         ctl->numBatchesUploaded = *(volatile uint32_t*)numBatchesUploaded_volatile;   // one snapshot for all threads
-        ctl->elapsedNanos = 0;
+        ctl->elapsedNanos = 0; ctl->elapsedByParity[0] = 0; ctl->elapsedByParity[1] = 0;
         ctl->memUsed = c.heap()->offset;
         ctl->allocDone = 0;
         for (int i = 0; i < 3; i++) { clearBatchCounters(&ctl->batch[i]); clearWorklist(&ctl->wl[i]); }
@@ -1506,6 +1544,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             for (int i = 0; i < 16; i++) ctl->subNanos[i] = 0;
             ctl->launchCount = 0;
             for (int i = 0; i < 4; i++) ctl->events[i] = 0;
+            for (int i = 0; i < 12; i++) for (int j = 0; j < 4; j++) ctl->roundHist[i][j] = 0;
             ctl->rowBump = 0; ctl->rowFreeCount = 0;
             c.firstChild()[0] = 0;
             c.parentOf()[0] = 0;
@@ -1540,25 +1579,32 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
 
     bool havePending = false;          // a counted batch whose allocation + insertion has not run yet
     Batch pending{};
-    uint32_t pendingSpilled = 0;
+    uint32_t pendingSpilled = 0, pendingBacklog = 0;
+    uint64_t pendingBound = 0;         // upper bound of what the pending batch's allocation can still take from the heap (voxels.cu:896-912
+                                       // evaluates the capacity guard with that batch already allocated)
     uint32_t allocEpochs = 0;          // in-phase allocations of this launch so far
+    auto slotSize = [&](uint32_t batchIndex) { return &batchSizes[batchIndex % SIMLOD_BATCH_STREAM_SIZE]; };
 
+    if (numBatches > 0) takeSnapshot(c, &ctl->batch[firstBatch % 3u], firstBatch & 1u, slotSize(firstBatch));
     for (uint32_t batchIndex = firstBatch; batchIndex < lastBatch; batchIndex++) {
+        // (sh_snap: taken after the last barrier — heap mark, clock, root state, this batch's size)
         Batch b;
         const uint32_t ringSlot = batchIndex % SIMLOD_BATCH_STREAM_SIZE;
-        b.size = min(ldv(&batchSizes[ringSlot]), (uint32_t)SIMLOD_MAX_BATCH_SIZE);
+        b.size = min(sh_snap.nextBatchSize, (uint32_t)SIMLOD_MAX_BATCH_SIZE);
         b.points = points + (uint64_t)ringSlot * SIMLOD_MAX_BATCH_SIZE;
         b.index = batchIndex;
         b.parity = batchIndex & 1u;
         b.bc = &ctl->batch[batchIndex % 3u];
 
         // capacity guard (voxels.cu:896-912): stop consuming batches 200 MB before the heap is full
-        const uint64_t memUsed = ldv(&ctl->memUsed) + (havePending ? pendingAllocationBound(pending) : 0ull);
+        const uint64_t memUsed = sh_snap.memUsed + (havePending ? pendingBound : 0ull);
         const bool memCapacityReached = memUsed + 200000000ull >= uniforms.persistentBufferCapacity;
         if (first) stats->memCapacityReached = memCapacityReached ? 1 : 0;
         if (memCapacityReached) break;
 
-        const bool deferSampling = ldv(&c.firstChild()[0]) == 0;    // root still a leaf: see DESIGN.md §4 (root grid is wiped when it splits)
+        const bool deferSampling = sh_snap.rootFirstChild == 0;    // root still a leaf: see DESIGN.md §4 (root grid is wiped when it splits)
+        const float elapsedMs = float(sh_snap.elapsedNanos) / 1000000.0f;
+        if (batchIndex > firstBatch && elapsedMs > 10.0f) break;   // MAX_PROCESSING_TIME (voxels.cu:22,940), as of the end of the previous batch's fused phase
 
         // ---- fused phase: allocate b-1 | count (+ sample) b | insert b-1 ------------------------------
         SUB_DONE(11);
@@ -1582,21 +1628,26 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         SUB_DONE(3);
         if (havePending) {
             if (first) finishBatchBookkeeping(c, pending, tStart);          // all allocations of b-1 are complete (waitAllocBlock)
-            insertAll(c, pending, pendingSpilled, min(ldv(&pending.bc->numBacklog), (uint32_t)scratch::VOXEL_SHARED));
+            insertAll(c, pending, pendingSpilled, pendingBacklog);
             if (threadIdx.x == 0) sh_allocTarget = 0;
             havePending = false;
         }
-        if (first) ctl->elapsedNanos = globaltimer() - tStart;
+        if (first) { const uint64_t el = globaltimer() - tStart; ctl->elapsedNanos = el; ctl->elapsedByParity[b.parity] = el; }
         SUB_DONE(4);
         grid.sync();
+        const uint32_t* nextSize = batchIndex + 1 < lastBatch ? slotSize(batchIndex + 1) : nullptr;
+        takeSnapshot(c, b.bc, b.parity, nextSize);
         SUB_DONE(5);
         PHASE_DONE(0);
 
         // ---- split rounds (voxels.cu:385-415 expand): 2 barriers each ------------------------
         uint32_t spillBegin = 0, spilledBefore = 0;
         for (int round = 0; round < 24; round++) {
-            const uint32_t spillEnd = min(ldv(&b.bc->numSpillTotal), (uint32_t)scratch::SPILLNODE_CAP);
+            const uint32_t spillEnd = min(sh_snap.numSpillTotal, (uint32_t)scratch::SPILLNODE_CAP);
             if (spillEnd == spillBegin) break;
+#if SIMLOD_TIMERS >= 2
+            const uint64_t tRound = first ? globaltimer() : 0ull;
+#endif
             markAffectedRun(c, b, spillBegin, spillEnd);
             buildWorklist(c, b, spillBegin, spillEnd, (uint32_t)round);
             splitRound(c, b, spillBegin, spillEnd);
@@ -1607,8 +1658,14 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
 #if SIMLOD_TIMERS >= 1
             if (first) ctl->phaseNanos[6] += 1;
 #endif
-            const uint32_t numSpilled = min(ldv(&b.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
+            const uint32_t numSpilled = min(sh_snap.numSpilled, (uint32_t)scratch::SPILL_CAP);     // (reserved when the split was requested: final since the snapshot)
+            if (threadIdx.x == 0) {
+                Ctl::Worklist* w = &ctl->wl[b.index % 3u];
+                const uint32_t lg = ldv(&w->legacy), nl = ldv(&w->cursor[round & 1]);
+                sh_roundLegacy = lg; sh_roundListed = nl;
+            }
             if (first) ctl->wl[b.index % 3u].cursor[(round + 1) & 1] = 0;       // the list of the previous round has been consumed
+            __syncthreads();
             if (deferSampling) passItems<false, true, false, false>(c, b, numSpilled, spilledBefore, (uint32_t)round, spillBegin, spillEnd);
             else               passItems<true, true, false, false>(c, b, numSpilled, spilledBefore, (uint32_t)round, spillBegin, spillEnd);
             SUB_DONE(8);
@@ -1616,25 +1673,34 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
             else               passFlush<true, true, false>(c, b, numSpilled, spilledBefore);
             SUB_DONE(9);
             grid.sync();
+#if SIMLOD_TIMERS >= 2
+            if (first) {
+                const uint32_t listed = sh_roundLegacy ? 0u : min(sh_roundListed, (uint32_t)scratch::WL_CAP), moved = numSpilled - spilledBefore;
+                const uint32_t cls = min(11u, (32u - (uint32_t)__clz(listed + moved)) / 2u);
+                ctl->roundHist[cls][0] += 1; ctl->roundHist[cls][1] += globaltimer() - tRound; ctl->roundHist[cls][2] += listed; ctl->roundHist[cls][3] += moved;
+            }
+#endif
+            takeSnapshot(c, b.bc, b.parity, nextSize);
             SUB_DONE(10);
             PHASE_DONE(2);
             spillBegin = spillEnd;
             spilledBefore = numSpilled;
         }
-        const uint32_t numSpilled = min(ldv(&b.bc->numSpilled), (uint32_t)scratch::SPILL_CAP);
+        const uint32_t numSpilled = min(sh_snap.numSpilled, (uint32_t)scratch::SPILL_CAP);
         if (deferSampling) {
             // the root was a leaf when the batch started: sample along the final paths, as the reference does after
             // expand() (voxels.cu:738-742). The root's grid may just have been cleared in place: probe it through L2.
             passItems<true, false, true, true>(c, b, numSpilled, 0, 0);
             passFlush<true, false, true>(c, b, numSpilled, 0);
             grid.sync();
+            takeSnapshot(c, b.bc, b.parity, nextSize);
             PHASE_DONE(3);
         }
         havePending = true;
         pending = b;
         pendingSpilled = numSpilled;
-        const float elapsedMs = float(ldv(&ctl->elapsedNanos)) / 1000000.0f;
-        if (elapsedMs > 10.0f) break;          // MAX_PROCESSING_TIME (voxels.cu:22,940)
+        pendingBacklog = min(sh_snap.numBacklog, (uint32_t)scratch::VOXEL_SHARED);
+        pendingBound = (((uint64_t)b.size + sh_snap.numSpilled + sh_snap.voxelsCreated) / SIMLOD_POINTS_PER_CHUNK + sh_snap.numDirtyLeaves + sh_snap.numDirtyVox + 2) * SIMLOD_CHUNK_STRIDE;
     }
 
     // ---- the last counted batch: allocate, then insert ------------------------------------------
@@ -1643,7 +1709,7 @@ kernel_construct(const Uniforms uniforms, Point* points, uint32_t* buffer, uint8
         grid.sync();
         PHASE_DONE(4);
         if (first) finishBatchBookkeeping(c, pending, tStart);
-        insertAll(c, pending, pendingSpilled, min(ldv(&pending.bc->numBacklog), (uint32_t)scratch::VOXEL_SHARED));
+        insertAll(c, pending, pendingSpilled, pendingBacklog);
     }
 
     // ---- octree statistics (voxels.cu:958-1009), same phase as the last insertion --------------------

@@ -282,8 +282,8 @@ int readStats(SimlodContext* ctx) {
 int checkOverflow(SimlodContext* ctx) {
     // bits 0, 3, 5 (spill buffer, nodes[], split list full) only POSTPONE a split — no sample is lost, the octree stays valid,
     // the bit stays visible in Stats::dbg; bits 1, 2, 4, 6 mean voxels or points were dropped: that is an error
-    const uint32_t flags = ctx->hStats->dbg & 0x156u;    // (bit 8: an internal invariant of the builder failed)
-    if (flags) return fail(SIMLOD_ERR_OVERFLOW, "kernel_construct dropped samples: a per-batch capacity was exceeded (Stats::dbg = 0x%x: 2 voxel backlog, 4 chunk directory, 16 chunk stack, 64 leaf rows); reset to clear", ctx->hStats->dbg);
+    const uint32_t flags = ctx->hStats->dbg & (uint32_t)SIMLOD_DBG_FATAL_MASK;
+    if (flags) return fail(SIMLOD_ERR_OVERFLOW, "kernel_construct dropped samples: a per-batch capacity was exceeded (Stats::dbg = 0x%x: 2 voxel backlog, 4 chunk directory, 16 chunk stack, 64 leaf rows, 256 internal); reset to clear", ctx->hStats->dbg);
     return SIMLOD_OK;
 }
 

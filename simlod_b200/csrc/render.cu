@@ -64,8 +64,16 @@ struct RCtl {
     uint32_t numVisibleNodes, numVisiblePoints, numVisibleVoxels, numVisibleInner, numVisibleLeaves;
     uint32_t overflow;
     uint32_t cacheHits, cacheWalks;      // lists served from the chunk-list cache / walked (developer counters)
-    uint64_t phaseNanos[6];              // @48 last frame, by the grid's first thread: clear|visibility, cut, items, draw (all passes), stats+EDL
+    uint64_t phaseNanos[6];              // @48 last frame, by the grid's first thread: clear|visibility+cut, -, items, draw (all passes), stats+EDL
+    // The cut runs in the first phase of a frame, so its counter cannot be cleared at the start of that frame (no barrier
+    // in between): the previous frame leaves it at 0 and says so with the magic next to it. A buffer that never saw a frame
+    // of this kernel (or was scribbled over since: both words lie inside the reference's first Node copy) takes one
+    // extra barrier. Nobody writes the magic before the last barrier of a frame, so all threads agree on what they read.
+    uint32_t cutCount;                   // @96 drawn nodes of this frame
+    uint32_t cutMagic;                   // @100
 };
+constexpr uint32_t CUT_MAGIC = 0xC07C0DE5u;
+static_assert(offsetof(RCtl, cutCount) == 96 && offsetof(RCtl, cutMagic) == 100, "cutCount / cutMagic are one aligned 8-byte pair");
 static_assert(offsetof(RCtl, cacheHits) == 40 && offsetof(RCtl, phaseNanos) == 48, "tools and tests read RCtl by offset");
 
 // ---- chunk-list cache ---------------------------------------------------------------------------------------
@@ -112,52 +120,86 @@ __device__ __forceinline__ bool planeRejects(float px, float py, float pz, float
     return d < 0.0f;
 }
 
-__device__ void computeVisibilityFlags(const Uniforms& u, Node* nodes, uint32_t numNodes, float cubeSize,
-                                       float cminx, float cminy, float cminz) {
+struct NodeBox { float mn[3], mx[3]; };
+__device__ __forceinline__ NodeBox nodeBox(uint32_t level, uint32_t X, uint32_t Y, uint32_t Z, float cubeSize, float cminx, float cminy, float cminz) {
+    NodeBox bx;
+    float fx = fpx::u2f(X), fy = fpx::u2f(Y), fz = fpx::u2f(Z);
+    float nodeSize = fpx::mul_ftz(cubeSize, fpx::ex2(-fpx::u2f(level)));      // cubeSize / pow(2, level)
+    bx.mn[0] = fpx::fma(nodeSize, fx, cminx); bx.mn[1] = fpx::fma(nodeSize, fy, cminy); bx.mn[2] = fpx::fma(nodeSize, fz, cminz);
+    bx.mx[0] = fpx::fma(nodeSize, fpx::add(fx, 1.0f), cminx); bx.mx[1] = fpx::fma(nodeSize, fpx::add(fy, 1.0f), cminy);
+    bx.mx[2] = fpx::fma(nodeSize, fpx::add(fz, 1.0f), cminz);
+    return bx;
+}
+// screen-space bounding rectangle of the 8 corners larger than 2 x minNodeSize in x or y (render.cu:783-818,880-890): a
+// function of the node's coordinates alone
+__device__ __forceinline__ bool boxIsLarge(const Uniforms& u, const NodeBox& bx) {
     const Row* T = u.transform_updateBound.rows;
+    float sminx = 0, smaxx = 0, sminy = 0, smaxy = 0;
+#pragma unroll
+    for (int corner = 0; corner < 8; corner++) {
+        float x = (corner & 4) ? bx.mx[0] : bx.mn[0];
+        float y = (corner & 2) ? bx.mx[1] : bx.mn[1];
+        float z = (corner & 1) ? bx.mx[2] : bx.mn[2];
+        float w = rowDot(T[3], x, y, z);
+        float rw = fpx::rcp(w);
+        float sx = fpx::mul(u.width, fpx::fma(fpx::mul_ftz(rowDot(T[0], x, y, z), rw), 0.5f, 0.5f));
+        float sy = fpx::mul(u.height, fpx::fma(fpx::mul_ftz(rowDot(T[1], x, y, z), rw), 0.5f, 0.5f));
+        if (corner == 0) { sminx = smaxx = sx; sminy = smaxy = sy; }
+        else { sminx = fminf(sminx, sx); smaxx = fmaxf(smaxx, sx); sminy = fminf(sminy, sy); smaxy = fmaxf(smaxy, sy); }
+    }
+    float dx = fpx::sub(smaxx, sminx), dy = fpx::sub(smaxy, sminy);
+    double limit = 2.0 * (double)u.minNodeSize;
+    return (double)dx > limit || (double)dy > limit;
+}
+// frustum planes rows[3] -+ rows[0..2] (math.cuh:175-182)
+__device__ __forceinline__ bool boxInFrustum(const Uniforms& u, const NodeBox& bx) {
+    const Row* T = u.transform_updateBound.rows;
+    bool inFrustum = true;
+#pragma unroll
+    for (int p = 0; p < 6 && inFrustum; p++) {
+        const Row& a = T[3];
+        const Row& b = T[p == 0 || p == 1 ? 0 : (p == 2 || p == 3 ? 1 : 2)];
+        bool minus = (p == 0 || p == 3 || p == 4);
+        float px = minus ? fpx::sub(a.x, b.x) : fpx::add(a.x, b.x);
+        float py = minus ? fpx::sub(a.y, b.y) : fpx::add(a.y, b.y);
+        float pz = minus ? fpx::sub(a.z, b.z) : fpx::add(a.z, b.z);
+        float pw = minus ? fpx::sub(a.w, b.w) : fpx::add(a.w, b.w);
+        if (planeRejects(px, py, pz, pw, bx.mn[0], bx.mn[1], bx.mn[2], bx.mx[0], bx.mx[1], bx.mx[2])) inFrustum = false;
+    }
+    return inFrustum;
+}
+
+__device__ __forceinline__ bool isLeaf(const Node* node) {
+    bool leaf = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) leaf = leaf && node->children[i] == nullptr;
+    return leaf;
+}
+
+// One thread per node: the node's flags (render.cu:762-901) and, in the same phase, the LOD cut (render.cu:906-933). A
+// node is drawn when it is a visible non-large child of a large node, or a large visible leaf. The parent's `isLarge` is a
+// function of the parent's coordinates (level - 1, X/2, Y/2, Z/2) and the frozen update transform alone, so the child
+// recomputes it instead of waiting for the thread that owns the parent: no barrier between the flags and the cut.
+__device__ void computeVisibilityAndCut(const Uniforms& u, Node* nodes, uint32_t numNodes, float cubeSize,
+                                        float cminx, float cminy, float cminz, RCtl* ctl, uint32_t* visList) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < numNodes; n += stride) {
         Node* node = &nodes[n];
-        uint32_t level = node->level;
-        float fx = fpx::u2f(node->X), fy = fpx::u2f(node->Y), fz = fpx::u2f(node->Z);
-        float nodeSize = fpx::mul_ftz(cubeSize, fpx::ex2(-fpx::u2f(level)));      // cubeSize / pow(2, level)
-        float mn[3] = {fpx::fma(nodeSize, fx, cminx), fpx::fma(nodeSize, fy, cminy), fpx::fma(nodeSize, fz, cminz)};
-        float mx[3] = {fpx::fma(nodeSize, fpx::add(fx, 1.0f), cminx), fpx::fma(nodeSize, fpx::add(fy, 1.0f), cminy),
-                       fpx::fma(nodeSize, fpx::add(fz, 1.0f), cminz)};
-
-        // screen-space bounding rectangle of the 8 corners (render.cu:783-818)
-        float sminx = 0, smaxx = 0, sminy = 0, smaxy = 0;
-#pragma unroll
-        for (int corner = 0; corner < 8; corner++) {
-            float x = (corner & 4) ? mx[0] : mn[0];
-            float y = (corner & 2) ? mx[1] : mn[1];
-            float z = (corner & 1) ? mx[2] : mn[2];
-            float w = rowDot(T[3], x, y, z);
-            float rw = fpx::rcp(w);
-            float sx = fpx::mul(u.width, fpx::fma(fpx::mul_ftz(rowDot(T[0], x, y, z), rw), 0.5f, 0.5f));
-            float sy = fpx::mul(u.height, fpx::fma(fpx::mul_ftz(rowDot(T[1], x, y, z), rw), 0.5f, 0.5f));
-            if (corner == 0) { sminx = smaxx = sx; sminy = smaxy = sy; }
-            else { sminx = fminf(sminx, sx); smaxx = fmaxf(smaxx, sx); sminy = fminf(sminy, sy); smaxy = fmaxf(smaxy, sy); }
+        const uint32_t level = node->level, X = node->X, Y = node->Y, Z = node->Z;
+        const NodeBox bx = nodeBox(level, X, Y, Z, cubeSize, cminx, cminy, cminz);
+        const bool large = boxIsLarge(u, bx);
+        const bool hasSamples = node->numPoints > 0 || node->numVoxels > 0;
+        const bool visible = hasSamples && boxInFrustum(u, bx);
+        node->visible = visible ? 1 : 0;
+        node->isLarge = large ? 1 : 0;
+        if (!visible) continue;
+        bool drawn;
+        if (large) drawn = isLeaf(node);
+        else drawn = level > 0 && boxIsLarge(u, nodeBox(level - 1, X >> 1, Y >> 1, Z >> 1, cubeSize, cminx, cminy, cminz));
+        if (drawn) {
+            uint32_t v = atomicAdd(&ctl->cutCount, 1u);
+            if (v < rbuf::VIS_CAP) visList[v] = n;
         }
-        float dx = fpx::sub(smaxx, sminx), dy = fpx::sub(smaxy, sminy);
-
-        // frustum planes rows[3] -+ rows[0..2] (math.cuh:175-182)
-        bool inFrustum = true;
-#pragma unroll
-        for (int p = 0; p < 6 && inFrustum; p++) {
-            const Row& a = T[3];
-            const Row& b = T[p == 0 || p == 1 ? 0 : (p == 2 || p == 3 ? 1 : 2)];
-            bool minus = (p == 0 || p == 3 || p == 4);
-            float px = minus ? fpx::sub(a.x, b.x) : fpx::add(a.x, b.x);
-            float py = minus ? fpx::sub(a.y, b.y) : fpx::add(a.y, b.y);
-            float pz = minus ? fpx::sub(a.z, b.z) : fpx::add(a.z, b.z);
-            float pw = minus ? fpx::sub(a.w, b.w) : fpx::add(a.w, b.w);
-            if (planeRejects(px, py, pz, pw, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2])) inFrustum = false;
-        }
-        bool hasSamples = node->numPoints > 0 || node->numVoxels > 0;
-        double limit = 2.0 * (double)u.minNodeSize;
-        node->visible = (inFrustum && hasSamples) ? 1 : 0;
-        node->isLarge = ((double)dx > limit || (double)dy > limit) ? 1 : 0;
     }
 }
 
@@ -177,13 +219,6 @@ struct EmitCtx {
     uint64_t* pool;
     uint32_t poolCap;            // 0: cache disabled (render buffer too small for this resolution)
 };
-
-__device__ __forceinline__ bool isLeaf(const Node* node) {
-    bool leaf = true;
-#pragma unroll
-    for (int i = 0; i < 8; i++) leaf = leaf && node->children[i] == nullptr;
-    return leaf;
-}
 
 // Node::getID() % 127 (structures.cuh:116-143, render.cu:74-76), with its arithmetic as compiled: the first nine digits
 // are shifted as 32-bit ints (wrap, then sign-extend into the 64-bit id), the rest as 64-bit values; unused name bytes
@@ -292,26 +327,6 @@ __device__ void emitNode(const EmitCtx& e, const Node* node) {
     emitList(e, node->voxelChunks, nV, numVoxels, level, colorId, &e.entries[2 * index + 1], e.items + base + nP);
 }
 
-// LOD cut (render.cu:906-933), one thread per node: the indices of the nodes to draw
-__device__ void lodCut(RCtl* ctl, uint32_t* visList, const Node* nodes, uint32_t numNodes) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < numNodes; n += stride) {
-        const Node* node = &nodes[n];
-        if (!node->isLarge) continue;
-        if (!isLeaf(node)) {
-            for (int i = 0; i < 8; i++) {
-                const Node* child = node->children[i];
-                if (child == nullptr || child->isLarge || !child->visible) continue;
-                uint32_t v = atomicAdd(&ctl->numVisibleNodes, 1u);
-                if (v < rbuf::VIS_CAP) visList[v] = (uint32_t)(child - nodes);
-            }
-        } else if (node->visible) {
-            uint32_t v = atomicAdd(&ctl->numVisibleNodes, 1u);
-            if (v < rbuf::VIS_CAP) visList[v] = n;
-        }
-    }
-}
-
 // drawn nodes -> chunk items: one WARP per node, the nodes spread over all warps of the grid (drawn nodes cluster in
 // nodes[]: the 8 children of a node are neighbours)
 __device__ void emitVisible(const EmitCtx& e, const uint32_t* visList, uint32_t numVisible) {
@@ -409,12 +424,23 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     ec.heapBase = reinterpret_cast<const uint8_t*>(nodes[0].grid) - 16;
     ec.heapUsed = nodes[0].grid ? *reinterpret_cast<const volatile uint64_t*>(ec.heapBase + 8) : 0ull;
 
+    const bool cutCounterReady = ctl->cutMagic == CUT_MAGIC;      // (see RCtl)
+    // developer timers (tools/render_times.py builds a -DSIMLOD_RENDER_TIMERS=1 variant): off in the shipped build, every warp
+    // pays for the `first` test at each site
+#ifndef SIMLOD_RENDER_TIMERS
+#define SIMLOD_RENDER_TIMERS 0
+#endif
     uint64_t tPhase = globaltimer();
+#if SIMLOD_RENDER_TIMERS
 #define RPHASE(k) do { if (first) { uint64_t _t = globaltimer(); ctl->phaseNanos[k] = _t - tPhase; tPhase = _t; } } while (0)
+#else
+#define RPHASE(k) do { } while (0)
+#endif
     if (first) {
         *frameStartTimestamp = tPhase;
         ctl->numItems = 0; ctl->head[0] = 0; ctl->head[1] = 0; ctl->head[2] = 0;
-        ctl->numVisibleNodes = 0; ctl->numVisiblePoints = 0; ctl->numVisibleVoxels = 0;
+        ctl->numVisiblePoints = 0; ctl->numVisibleVoxels = 0;
+        if (!cutCounterReady) ctl->cutCount = 0;
         ctl->numVisibleInner = 0; ctl->numVisibleLeaves = 0; ctl->overflow = 0;
         ctl->cacheHits = 0; ctl->cacheWalks = 0;
         if (ec.poolCap != 0 && (ec.cache->magic != CACHE_MAGIC || ec.cache->poolCap != ec.poolCap || ec.cache->cursor >= ec.poolCap)) {
@@ -423,7 +449,8 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
             ec.cache->magic = CACHE_MAGIC; ec.cache->cursor = 0; ec.cache->poolCap = ec.poolCap;
         }
     }
-    // ---- phase 1: clear the targets | visibility flags of every node (independent) -------------------------------
+    if (!cutCounterReady) grid.sync();
+    // ---- phase 1: clear the targets | visibility flags of every node + LOD cut (independent) ----------------------
     // clear: depth = +inf (0x7f800000), colour = 0x00332211 (render.cu:1126-1131)
     {
         const uint64_t clearValue = (0x7f800000ull << 32) | 0x00332211ull;
@@ -441,16 +468,14 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     float bsz = fpx::sub(uniforms.boxMax[2], uniforms.boxMin[2]);
     float cubeSize = fmaxf(fmaxf(bsx, bsy), bsz);
     const uint32_t numNodes = min(ldv(&stats->numNodes), (uint32_t)rbuf::NODE_TAB);
-    computeVisibilityFlags(uniforms, nodes, numNodes, cubeSize, uniforms.boxMin[0], uniforms.boxMin[1], uniforms.boxMin[2]);
+    uint32_t* visList = reinterpret_cast<uint32_t*>(base + rbuf::OFF_VISLIST);
+    computeVisibilityAndCut(uniforms, nodes, numNodes, cubeSize, uniforms.boxMin[0], uniforms.boxMin[1], uniforms.boxMin[2], ctl, visList);
     grid.sync();
     RPHASE(0);
-
-    // ---- phase 2: LOD cut; phase 3: chunk items of the drawn nodes -----------------------------------------------
-    uint32_t* visList = reinterpret_cast<uint32_t*>(base + rbuf::OFF_VISLIST);
-    lodCut(ctl, visList, nodes, numNodes);
-    grid.sync();
     RPHASE(1);
-    if (nodes[0].grid != nullptr) emitVisible(ec, visList, min(ldv(&ctl->numVisibleNodes), (uint32_t)rbuf::VIS_CAP));
+
+    // ---- phase 2: chunk items of the drawn nodes ------------------------------------------------------------------
+    if (nodes[0].grid != nullptr) emitVisible(ec, visList, min(ldv(&ctl->cutCount), (uint32_t)rbuf::VIS_CAP));
     grid.sync();
     RPHASE(2);
 
@@ -523,7 +548,8 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     // showBoundingBox is set; it is a debug overlay and not part of this path.
 
     if (first) {      // render.cu:1244-1252
-        stats->numVisibleNodes = ldv(&ctl->numVisibleNodes);
+        stats->numVisibleNodes = ldv(&ctl->cutCount);
+        ctl->cutCount = 0; ctl->cutMagic = CUT_MAGIC;           // for the next frame (nothing reads the counter after the items phase)
         stats->numVisibleInner = ldv(&ctl->numVisibleInner);
         stats->numVisibleLeaves = ldv(&ctl->numVisibleLeaves);
         stats->numVisiblePoints = ldv(&ctl->numVisiblePoints);

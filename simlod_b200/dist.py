@@ -173,8 +173,12 @@ class SpatialExchange:
     back without a host round trip, land contiguously in the receiver (senders in rank order within a batch,
     batches in order) and are acquired with one wait; the receiver then inserts the whole group with one
     simlod_insert_device call, i.e. at the streaming rate of the builder instead of one blocking launch per batch.
-    There are two group regions, used alternately: a sender starts group g+2 only after it has seen every
-    receiver's flags of group g+1, which a receiver releases after it has consumed group g."""
+    A group can also be sent ahead (`send_group` now, `wait_group` later): the scatters of group g+1 are enqueued
+    BEFORE the insertion of group g and acquired after it, so the peers' stores land in this rank's HBM while its SMs
+    build the octree, and the wait finds the flags already there. There are three group regions, used in turn: a
+    sender starts group g+3 only after it has seen every receiver's flags of group g+2, and a receiver's scatter of
+    g+2 (which sets those flags) runs, in stream order, after its insertion of group g — the group that occupied the
+    region g+3 lands in."""
 
     FLAG_BYTES = 4096
 
@@ -188,22 +192,24 @@ class SpatialExchange:
         self.capacity, self.depth = int(capacity_points), int(depth)
         region = self.depth * self.world * self.capacity * 16  # worst case: every sender's whole group lands here
         self.region_bytes = region
+        self.regions = 3
+        self.pending = []                                      # groups sent but not yet acquired: (base, points arriving here, last step)
         self.step = 0                                          # batches sent so far = value of my flag in every receiver
         self.group = 0
         self.prepared = {}                                     # (device_ptr, count) -> G x G matrix of that batch
         if mode == "p2p":
             import torch.distributed._symmetric_memory as symm_mem
-            self.recv = symm_mem.empty(2 * region + self.FLAG_BYTES, dtype=torch.uint8, device=self.device)
+            self.recv = symm_mem.empty(self.regions * region + self.FLAG_BYTES, dtype=torch.uint8, device=self.device)
             self.handle = symm_mem.rendezvous(self.recv, dist.group.WORLD)
             self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
             assert self.peer_ptrs[self.rank] == self.recv.data_ptr()
-            self.recv[2 * region:].zero_()                     # flag words: [sender] u32, monotonically increasing batch numbers
+            self.recv[self.regions * region:].zero_()                     # flag words: [sender] u32, monotonically increasing batch numbers
             torch.cuda.synchronize()
             dist.barrier()
-            self.flag_ptrs = [p + 2 * region + 4 * self.rank for p in self.peer_ptrs]      # my word in every receiver
-            self.local_flags = self.recv.data_ptr() + 2 * region
+            self.flag_ptrs = [p + self.regions * region + 4 * self.rank for p in self.peer_ptrs]      # my word in every receiver
+            self.local_flags = self.recv.data_ptr() + self.regions * region
         elif mode == "nccl":
-            self.recv = torch.empty(2 * region, dtype=torch.uint8, device=self.device)
+            self.recv = torch.empty(self.regions * region, dtype=torch.uint8, device=self.device)
             self.send = torch.empty(self.capacity * 16, dtype=torch.uint8, device=self.device)
         else:
             raise ValueError("mode must be 'p2p' or 'nccl'")
@@ -230,18 +236,19 @@ class SpatialExchange:
         for k, (p, c) in enumerate(batches):
             self.prepared[(int(p), int(c))] = allc[:, k, :]
 
-    def exchange_group(self, batches):
-        """Send the batches [(device_ptr, count)] (at most `depth`) to their owners. Returns (device address, number
-        of points) of what this rank received — contiguous, batches in order, senders in rank order within a batch —
-        valid until the group after next."""
+    def send_group(self, batches):
+        """Enqueue the scatters of the batches [(device_ptr, count)] (at most `depth`) towards their owners and return
+        without waiting for the peers: pair with `wait_group`. At most two groups may be in flight (three regions)."""
         import torch
         if len(batches) > self.depth:
             raise ValueError("group of %d batches exceeds the exchange depth %d" % (len(batches), self.depth))
         if any(c > self.capacity for _, c in batches):
             raise ValueError("a batch exceeds the exchange capacity of %d points" % self.capacity)
+        if len(self.pending) >= self.regions - 1:
+            raise RuntimeError("at most %d groups can be in flight" % (self.regions - 1))
         if any((int(p), int(c)) not in self.prepared for p, c in batches):
             self.prepare(batches)
-        base = (self.group & 1) * self.region_bytes
+        base = (self.group % self.regions) * self.region_bytes
         self.group += 1
         arrived = np.zeros(self.world, dtype=np.int64)         # points every receiver already holds of this group
         for ptr, count in batches:
@@ -258,10 +265,21 @@ class SpatialExchange:
                 all_to_all_points(self.send, self.recv[at:base + self.region_bytes], matrix, self.rank)
                 torch.cuda.current_stream().synchronize()
             arrived += np.asarray(matrix, dtype=np.int64).sum(axis=0)
+        self.pending.append((base, int(arrived[self.rank]), self.step))
+
+    def wait_group(self):
+        """Acquire the oldest group in flight. Returns (device address, number of points) of what this rank received —
+        contiguous, batches in order, senders in rank order within a batch — valid until two more groups have been sent."""
+        base, n, step = self.pending.pop(0)
         if self.mode == "p2p":
-            # flags are batch numbers and every sender's scatters run in stream order: the last value covers the group
-            self.sim.partition_wait(self.local_flags, self.world, self.step, self.timeout_ms)
-        return self.recv.data_ptr() + base, int(arrived[self.rank])
+            # flags are batch numbers and every sender's scatters run in stream order: the group's last value covers it
+            self.sim.partition_wait(self.local_flags, self.world, step, self.timeout_ms)
+        return self.recv.data_ptr() + base, n
+
+    def exchange_group(self, batches):
+        """send_group + wait_group: send the batches and return what this rank received."""
+        self.send_group(batches)
+        return self.wait_group()
 
     def exchange(self, device_ptr, count):
         """One batch (a group of one)."""

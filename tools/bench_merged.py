@@ -63,7 +63,8 @@ def sync_all():
 
 
 def run(mode):
-    ex = sdist.SpatialExchange(sim, LEVEL, owners, capacity_points=B, depth=DEPTH, mode=mode, device=dev)
+    overlap = mode.endswith("_overlap")          # send group g+1 before inserting group g (dist.py: send_group / wait_group)
+    ex = sdist.SpatialExchange(sim, LEVEL, owners, capacity_points=B, depth=DEPTH, mode=mode.replace("_overlap", ""), device=dev)
     best = None
     for rep in range(3):
         sim.reset()
@@ -74,9 +75,17 @@ def run(mode):
         for w0 in range(0, K, 32):                   # plan a window of steps: their counts travel in one all_gather
             ex.prepare([(src + i * B * 16, B) for i in range(w0, min(K, w0 + 32))])
         t_prep = time.perf_counter() - t0
-        for g0 in range(0, K, DEPTH):
+        groups = [[(src + i * B * 16, B) for i in range(g0, min(K, g0 + DEPTH))] for g0 in range(0, K, DEPTH)]
+        if overlap:
+            ex.send_group(groups[0])
+        for gi, group in enumerate(groups):
             a = time.perf_counter()
-            ptr, n = ex.exchange_group([(src + i * B * 16, B) for i in range(g0, min(K, g0 + DEPTH))])
+            if overlap:
+                ptr, n = ex.wait_group()
+                if gi + 1 < len(groups):
+                    ex.send_group(groups[gi + 1])
+            else:
+                ptr, n = ex.exchange_group(group)
             b = time.perf_counter()
             if n:
                 kms, _ = sim.insert_device(ptr, n)
@@ -131,7 +140,7 @@ def rebuild_locally():
 
 
 want_canon, want_stats = rebuild_locally()
-for mode in ("nccl", "p2p"):
+for mode in ("nccl", "p2p", "p2p_overlap"):
     try:
         r, canon, st = run(mode)
         diffs = oracle.compare_canon(canon, want_canon, mode) + oracle.compare_stats(st, want_stats)

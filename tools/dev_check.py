@@ -132,6 +132,7 @@ for K in sizes:
             sub = sim.memcpy_dtoh(sim.buffers().momentary + 800, 128).view(np.uint64).astype(np.float64)
             if best is None or kms < best[0]:
                 best = (kms, tms, ph, sub)
+                hist = sim.memcpy_dtoh(sim.buffers().momentary + 1008, 12 * 32).view(np.uint64).reshape(12, 4)
         kms, tms, ph, sub = best
         vb = sim.memcpy_dtoh(sim.buffers().momentary + 64, 32).view(np.uint64)
         print("terrain %dM [%s]: kernel %.3f ms = %.0f Mpts/s, total %.3f ms = %.0f Mpts/s | voxels fresh/rewalk %d/%d spilled %d | nodes %d"
@@ -139,6 +140,11 @@ for K in sizes:
         if ph.sum() > 0:
             print("   us/batch %s | rounds/batch %.2f" % ({k: round(float(v) / 1e3 / K, 1) for k, v in zip(PHASES, ph) if k != "rounds(count)"}, ph[6] / K), flush=True)
             print("   block 0 timeline, us/batch:", {k: round(float(v) / 1e3 / K, 1) for k, v in zip(SUBS, sub)}, flush=True)
+            for cls in range(12):
+                r_, ns, li, sp = [int(x) for x in hist[cls]]
+                if r_:
+                    print("   rounds moving < %8d items: %5d rounds, %7.1f us each (split + re-walk), listed %8.0f + spilled %8.0f items per round, %5.1f %% of the round time"
+                          % (1 << (2 * cls + 1), r_, ns / r_ / 1e3, li / r_, sp / r_, 100.0 * ns / max(1, int(hist[:, 1].sum()))), flush=True)
         if timed is None:
             break
     sim.use_module(0, None)

@@ -26,6 +26,10 @@ KNOBS = {
     "occ5": ["-DSIMLOD_BLOCKS_PER_SM=5"],
     "occ3_t2": ["-DSIMLOD_BLOCKS_PER_SM=3", "-DSIMLOD_TIMERS=2"],
     "tile256": ["-DSIMLOD_TILE_POINTS=256"],
+    "rwdedup": ["-DSIMLOD_REWALK_DEDUP=1"],
+    "rwl2": ["-DSIMLOD_REWALK_L2TEST=1"],
+    "rwdedup_t2": ["-DSIMLOD_REWALK_DEDUP=1", "-DSIMLOD_TIMERS=2"],
+    "rwdedup_l2": ["-DSIMLOD_REWALK_DEDUP=1", "-DSIMLOD_REWALK_L2TEST=1"],
     "tile1024": ["-DSIMLOD_TILE_POINTS=1024"],
 }
 only = [a for a in sys.argv[1:] if not a.isdigit()]
@@ -56,7 +60,7 @@ sim.set_box((0, 0, 0), data.TERRAIN_EXTENT)
 dptr = sim.device_alloc(n * 16)
 sim.generate(sim.GEN_TERRAIN, dptr, n, 0, n, 7)
 PHASES = ["fused", "split", "rewalk", "deferred", "final_alloc", "final_insert", "rounds(count)", "prologue"]
-SUBS = ["f.alloc", "f.count", "f.wait", "f.flush", "f.insert", "f.barrier", "s.work", "s.barrier", "r.items", "r.flush", "r.barrier"]
+SUBS = ["f.alloc", "f.count", "f.wait", "f.flush", "f.insert", "f.barrier", "s.work", "s.barrier", "r.items", "r.flush", "r.barrier", "f.top", "r.setup", "r.listed", "r.spilled"]
 
 
 def full_build(module):
@@ -67,7 +71,7 @@ def full_build(module):
         kms, tms = sim.insert_device(dptr, n)
         if best is None or kms < best[0]:
             ph = sim.memcpy_dtoh(sim.buffers().momentary + 96, 64).view(np.uint64).astype(np.float64)
-            sub = sim.memcpy_dtoh(sim.buffers().momentary + 800, 96).view(np.uint64).astype(np.float64)
+            sub = sim.memcpy_dtoh(sim.buffers().momentary + 800, 128).view(np.uint64).astype(np.float64)
             best = (kms, tms, ph, sub)
     st = sim.stats()
     canon = oracle.canon_from_image(*sim.download_octree())

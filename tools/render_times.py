@@ -21,7 +21,15 @@ sim.insert_device(dptr, n)
 mx = data.TERRAIN_EXTENT
 cams = [("autofocus+%d" % k, camera.autofocus(mx, 1920, 1080, yaw_offset=k * np.pi / 2)) for k in range(4)]
 cams += [("morro_bird", camera.orbit_camera(width=1920, height=1080, **camera.MORRO_BIRD)), ("morro_close", camera.orbit_camera(width=1920, height=1080, **camera.MORRO_CLOSE))]
-NAMES = ["clear|vis", "cut", "items", "draw", "stats+edl"]
+NAMES = ["clear|vis+cut", "-", "items", "draw", "stats+edl"]
+# the shipped kernel carries no timers: a -DSIMLOD_RENDER_TIMERS=1 build of the same source gives the per-phase picture
+import subprocess  # noqa: E402
+timed = os.path.join(ROOT, "tools", "exp", "render_timers.cubin")
+os.makedirs(os.path.dirname(timed), exist_ok=True)
+r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-cubin", "-DSIMLOD_RENDER_TIMERS=1", "-o", timed,
+                    os.path.join(ROOT, "simlod_b200", "csrc", "render.cu")], capture_output=True, text=True)
+if r.returncode != 0:
+    print("timers build failed:", r.stderr[-300:]); timed = None
 for hqs in (0, 1):
     sim.set_settings(useHighQualityShading=hqs)
     tot_s = tot_ms = tot_ref = 0.0
@@ -30,6 +38,8 @@ for hqs in (0, 1):
         cold = sim.render()
         ms = min(sim.render() for _ in range(5))
         s = sim.stats()
+        if timed:
+            sim.use_module(1, timed); sim.render(); sim.render(); sim.use_module(1, None)
         raw = sim.memcpy_dtoh(sim.buffers().renderbuffer, 96)
         c = raw[:48].view(np.uint32); ph = raw[48:88].view(np.uint64).astype(np.float64) / 1e3
         samples = s.numVisiblePoints + s.numVisibleVoxels
