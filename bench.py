@@ -435,7 +435,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bench_merged_octree(sim, dptr, nb_avail, rank, world, dev, barrier):
@@ -508,8 +508,28 @@ def bench_merged_octree(sim, dptr, nb_avail, rank, world, dev, barrier):
             "received_this_rank": int(received), "bit_exactness": "tests/test_merged_octree.py, tools/bench_merged.py (every rank's octree vs a local rebuild)"}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE line, the JSON result: whatever libraries print on fd 1 meanwhile (NCCL's version banner, a
+    device-side printf of the reference's reset kernel) goes to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    emit(line)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -736,7 +756,7 @@ def main():
             line["las_decode"] = las
         if stream:
             line["stream_file"] = stream
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
