@@ -524,7 +524,7 @@ def emit(line):
     sys.stdout.flush()
     if _REAL_STDOUT is not None:
         os.dup2(_REAL_STDOUT, 1)
-    emit(line)
+    print(json.dumps(line), flush=True)
 
 
 def main():
