@@ -11,7 +11,7 @@ for nb in (16, NB):
     path = "/dev/shm/probe_%d.simlod" % os.getpid()
     data.write_simlod(path, np.concatenate(batches[:nb]), mn, mx)
     sim = SimLOD(320, 176, persistent_bytes=max(4 << 30, nb * (220 << 20)))
-    for threads in (16, 32, 48):
+    for threads in (8, 16, 24, 32):
         best = 1e9
         for rep in range(3):
             t0 = time.perf_counter(); got, kms, tms = sim.insert_simlod_file(path, loader_threads=threads); dt = time.perf_counter() - t0
