@@ -947,59 +947,108 @@ __device__ __forceinline__ void passItems(const Ctx& c, const Batch& b, uint32_t
             // ---- (1) the items the split phase named (buildWorklist): batch points, and points spilled in earlier rounds. Each sits
             // in a leaf that was split in THIS round (that is how it got on the list), so the step down is the same as in (2):
             // the leaf's record gives the children and the only grid to sample
-            for (uint32_t base = rewalkFirstGranule(); base < numListed; base += rewalkGranuleStride()) {
-                const uint32_t u = base + laneId();
-                bool valid = u < numListed;
-                const uint32_t i = valid ? wl[u] : 0u;
-                const bool spilledItem = valid && i >= scratch::MAX_BATCH;
-                uint4 pt = make_uint4(0, 0, 0, 0);
-                uint32_t node = 0, level = 0, childBase = 0;
-                if (valid) {
-                    pt = spilledItem ? *reinterpret_cast<const uint4*>(c.spilled() + (i - scratch::MAX_BATCH)) : ldPoint(b.points + i);
-                    const uint32_t lp = leafOf[i];
-                    node = lp & 0xffffffu; level = lp >> 24;
-                    uint32_t k = 0;
-                    while (k < numSplit && sh_splitInfo[k].node != node) k++;
-                    if (k < numSplit) childBase = sh_splitInfo[k].childBase;
-                    else { valid = false; atomicOr(&c.ctl()->errorFlags, ERR_INTERNAL); }      // cannot happen: listed items sit in split leaves
-                    valid = valid && level < SIMLOD_MAX_DEPTH;               // a level-20 node is the leaf even after it "split" (voxels.cu:169)
+            // Both loops are software-pipelined: a granule's work is a chain of dependent loads (list entry -> leaf word and
+            // point -> grid word -> atomic), and a warp has only a handful of granules, so the list entry two granules ahead and
+            // the leaf word + point one granule ahead are in flight while a granule is processed. The grid of the split leaf comes
+            // from its record (no side-table load).
+            constexpr uint32_t NO_ITEM = 0xffffffffu;
+            auto sampleSplitLeaf = [&](uint64_t grid, const Coords& q, uint32_t color, uint32_t node, uint32_t level) {
+                if (!nested(q)) atomicOr(&c.ctl()->errorFlags, ERR_FAR_POINT);         // (as sampleUp flags it)
+                const uint32_t cell = cellAt(q, level);
+                uint32_t* word = reinterpret_cast<uint32_t*>(grid) + (cell >> 5);
+                const uint32_t bit = 1u << (cell & 31u);
+                const uint32_t seen = (UNCACHED_GRID || SIMLOD_REWALK_L2TEST) ? ldcg(word) : *word;
+                if ((seen & bit) == 0 && (atomicOr(word, bit) & bit) == 0) recordVoxel(c, b, node, cell, color);
+            };
+            {
+                const uint32_t stride = rewalkGranuleStride();
+                auto loadIndex = [&](uint32_t bs) { const uint32_t u = bs + laneId(); return (bs < numListed && u < numListed) ? wl[u] : NO_ITEM; };
+                auto loadItem = [&](uint32_t i, uint32_t& lp, uint4& pt) {
+                    lp = 0; pt = make_uint4(0, 0, 0, 0);
+                    if (i != NO_ITEM) {
+                        pt = i >= scratch::MAX_BATCH ? *reinterpret_cast<const uint4*>(c.spilled() + (i - scratch::MAX_BATCH)) : ldPoint(b.points + i);
+                        lp = leafOf[i];
+                    }
+                };
+                uint32_t base = rewalkFirstGranule();
+                uint32_t iCur = loadIndex(base), iNext = loadIndex(base + stride);
+                uint32_t lpCur; uint4 ptCur;
+                loadItem(iCur, lpCur, ptCur);
+                for (; base < numListed; base += stride) {
+                    uint32_t lpNext; uint4 ptNext;
+                    loadItem(iNext, lpNext, ptNext);                                   // granule base + stride
+                    const uint32_t iNext2 = loadIndex(base + 2u * stride);
+                    const uint32_t i = iCur;
+                    const uint4 pt = ptCur;
+                    bool valid = i != NO_ITEM;
+                    const bool spilledItem = valid && i >= scratch::MAX_BATCH;
+                    uint32_t node = 0, level = 0, childBase = 0;
+                    uint64_t grid = 0;
+                    if (valid) {
+                        node = lpCur & 0xffffffu; level = lpCur >> 24;
+                        uint32_t k = 0;
+                        while (k < numSplit && sh_splitInfo[k].node != node) k++;
+                        if (k < numSplit) { childBase = sh_splitInfo[k].childBase; grid = sh_splitInfo[k].grid; }
+                        else { valid = false; atomicOr(&c.ctl()->errorFlags, ERR_INTERNAL); }      // cannot happen: listed items sit in split leaves
+                        valid = valid && level < SIMLOD_MAX_DEPTH;               // a level-20 node is the leaf even after it "split" (voxels.cu:169)
+                    }
+                    if (__any_sync(0xffffffffu, valid)) {
+                        bool forceGlobal;
+                        const uint32_t myk = reserve(valid, forceGlobal);
+                        const Coords q = quantize(c, pt);
+                        const uint32_t child = childBase + childIndexAt(q, level);
+                        if (SAMPLE && valid) sampleSplitLeaf(grid, q, pt.w, node, level);
+                        __syncwarp();
+                        uint32_t slot = 0;
+                        if (COUNT) slot = countInto<true>(c, b, valid, child, level + 1, valid && !spilledItem ? c.runBloom() + (i / perRun) * BLOOM_WORDS : nullptr, forceGlobal);
+                        if (valid && COUNT) remember(i, child | ((level + 1) << 24), slot, myk, forceGlobal);
+                    }
+                    iCur = iNext; lpCur = lpNext; ptCur = ptNext; iNext = iNext2;
                 }
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                bool forceGlobal;
-                const uint32_t myk = reserve(valid, forceGlobal);
-                const Coords q = quantize(c, pt);
-                const uint32_t child = childBase + childIndexAt(q, level);
-                if (SAMPLE && valid) sampleUp<UNCACHED_GRID || SIMLOD_REWALK_L2TEST, SIMLOD_REWALK_DEDUP>(c, b, q, pt.w, node, level, level);
-                __syncwarp();
-                uint32_t slot = 0;
-                if (COUNT) slot = countInto<true>(c, b, valid, child, level + 1, valid && !spilledItem ? c.runBloom() + (i / perRun) * BLOOM_WORDS : nullptr, forceGlobal);
-                if (valid && COUNT) remember(i, child | ((level + 1) << 24), slot, myk, forceGlobal);
             }
             RW_DONE(13);
             // ---- (2) the points spilled in this round, leaf by leaf: a warp's 32 points come out of ONE split leaf, whose
             // record (children, grid, level) is in shared memory — no leaf look-up, no descent: the child is one step down,
             // the only grid on the way is the leaf's own fresh one
-            const uint32_t numGranules = sh_splitGranule[numSplit];
-            for (uint32_t g = rewalkFirstGranule() / 32u; g < numGranules; g += rewalkGranuleStride() / 32u) {
-                uint32_t lo = 0, hi = numSplit;                          // last split with first granule <= g
-                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh_splitGranule[mid] <= g) lo = mid; else hi = mid; }
-                const uint32_t node = sh_splitInfo[lo].node, level = sh_splitInfo[lo].level, childBase = sh_splitInfo[lo].childBase;
-                const uint32_t within = (g - sh_splitGranule[lo]) * 32u + laneId();
-                bool valid = within < sh_splitInfo[lo].stored && level < SIMLOD_MAX_DEPTH;
-                const uint32_t j = sh_splitInfo[lo].base + within;
-                const uint32_t i = (uint32_t)scratch::MAX_BATCH + j;
-                uint4 pt = make_uint4(0, 0, 0, 0);
-                if (valid) pt = *reinterpret_cast<const uint4*>(c.spilled() + j);
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                bool forceGlobal;
-                const uint32_t myk = reserve(valid, forceGlobal);
-                const Coords q = quantize(c, pt);
-                const uint32_t child = childBase + childIndexAt(q, level);
-                if (SAMPLE && valid) sampleUp<UNCACHED_GRID || SIMLOD_REWALK_L2TEST, SIMLOD_REWALK_DEDUP>(c, b, q, pt.w, node, level, level);
-                __syncwarp();
-                uint32_t slot = 0;
-                if (COUNT) slot = countInto(c, b, valid, child, level + 1, nullptr, forceGlobal);
-                if (valid && COUNT) remember(i, child | ((level + 1) << 24), slot, myk, forceGlobal);
+            {
+                const uint32_t numGranules = sh_splitGranule[numSplit];
+                const uint32_t gStride = rewalkGranuleStride() / 32u;
+                struct Granule { uint32_t lo, j; bool valid; };
+                auto locate = [&](uint32_t g) {
+                    Granule r; r.lo = 0; r.j = 0; r.valid = false;
+                    if (g < numGranules) {
+                        uint32_t lo = 0, hi = numSplit;                      // last split with first granule <= g
+                        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh_splitGranule[mid] <= g) lo = mid; else hi = mid; }
+                        const uint32_t within = (g - sh_splitGranule[lo]) * 32u + laneId();
+                        r.lo = lo; r.j = sh_splitInfo[lo].base + within;
+                        r.valid = within < sh_splitInfo[lo].stored && sh_splitInfo[lo].level < SIMLOD_MAX_DEPTH;
+                    }
+                    return r;
+                };
+                auto loadSpilled = [&](const Granule& gr) { return gr.valid ? *reinterpret_cast<const uint4*>(c.spilled() + gr.j) : make_uint4(0, 0, 0, 0); };
+                uint32_t g = rewalkFirstGranule() / 32u;
+                Granule cur = locate(g);
+                uint4 ptCur = loadSpilled(cur);
+                for (; g < numGranules; g += gStride) {
+                    const Granule next = locate(g + gStride);
+                    const uint4 ptNext = loadSpilled(next);
+                    const bool valid = cur.valid;
+                    if (__any_sync(0xffffffffu, valid)) {
+                        const uint32_t node = sh_splitInfo[cur.lo].node, level = sh_splitInfo[cur.lo].level, childBase = sh_splitInfo[cur.lo].childBase;
+                        const uint32_t i = (uint32_t)scratch::MAX_BATCH + cur.j;
+                        const uint4 pt = ptCur;
+                        bool forceGlobal;
+                        const uint32_t myk = reserve(valid, forceGlobal);
+                        const Coords q = quantize(c, pt);
+                        const uint32_t child = childBase + childIndexAt(q, level);
+                        if (SAMPLE && valid) sampleSplitLeaf(sh_splitInfo[cur.lo].grid, q, pt.w, node, level);
+                        __syncwarp();
+                        uint32_t slot = 0;
+                        if (COUNT) slot = countInto(c, b, valid, child, level + 1, nullptr, forceGlobal);
+                        if (valid && COUNT) remember(i, child | ((level + 1) << 24), slot, myk, forceGlobal);
+                    }
+                    cur = next; ptCur = ptNext;
+                }
             }
             RW_DONE(14);
         } else {

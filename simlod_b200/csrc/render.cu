@@ -335,22 +335,67 @@ __device__ void emitVisible(const EmitCtx& e, const uint32_t* visList, uint32_t 
     for (uint32_t v = warp; v < numVisible; v += numWarps) emitNode(e, &e.nodes[visList[v]]);
 }
 
-// one pass over the frame's items: persistent warps pop chunk items with a single atomicAdd each.
+// one pass over the frame's items: every warp starts with the item of its own number (no atomic: 4 736 warps popping the
+// same counter at the same instant serialise for 10-20 us, a third of a small frame), then persistent warps pop the rest
+// with a single atomicAdd each; a frame with no more items than warps touches the counter not at all.
 // (Measured and rejected, profiles/r02/render_notes.md: quarter-chunk items, 2 / 4 warps per item on small frames, the next
 // pop prefetched under the current item, four sample loads in flight per lane — each within 3 % of this loop or slower.)
 template <typename F>
 __device__ __forceinline__ void forEachSample(const uint8_t* heapBase, const WorkItem* items, uint32_t numItems, uint32_t* head, F&& f) {
     const uint32_t lane = laneId();
-    for (;;) {
-        uint32_t it = 0;
-        if (lane == 0) it = atomicAdd(head, 1u);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= numItems) break;
+    const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t it = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;       // neighbouring items (chunks of one node) go to different SMs
+    while (it < numItems) {
         WorkItem w = items[it];
-        if (w == ITEM_EMPTY || w == 0) continue;
-        const uint4* pts = itemSamples(heapBase, w);
-        const uint32_t count = itemCount(w), level = itemLevel(w), colorId = itemColorId(w);
-        for (uint32_t i = lane; i < count; i += 32) f(pts[i], level, colorId);
+        if (w != ITEM_EMPTY && w != 0) {
+            const uint4* pts = itemSamples(heapBase, w);
+            const uint32_t count = itemCount(w), level = itemLevel(w), colorId = itemColorId(w);
+            for (uint32_t i = lane; i < count; i += 32) f(pts[i], level, colorId);
+        }
+        if (numItems <= numWarps) break;
+        uint32_t nx = 0;
+        if (lane == 0) nx = atomicAdd(head, 1u);
+        it = numWarps + __shfl_sync(0xffffffffu, nx, 0);
+    }
+}
+
+// The same walk for passes whose per-sample work is "compute a pixel, look at it, maybe update it" with one pixel per
+// sample (pointSize 1): ILP samples of a lane are in flight together — their 16-byte loads first, then their framebuffer
+// probes — instead of one dependent load chain per sample. A small frame has fewer items than warps, so its draw time IS
+// that chain: 1000 samples / 32 lanes = 32 trips of (sample load + probe) per warp.
+#ifndef SIMLOD_DRAW_ILP
+#define SIMLOD_DRAW_ILP 8              // tuning knob (tools/render_times.py --flags)
+#endif
+template <typename Prep, typename Probe, typename Commit>
+__device__ __forceinline__ void forEachSampleStaged(const uint8_t* heapBase, const WorkItem* items, uint32_t numItems, uint32_t* head,
+                                                    Prep&& prep, Probe&& probe, Commit&& commit) {
+    constexpr int ILP = SIMLOD_DRAW_ILP;
+    const uint32_t lane = laneId();
+    const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t it = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    while (it < numItems) {
+        WorkItem w = items[it];
+        if (w != ITEM_EMPTY && w != 0) {
+            const uint4* pts = itemSamples(heapBase, w);
+            const uint32_t count = itemCount(w), level = itemLevel(w), colorId = itemColorId(w);
+            for (uint32_t i0 = lane; i0 < count; i0 += 32 * ILP) {
+                uint4 p[ILP];
+                uint32_t pixel[ILP];
+                uint64_t value[ILP], seen[ILP];
+#pragma unroll
+                for (int u = 0; u < ILP; u++) { const uint32_t i = i0 + 32u * u; p[u] = i < count ? pts[i] : make_uint4(0, 0, 0, 0); }
+#pragma unroll
+                for (int u = 0; u < ILP; u++) { pixel[u] = 0xffffffffu; value[u] = 0; if (i0 + 32u * u < count) prep(p[u], level, colorId, pixel[u], value[u]); }
+#pragma unroll
+                for (int u = 0; u < ILP; u++) seen[u] = pixel[u] != 0xffffffffu ? probe(pixel[u]) : 0ull;
+#pragma unroll
+                for (int u = 0; u < ILP; u++) if (pixel[u] != 0xffffffffu) commit(pixel[u], value[u], seen[u]);
+            }
+        }
+        if (numItems <= numWarps) break;
+        uint32_t nx = 0;
+        if (lane == 0) nx = atomicAdd(head, 1u);
+        it = numWarps + __shfl_sync(0xffffffffu, nx, 0);
     }
 }
 
@@ -484,7 +529,21 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
     const int pointSize = uniforms.pointSize;
     const uint8_t* heapBase = ec.heapBase;
 
-    if (uniforms.showPoints && !hqs) {
+    if (uniforms.showPoints && !hqs && pointSize == 1) {
+        // single pass, one pixel per sample: depth|colour packed in 64 bits, atomicMin (render.cu:61-104,161-210)
+        forEachSampleStaged(heapBase, items, numItems, &ctl->head[0],
+            [&](uint4 p, uint32_t level, uint32_t colorId, uint32_t& pixel, uint64_t& value) {
+                Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
+                if (!pr.inside) return;
+                value = ((uint64_t)__float_as_uint(pr.depth) << 32) | sampleColor(uniforms, p.w, level, colorId);
+                uint32_t qx = (uint32_t)max(0, min(pr.x, width)), qy = (uint32_t)max(0, min(pr.y, height));      // (render.cu:91-92)
+                pixel = qx + (uint32_t)width * qy;
+            },
+            [&](uint32_t pixel) { return framebuffer[pixel]; },
+            [&](uint32_t pixel, uint64_t value, uint64_t seen) {
+                if (value < seen) atomicMin(reinterpret_cast<unsigned long long*>(&framebuffer[pixel]), (unsigned long long)value);
+            });
+    } else if (uniforms.showPoints && !hqs) {
         // single pass: depth|colour packed in 64 bits, atomicMin (render.cu:61-104,161-210)
         forEachSample(heapBase, items, numItems, &ctl->head[0], [&](uint4 p, uint32_t level, uint32_t colorId) {
             Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
@@ -498,6 +557,37 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
                 if (encoded < framebuffer[pixelID]) atomicMin(reinterpret_cast<unsigned long long*>(&framebuffer[pixelID]), (unsigned long long)encoded);
             }
         });
+    } else if (uniforms.showPoints && hqs && pointSize == 1) {
+        // the two HQS passes with one pixel per sample, staged like the single pass above
+        auto prepHqs = [&](uint4 p, uint32_t level, uint32_t colorId, uint32_t& pixel, uint64_t& value) {
+            Projected pr = project(T, uniforms.width, uniforms.height, __uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z));
+            if (!pr.inside || !(pr.depth > 0.0f)) return;
+            value = ((uint64_t)__float_as_uint(pr.depth) << 32) | sampleColor(uniforms, p.w, level, colorId);
+            uint32_t qx = (uint32_t)max(0, min(pr.x, width)), qy = (uint32_t)max(0, min(pr.y, height));
+            pixel = qx + (uint32_t)width * qy;
+        };
+        auto probeDepth = [&](uint32_t pixel) { return (uint64_t)fb_depth[pixel]; };
+        // pass 1: closest depth per pixel (render.cu:247-391)
+        forEachSampleStaged(heapBase, items, numItems, &ctl->head[1], prepHqs, probeDepth,
+            [&](uint32_t pixel, uint64_t value, uint64_t seen) {
+                const uint32_t udepth = (uint32_t)(value >> 32);
+                if (udepth < (uint32_t)seen) atomicMin(&fb_depth[pixel], udepth);
+            });
+        grid.sync();
+        // pass 2: accumulate colours of samples within 1 % of the closest depth (render.cu:406-602)
+        forEachSampleStaged(heapBase, items, numItems, &ctl->head[2], prepHqs, probeDepth,
+            [&](uint32_t pixel, uint64_t value, uint64_t seen) {
+                const float depth = __uint_as_float((uint32_t)(value >> 32)), fbDepth = __uint_as_float((uint32_t)seen);
+                const uint32_t color = (uint32_t)value;
+                if (depth < fpx::mul(fbDepth, 1.01f)) {
+                    // the four 32-bit sums {R, G, B, n} of render.cu:560-580 as two 64-bit adds on the same 16 bytes: a low half
+                    // cannot carry into the high one (255 x samples per pixel < 2^32)
+                    unsigned long long* acc = reinterpret_cast<unsigned long long*>(&fb_color[4 * pixel]);
+                    atomicAdd(acc + 0, (unsigned long long)(color & 0xffu) | ((unsigned long long)((color >> 8) & 0xffu) << 32));
+                    atomicAdd(acc + 1, (unsigned long long)((color >> 16) & 0xffu) | (1ull << 32));
+                }
+            });
+        grid.sync();
     } else if (uniforms.showPoints && hqs) {
         // pass 1: closest depth per pixel (render.cu:247-391)
         forEachSample(heapBase, items, numItems, &ctl->head[1], [&](uint4 p, uint32_t level, uint32_t colorId) {
@@ -533,6 +623,8 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
             }
         });
         grid.sync();
+    }
+    if (uniforms.showPoints && hqs) {
         // resolve (render.cu:606-632)
         for (uint32_t i = gtid; i < numPixels; i += gstride) {
             uint4 acc = reinterpret_cast<const uint4*>(fb_color)[i];

@@ -10,7 +10,8 @@ sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 from simlod_b200 import SimLOD, camera, data  # noqa: E402
 
-K = int(sys.argv[1]) if len(sys.argv) > 1 else 36
+K = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 36
+VARIANTS = [a for a in sys.argv[1:] if a.endswith(".cubin")]          # extra render cubins to time beside the shipped one
 n = K * 1_000_000
 sim = SimLOD(1920, 1080, persistent_bytes=max(4 << 30, K * (60 << 20)))
 sim.set_box((0, 0, 0), data.TERRAIN_EXTENT)
@@ -33,6 +34,7 @@ if r.returncode != 0:
 for hqs in (0, 1):
     sim.set_settings(useHighQualityShading=hqs)
     tot_s = tot_ms = tot_ref = 0.0
+    var_ms = {}
     for name, (view, proj) in cams:
         sim.set_camera(view, proj)
         cold = sim.render()
@@ -46,9 +48,14 @@ for hqs in (0, 1):
         ref = None
         if os.path.exists(oracle.REF_CUBINS[1]):
             sim.use_module(1, oracle.REF_CUBINS[1]); sim.render(); ref = min(sim.render() for _ in range(3)); sim.use_module(1, None)
+        extra = ""
+        for v in VARIANTS:
+            sim.use_module(1, v); sim.render(); extra += " | %s %.4f" % (os.path.basename(v), min(sim.render() for _ in range(5))); sim.use_module(1, None)
+            var_ms[v] = var_ms.get(v, 0.0) + float(extra.rsplit(" ", 1)[1])
         print("hqs %d %-12s cold %.3f warm %.4f ms (ref %s) | %d nodes %d items %.2f M samples %.1f Gs/s | cache hits/walks %d/%d | us %s" % (
             hqs, name, cold, ms, "%.4f" % ref if ref else "-", s.numVisibleNodes, int(c[0]), samples / 1e6, samples / ms / 1e6, int(c[10]), int(c[11]),
-            {k: round(float(v), 1) for k, v in zip(NAMES, ph)}), flush=True)
+            {k: round(float(v), 1) for k, v in zip(NAMES, ph)}) + extra, flush=True)
         tot_s += samples; tot_ms += ms; tot_ref += ref or 0.0
-    print("hqs %d aggregate %.1f Gsamples/s (reference kernel %.1f)" % (hqs, tot_s / tot_ms / 1e6, tot_s / tot_ref / 1e6 if tot_ref else 0.0), flush=True)
+    print("hqs %d aggregate %.1f Gsamples/s (reference kernel %.1f)" % (hqs, tot_s / tot_ms / 1e6, tot_s / tot_ref / 1e6 if tot_ref else 0.0),
+          {os.path.basename(v): round(tot_s / m / 1e6, 1) for v, m in var_ms.items()}, flush=True)
 sim.close()
