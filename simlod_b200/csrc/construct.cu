@@ -722,11 +722,8 @@ __device__ __forceinline__ void walk(const Ctx& c, const Batch& b, LeafCache& ca
 // walks the current one, so the HBM latency of the batch read leaves the critical path and no
 // registers or LSU slots are spent on it. Threads then read their point with one LDS.128.
 // ------------------------------------------------------------------------------------------
-#ifndef SIMLOD_REWALK_DEDUP
-#define SIMLOD_REWALK_DEDUP 0          // tuning knobs (tools/exp_variants.py): one atomicOr per distinct cell among a warp's re-walked items;
-#endif
 #ifndef SIMLOD_REWALK_L2TEST
-#define SIMLOD_REWALK_L2TEST 0         // pre-test the freshly cleared grids of a re-walk through L2 instead of L1
+#define SIMLOD_REWALK_L2TEST 0         // tuning knob (tools/exp_variants.py): pre-test the freshly cleared grids of a re-walk through L2 instead of L1
 #endif
 #ifndef SIMLOD_TILE_POINTS
 #define SIMLOD_TILE_POINTS 512         // tuning knob: a multiple of 256

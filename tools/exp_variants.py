@@ -26,10 +26,7 @@ KNOBS = {
     "occ5": ["-DSIMLOD_BLOCKS_PER_SM=5"],
     "occ3_t2": ["-DSIMLOD_BLOCKS_PER_SM=3", "-DSIMLOD_TIMERS=2"],
     "tile256": ["-DSIMLOD_TILE_POINTS=256"],
-    "rwdedup": ["-DSIMLOD_REWALK_DEDUP=1"],
     "rwl2": ["-DSIMLOD_REWALK_L2TEST=1"],
-    "rwdedup_t2": ["-DSIMLOD_REWALK_DEDUP=1", "-DSIMLOD_TIMERS=2"],
-    "rwdedup_l2": ["-DSIMLOD_REWALK_DEDUP=1", "-DSIMLOD_REWALK_L2TEST=1"],
     "tile1024": ["-DSIMLOD_TILE_POINTS=1024"],
 }
 only = [a for a in sys.argv[1:] if not a.isdigit()]
@@ -80,7 +77,7 @@ def full_build(module):
 
 (base_ms, _, _, _), base_stats, base_canon = full_build(None)
 print("shipped kernel: %.3f ms for %d batches = %.0f Mpoints/s kernel-only, grid %d" % (base_ms, K, n / base_ms / 1e3, sim.launch_info()["construct_blocks"]), flush=True)
-for v in sorted(glob.glob(os.path.join(EXP, "*.cubin"))):
+for v in sorted(glob.glob(os.path.join(EXP, "knob_*.cubin")) + glob.glob(os.path.join(EXP, "construct_*.cubin"))):
     label = os.path.basename(v)
     try:
         (ms, tms, ph, sub), st, canon = full_build(v)
