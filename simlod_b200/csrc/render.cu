@@ -658,8 +658,11 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
         const uint32_t numTilesX = (uint32_t)width / tileSize, numTilesY = (uint32_t)height / tileSize;
         const uint32_t numTiles = numTilesX * numTilesY;
         const uint32_t tilesPerBlock = numTiles / gridDim.x;
+#ifndef SIMLOD_EDL_SYNC
+#define SIMLOD_EDL_SYNC 1              // tuning knob: the reference's two block barriers per tile (nothing here needs them)
+#endif
         for (uint32_t i = 0; i < tilesPerBlock; i++) {
-            __syncthreads();
+            if (SIMLOD_EDL_SYNC) __syncthreads();
             int tileID = (int)(i * gridDim.x + blockIdx.x);
             int tileX = tileID % (int)numTilesX, tileY = tileID / (int)numTilesX;
             int tileStart = tileX * (int)tileSize + tileY * width * (int)tileSize;
@@ -687,7 +690,7 @@ kernel_render(uint32_t* buffer, const Uniforms uniforms, Node* nodes, cudaSurfac
             fbp[pixelID].color = shaded;
             // colour -> RGBA8 surface (render.cu:1334-1343), fused: EDL only ever reads neighbours' depths
             surf2Dwrite(shaded, gl_colorbuffer, (pixelID % width) * 4, pixelID / width);
-            __syncthreads();
+            if (SIMLOD_EDL_SYNC) __syncthreads();
         }
         // pixels outside the tiles the EDL pass covers keep their raw colour
         const uint32_t tilesCovered = tilesPerBlock * gridDim.x;
