@@ -136,6 +136,28 @@ def exchange_layout(matrix, rank):
     return send_offsets, landing_offsets, int(m[:, rank].sum())
 
 
+EXCHANGE_REGIONS = 3        # receive regions of SpatialExchange, used in turn (group g lands in region g % 3)
+
+
+def pipeline_ops(num_groups, ahead=True):
+    """The order in which a rank issues the steps of a merged-octree build (bench.py: bench_merged_octree,
+    tools/bench_merged.py): ("send", g) enqueues the scatters of group g, ("wait", g) blocks until every sender's
+    group g has arrived here, ("insert", g) builds it into the octree (blocking). `ahead`: group g+1 is sent before
+    group g is inserted, so that the peers' stores land while this rank's SMs are busy; otherwise send, wait, insert
+    one group at a time. tests/test_merged_octree.py checks this order against the region rule by simulation."""
+    ops = []
+    if ahead and num_groups > 0:
+        ops.append(("send", 0))
+    for g in range(num_groups):
+        if not ahead:
+            ops.append(("send", g))
+        ops.append(("wait", g))
+        if ahead and g + 1 < num_groups:
+            ops.append(("send", g + 1))
+        ops.append(("insert", g))
+    return ops
+
+
 def gather_counts(my_counts, device="cpu"):
     """all_gather of the per-destination counts: the G x G matrix of this step (same on every rank)."""
     import torch
@@ -192,7 +214,7 @@ class SpatialExchange:
         self.capacity, self.depth = int(capacity_points), int(depth)
         region = self.depth * self.world * self.capacity * 16  # worst case: every sender's whole group lands here
         self.region_bytes = region
-        self.regions = 3
+        self.regions = EXCHANGE_REGIONS
         self.pending = []                                      # groups sent but not yet acquired: (base, points arriving here, last step)
         self.step = 0                                          # batches sent so far = value of my flag in every receiver
         self.group = 0
