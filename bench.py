@@ -15,11 +15,13 @@ With N > 1 every rank owns a complete builder and inserts its own 350 M-point sc
 (tile g of a survey of N tiles): per-GPU work is identical to N = 1, scaling is weak, and there is no data-path
 collective (NCCL carries barrier / max-time / stats reductions only). BASELINE.json configs[3] as SURVEY.md §8d defines
 it — ONE sphere shell of N x 250 M points, rank g inserts the batches b = g (mod N) — is measured next to it and reported
-under `config4`.
+under `config4`; ONE octree over the N GPUs (spatial exchange over NVLink peer memory) under
+`merged_octree`.
 
 Numbers:
   value        Mpoints/s, all ranks' points / max-over-ranks median device time of a pass, batches already resident
-               in HBM (device-to-device copies into the 50-slot ring are inside the timed region)
+               in HBM and consumed in place (simlod_insert_device maps the 50-slot ring window onto the caller's buffer;
+               all launch gaps are inside the timed region)
   e2e          same metric through the public API from pinned HOST memory: per step one 16 MB host->device copy
                and one 112-byte Stats read-back per launch inside the timed region
   roofline     kernel_construct: algorithmic bytes (16 in + 16 out + 32*s + 16*v per point)
