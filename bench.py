@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--passes", type=int, default=5, help="timed passes over the whole stream (median reported)")
     ap.add_argument("--batches", type=int, default=CONFIG3_BATCHES, help="developer knob: batches of the stream (350 = config 3)")
-    ap.add_argument("--cpu-sample-batches", type=int, default=8)
+    ap.add_argument("--cpu-sample-batches", type=int, default=16, help="batches of the stream the 1-thread CPU oracle inserts for cpu_baseline (about 6-10 s)")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the LAS / file-streamer / config-4 legs")
